@@ -1,0 +1,198 @@
+/*
+ * longbow_b200.h -- C ABI of liblongbow_b200.so, the B200-native (sm_100a) replacement for
+ * Longbow's vector-distance / k-NN hot path.
+ *
+ * Plain pointers and sizes only; no C++/torch types.  This is exactly what the reference's
+ * cgo layer binds (see INTEGRATION.md for the Go stubs).  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - Return value: 0 = success (internal/gpu/faiss_gpu.go:99-101,134-137 treats non-zero as
+ *     "failed with code %d").  Non-zero codes are the LB_ERR_* values below and are stable.
+ *     Constructors that return a pointer return NULL on failure (faiss_gpu.go:57-66).
+ *   - No CPU fallback: if there is no usable CUDA device the call fails with a code.
+ *   - Host entry points are synchronous: inputs are fully consumed (copied to the device)
+ *     and outputs fully written before they return, so the caller (Go) may free or move its
+ *     slices immediately (cgo pointer rules).  They are thread-safe: any number of threads may
+ *     search one handle concurrently (faiss_gpu.go:40,108 takes a read lock); add / free /
+ *     set_* need exclusive access, as the reference's write lock provides.
+ *   - *_device entry points take device pointers plus a cudaStream_t (as void*), enqueue work
+ *     on that stream and return without synchronising.
+ *   - Labels are 0-based insertion positions (the ids passed to gpu.Index.Add never reach C,
+ *     faiss_gpu.go:93-97) plus the handle's id_base, as int64.  Missing results: label -1,
+ *     distance FLT_MAX.
+ *   - Distances are the reference's simd values: sqrt'd Euclidean
+ *     (internal/simd/distance_functions.go:17-31), 1 - cosine similarity (:47-55), and the
+ *     NEGATED dot product (internal/store/distance_resolvers.go:11-16; docs/distance_metrics.md:42-55).
+ *     Results are ordered by (distance, label) ascending.
+ *   - Bitmaps are dense, little-endian 64-bit words, bit i <-> row (VectorID) i.
+ *       tombstones: bit set = deleted (internal/store/arrow_hnsw.go:147,468-472)
+ *       allow:      bit set = passes the predicate (internal/query/bitmap.go:13-120)
+ */
+#ifndef LONGBOW_B200_H
+#define LONGBOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB_OK 0
+#define LB_ERR_INVALID 1     /* bad argument (NULL handle, k <= 0, size mismatch ...) */
+#define LB_ERR_CUDA 2        /* CUDA runtime/driver error; text via lb_last_error() */
+#define LB_ERR_OOM 3         /* device or host allocation failed */
+#define LB_ERR_UNSUPPORTED 4 /* no kernel for this (metric, dtype): registry miss, dispatch.go:275-278 */
+#define LB_ERR_STATE 5       /* handle not in the required state (e.g. PQ without codes) */
+#define LB_ERR_NO_DEVICE 6   /* no CUDA device / device id out of range */
+
+/* internal/simd/registry.go:8-14 */
+enum lb_metric { LB_METRIC_L2 = 0, LB_METRIC_COSINE = 1, LB_METRIC_DOT = 2 };
+/* internal/simd/registry.go:31-47 (first four) */
+enum lb_dtype { LB_F32 = 0, LB_F16 = 1, LB_I8 = 2, LB_U8 = 3 };
+
+/* Thread-local text of the last failure on the calling thread ("" if none). */
+const char *lb_last_error(void);
+/* Library / device info: SM count, device name; returns LB_ERR_NO_DEVICE without a GPU. */
+int lb_device_info(int device, int *sm_count, size_t *total_mem, char *name, size_t name_len);
+
+/* ------------------------------------------------------------------------------------------
+ * 1. The six symbols internal/gpu/faiss_gpu.go:16-21 declares and links today.
+ *    fp32, Euclidean (sqrt'd, matching simd.EuclideanDistance and the Metal backends,
+ *    internal/gpu/metal_gpu.go:104), labels = insertion positions.
+ * ---------------------------------------------------------------------------------------- */
+void *faiss_gpu_resources_new(int device);                    /* faiss_gpu.go:16 */
+void faiss_gpu_resources_free(void *res);                     /* faiss_gpu.go:17 */
+void *faiss_gpu_index_flat_l2_new(void *res, int dim);        /* faiss_gpu.go:18 */
+void faiss_gpu_index_flat_l2_free(void *idx);                 /* faiss_gpu.go:19 */
+int faiss_gpu_index_add(void *idx, int64_t n, float *vectors);/* faiss_gpu.go:20 */
+int faiss_gpu_index_search(void *idx, int64_t n, float *queries, int k, float *distances,
+                           int64_t *labels);                  /* faiss_gpu.go:21 */
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Dense index: rows of one Arrow FixedSizeList<T, dim> column mirrored in HBM.
+ *    Replaces BruteForceIndex.SearchVectors (internal/store/adaptive_index.go:161-225), the
+ *    re-rank stage (internal/store/parallel_search.go:147-365, hnsw_batch.go:104-245) and the
+ *    simd batch functions (internal/simd/batch_operations.go:17-157) for resident data.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct lb_index lb_index;
+
+int lb_index_create(int device, int dim, int dtype, int metric, lb_index **out);
+void lb_index_free(lb_index *idx);
+/* Pre-size the HBM mirror (rows).  Optional; add grows geometrically otherwise. */
+int lb_index_reserve(lb_index *idx, int64_t n_rows);
+/* Append n rows from a host buffer laid out as the Arrow child values buffer: row-major,
+ * contiguous, n*dim elements (internal/store/arrow_utils.go:112-171).  gpu.Index.Add. */
+int lb_index_add(lb_index *idx, const void *rows, int64_t n);
+int lb_index_add_device(lb_index *idx, const void *d_rows, int64_t n, void *stream);
+int64_t lb_index_size(const lb_index *idx);
+int lb_index_dim(const lb_index *idx);
+/* Labels returned = local row + id_base (row-sharded multi-GPU: base of this shard). */
+int lb_index_set_id_base(lb_index *idx, int64_t id_base);
+/* Tombstones (index state).  words = ceil(nbits/64); NULL clears.  nbits may be < size
+ * (missing bits = live). */
+int lb_index_set_tombstones(lb_index *idx, const uint64_t *bitmap, int64_t nbits);
+int lb_index_set_tombstones_device(lb_index *idx, const uint64_t *d_bitmap, int64_t nbits, void *stream);
+
+/* Batched exact k-NN: nq queries (row-major [nq*dim], same dtype as the index) -> [nq*k]
+ * distances and labels.  allow: optional predicate bitmap over local rows shared by the
+ * batch (one Filters set per VectorSearchRequest, internal/query/requests.go:4-20), nbits
+ * must cover the index.  Replaces the per-query loop at
+ * internal/store/vector_search_action.go:73. */
+int lb_index_search(lb_index *idx, const void *queries, int64_t nq, int k, const uint64_t *allow,
+                    float *distances, int64_t *labels);
+int lb_index_search_device(lb_index *idx, const void *d_queries, int64_t nq, int k,
+                           const uint64_t *d_allow, float *d_distances, int64_t *d_labels,
+                           void *stream);
+
+/* Re-rank: per query a list of c candidate VectorIDs (uint32, internal/core/types.go:7);
+ * ids that are out of range, tombstoned or fail `allow` are dropped; exact distances of the
+ * rest; ascending; first k.  ArrowHNSW.RerankBatch / processChunkInternal. */
+int lb_index_rerank(lb_index *idx, const void *queries, int64_t nq, const uint32_t *cand_ids, int c,
+                    int k, const uint64_t *allow, float *distances, int64_t *labels);
+int lb_index_rerank_device(lb_index *idx, const void *d_queries, int64_t nq, const uint32_t *d_cand_ids,
+                           int c, int k, const uint64_t *d_allow, float *d_distances, int64_t *d_labels,
+                           void *stream);
+
+/* One query against every resident row -> size() distances in row order
+ * (simd.EuclideanDistanceBatchFlat with the flat buffer already in HBM). */
+int lb_index_distances(lb_index *idx, const void *query, float *out);
+
+/* Diagnostics of the last search on this handle by the calling thread: number of queries whose
+ * result was NOT certified exact by the coarse-margin test (see DESIGN.md "certification").
+ * 0 means every returned top-k provably equals the exhaustive exact top-k. */
+int64_t lb_index_last_uncertified(const lb_index *idx);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Stateless simd surface (host buffers in, host buffers out; data uploaded per call).
+ *    Mirrors internal/simd/batch_operations.go so internal/store can route through cgo.
+ * ---------------------------------------------------------------------------------------- */
+/* simd.{Euclidean,Cosine,DotProduct}DistanceBatch / EuclideanDistanceBatchFlat /
+ * EuclideanDistanceF16Batch / EuclideanDistanceSQ8Batch: one query x n rows in a flat buffer.
+ * Dot returns the RAW dot product here (simd.DotProductBatch), not negated.  LB_U8 + L2 returns
+ * the squared distance as float32(int32) (internal/simd/sq8.go:37-66). */
+int lb_simd_distance_batch_flat(int device, int metric, int dtype, const void *query, const void *flat,
+                                int64_t n, int dim, float *results);
+/* simd.ADCDistanceBatch (batch_operations.go:119-127): table [m*256] fp32, codes [n*m]. */
+int lb_simd_adc_distance_batch(int device, const float *table, const uint8_t *flat_codes, int m,
+                               int64_t n, float *results);
+/* Arrow compute "select_k_neighbors" (internal/store/arrow_kernels.go:230-345): indices of the
+ * k smallest distances, (distance, index) ascending. */
+int lb_select_k(int device, const float *distances, int64_t n, int k, int64_t *out_indices,
+                float *out_distances);
+/* Shard merge (internal/store/sharded_hnsw.go:432-503, result_merger.go:34-100):
+ * [parts][nq][k_in] sorted lists -> [nq][k] by (distance, label); label -1 = padding. */
+int lb_merge_topk(int device, const float *distances, const int64_t *labels, int parts, int64_t nq,
+                  int k_in, int k, float *out_distances, int64_t *out_labels);
+int lb_merge_topk_device(int device, const float *d_distances, const int64_t *d_labels, int parts,
+                         int64_t nq, int k_in, int k, float *d_out_distances, int64_t *d_out_labels,
+                         void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Product quantisation (internal/pq): ADC LUT build, ADC code scan + top-k', fp32 re-rank.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct lb_pq lb_pq;
+
+/* From the serialised encoder: [dims,M,K u32 LE][M*K*subDim f32 LE]
+ * (internal/pq/persistence.go:15-36).  K must be 256 (simd.ADCDistanceBatch hard-codes the
+ * stride, internal/simd/simd.go:350). */
+int lb_pq_create(int device, const void *blob, size_t blob_len, lb_pq **out);
+void lb_pq_free(lb_pq *pq);
+int lb_pq_params(const lb_pq *pq, int *dims, int *m, int *k, int *sub_dim);
+/* Append n PQ codes, row-major [n*M] (host / device). */
+int lb_pq_add_codes(lb_pq *pq, const uint8_t *codes, int64_t n);
+int lb_pq_add_codes_device(lb_pq *pq, const uint8_t *d_codes, int64_t n, void *stream);
+int64_t lb_pq_size(const lb_pq *pq);
+/* fp32 L2 index holding the raw vectors of the same rows, used by the re-rank stage.
+ * Not owned.  NULL detaches (search then returns the ADC top-k). */
+int lb_pq_attach_raw(lb_pq *pq, lb_index *raw);
+int lb_pq_set_tombstones(lb_pq *pq, const uint64_t *bitmap, int64_t nbits);
+/* PQEncoder.BuildADCTable (internal/pq/adc_table.go:15-51): table[m*K+k], squared L2. */
+int lb_pq_build_adc_table(lb_pq *pq, const float *query, float *table);
+/* PQEncoder.Encode for n vectors (internal/pq/encoder.go:76-136). */
+int lb_pq_encode(lb_pq *pq, const float *vectors, int64_t n, uint8_t *codes);
+/* ADC scan of all resident codes for nq fp32 queries, fused top-kprime, then (if a raw index
+ * is attached) exact fp32 Euclidean re-rank of those candidates -> top-k. */
+int lb_pq_search(lb_pq *pq, const float *queries, int64_t nq, int k, int kprime, const uint64_t *allow,
+                 float *distances, int64_t *labels);
+int lb_pq_search_device(lb_pq *pq, const float *d_queries, int64_t nq, int k, int kprime,
+                        const uint64_t *d_allow, float *d_distances, int64_t *d_labels, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 5. Predicate -> dense bitmap (internal/simd/simd.go:572-761 compare kernels,
+ *    internal/query/filter_evaluator.go:700-758).  op: 0 ==, 1 !=, 2 >, 3 >=, 4 <, 5 <=.
+ *    The result is AND-ed into `bitmap` when and_into != 0, else overwrites it.
+ * ---------------------------------------------------------------------------------------- */
+int lb_filter_i64(int device, const int64_t *column, int64_t n, int op, int64_t value, int and_into,
+                  uint64_t *bitmap);
+int lb_filter_f32(int device, const float *column, int64_t n, int op, float value, int and_into,
+                  uint64_t *bitmap);
+
+/* Count of kernel launches issued by this library in this process (bench evidence). */
+int64_t lb_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LONGBOW_B200_H */

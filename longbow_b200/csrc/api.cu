@@ -1,0 +1,855 @@
+// api.cu -- the C ABI of liblongbow_b200.so (include/longbow_b200.h): handles, HBM mirrors,
+// scratch management, launch planning.  No CPU fallback anywhere: without a CUDA device every
+// entry point fails with a code.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#pragma GCC visibility push(default)
+#include "../../include/longbow_b200.h"
+#pragma GCC visibility pop
+#include "kernels.cuh"
+
+namespace lb {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local std::string t_err;
+static int fail(int code, const char* what) {
+    t_err = what ? what : "";
+    return code;
+}
+static int fail_cuda(cudaError_t e, const char* where) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+    t_err = buf;
+    cudaGetLastError();  // clear sticky-less errors
+    return e == cudaErrorMemoryAllocation ? LB_ERR_OOM : LB_ERR_CUDA;
+}
+#define CK(call)                                             \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+static size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : dt == DT_F16 ? 2 : 1; }
+
+struct DeviceInfo {
+    int sm_count = 0;
+    bool ok = false;
+};
+static DeviceInfo g_dev[64];
+static std::mutex g_dev_mu;
+
+static int use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(LB_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n || device >= 64) return fail(LB_ERR_NO_DEVICE, "device id out of range");
+    CK(cudaSetDevice(device));
+    std::lock_guard<std::mutex> g(g_dev_mu);
+    if (!g_dev[device].ok) {
+        cudaDeviceProp p;
+        CK(cudaGetDeviceProperties(&p, device));
+        if (p.major < 10) return fail(LB_ERR_NO_DEVICE, "device is not sm_100 class (built for sm_100a only)");
+        g_dev[device].sm_count = p.multiProcessorCount;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = ~0ull;  // keep freed scratch cached in the pool
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        g_dev[device].ok = true;
+    }
+    return LB_OK;
+}
+
+// stream-ordered scratch
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    cudaError_t get(void** p, size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(p, bytes, st);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    ~Scratch() {
+        for (void* p : ptrs) cudaFreeAsync(p, st);
+    }
+};
+
+}  // namespace lb
+
+using namespace lb;
+
+// ---------------------------------------------------------------------------------------------
+struct lb_index {
+    int device, dim, dtype, metric;
+    void* rows = nullptr;  // [capacity][dim]
+    float* aux = nullptr;  // [capacity]
+    int64_t size = 0, capacity = 0;
+    uint32_t* tomb = nullptr;
+    int64_t tomb_bits = 0, tomb_cap_words = 0;
+    int64_t id_base = 0;
+    int sm_count = 0;
+    std::atomic<int64_t> last_uncertified{0};
+};
+
+struct lb_pq {
+    int device, dims, M, K, sub;
+    float* codebooks = nullptr;  // [M][K][sub]
+    uint8_t* codes = nullptr;    // [capacity][M]
+    int64_t size = 0, capacity = 0;
+    lb_index* raw = nullptr;
+    uint32_t* tomb = nullptr;
+    int64_t tomb_bits = 0;
+    int sm_count = 0;
+};
+
+struct faiss_res {
+    int device;
+};
+
+static int grow(void** buf, int64_t* cap, int64_t need, size_t row_bytes, int64_t used, float** aux) {
+    if (need <= *cap) return LB_OK;
+    int64_t ncap = *cap + (*cap >> 1);
+    if (ncap < need) ncap = need;
+    if (ncap < 1024) ncap = 1024;
+    void* nb = nullptr;
+    cudaError_t e = cudaMalloc(&nb, (size_t)ncap * row_bytes);
+    if (e != cudaSuccess && ncap > need) {  // retry with the exact size
+        cudaGetLastError();
+        ncap = need;
+        e = cudaMalloc(&nb, (size_t)ncap * row_bytes);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(rows)");
+    float* na = nullptr;
+    if (aux) {
+        e = cudaMalloc((void**)&na, (size_t)ncap * sizeof(float));
+        if (e != cudaSuccess) { cudaFree(nb); return fail_cuda(e, "cudaMalloc(aux)"); }
+    }
+    CK(cudaDeviceSynchronize());
+    if (used > 0) {
+        CK(cudaMemcpy(nb, *buf, (size_t)used * row_bytes, cudaMemcpyDeviceToDevice));
+        if (aux) CK(cudaMemcpy(na, *aux, (size_t)used * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    if (*buf) cudaFree(*buf);
+    *buf = nb;
+    if (aux) { if (*aux) cudaFree(*aux); *aux = na; }
+    *cap = ncap;
+    return LB_OK;
+}
+
+static bool supported(int dtype, int metric) {
+    if (metric < 0 || metric > 2) return false;
+    if (dtype == DT_F32 || dtype == DT_F16) return true;
+    if (dtype == DT_I8) return metric != METRIC_COSINE;  // dispatch.go:241-242: no int8 cosine kernel
+    return false;
+}
+
+extern "C" {
+
+const char* lb_last_error(void) { return t_err.c_str(); }
+int64_t lb_kernel_launch_count(void) { return g_launches.load(); }
+
+int lb_device_info(int device, int* sm_count, size_t* total_mem, char* name, size_t name_len) {
+    int rc = use_device(device);
+    if (rc) return rc;
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    if (name && name_len) { strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+    return LB_OK;
+}
+
+// ------------------------------------------------------------------------------- dense index
+int lb_index_create(int device, int dim, int dtype, int metric, lb_index** out) {
+    if (!out) return fail(LB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (dim <= 0) return fail(LB_ERR_INVALID, "dimension must be positive");
+    if (!supported(dtype, metric)) return fail(LB_ERR_UNSUPPORTED, "no kernel for this (metric, dtype)");
+    int rc = use_device(device);
+    if (rc) return rc;
+    lb_index* idx = new (std::nothrow) lb_index();
+    if (!idx) return fail(LB_ERR_OOM, "host allocation failed");
+    idx->device = device; idx->dim = dim; idx->dtype = dtype; idx->metric = metric;
+    idx->sm_count = g_dev[device].sm_count;
+    *out = idx;
+    return LB_OK;
+}
+
+void lb_index_free(lb_index* idx) {
+    if (!idx) return;
+    if (cudaSetDevice(idx->device) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        if (idx->rows) cudaFree(idx->rows);
+        if (idx->aux) cudaFree(idx->aux);
+        if (idx->tomb) cudaFree(idx->tomb);
+    }
+    cudaGetLastError();
+    delete idx;
+}
+
+int lb_index_reserve(lb_index* idx, int64_t n_rows) {
+    if (!idx || n_rows < 0) return fail(LB_ERR_INVALID, "bad argument");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    if (n_rows <= idx->capacity) return LB_OK;
+    // exact-size reservation (180 GB parts: no geometric slack)
+    size_t rb = (size_t)idx->dim * dtype_size(idx->dtype);
+    void* nb = nullptr;
+    float* na = nullptr;
+    cudaError_t e = cudaMalloc(&nb, (size_t)n_rows * rb);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(rows)");
+    e = cudaMalloc((void**)&na, (size_t)n_rows * 4);
+    if (e != cudaSuccess) { cudaFree(nb); return fail_cuda(e, "cudaMalloc(aux)"); }
+    CK(cudaDeviceSynchronize());
+    if (idx->size > 0) {
+        CK(cudaMemcpy(nb, idx->rows, (size_t)idx->size * rb, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(na, idx->aux, (size_t)idx->size * 4, cudaMemcpyDeviceToDevice));
+    }
+    if (idx->rows) cudaFree(idx->rows);
+    if (idx->aux) cudaFree(idx->aux);
+    idx->rows = nb; idx->aux = na; idx->capacity = n_rows;
+    return LB_OK;
+}
+
+static int index_add_common(lb_index* idx, const void* src, int64_t n, bool src_on_device, cudaStream_t st) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    if (n < 0) return fail(LB_ERR_INVALID, "n < 0");
+    if (n == 0) return LB_OK;
+    if (!src) return fail(LB_ERR_INVALID, "rows is NULL");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    if (idx->size + n > 0xfff00000ll) return fail(LB_ERR_INVALID, "more than 2^32 rows per device handle");
+    size_t rb = (size_t)idx->dim * dtype_size(idx->dtype);
+    rc = grow(&idx->rows, &idx->capacity, idx->size + n, rb, idx->size, &idx->aux);
+    if (rc) return rc;
+    char* dst = (char*)idx->rows + (size_t)idx->size * rb;
+    CK(cudaMemcpyAsync(dst, src, (size_t)n * rb, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    int64_t row0 = idx->size;
+    idx->size += n;
+    if (idx->metric != METRIC_DOT)
+        CK(launch_row_aux(idx->dtype, idx->rows, idx->size, idx->dim, idx->metric, idx->aux, row0, st));
+    if (!src_on_device) CK(cudaStreamSynchronize(st));  // cgo: the Go slice may move after return
+    return LB_OK;
+}
+
+int lb_index_add(lb_index* idx, const void* rows, int64_t n) {
+    return index_add_common(idx, rows, n, false, cudaStreamPerThread);
+}
+int lb_index_add_device(lb_index* idx, const void* d_rows, int64_t n, void* stream) {
+    return index_add_common(idx, d_rows, n, true, (cudaStream_t)stream);
+}
+int64_t lb_index_size(const lb_index* idx) { return idx ? idx->size : -1; }
+int lb_index_dim(const lb_index* idx) { return idx ? idx->dim : -1; }
+int lb_index_set_id_base(lb_index* idx, int64_t b) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    idx->id_base = b;
+    return LB_OK;
+}
+int64_t lb_index_last_uncertified(const lb_index* idx) { return idx ? idx->last_uncertified.load() : -1; }
+
+static int set_bitmap(int device, uint32_t** dst, int64_t* dst_bits, const uint64_t* src, int64_t nbits,
+                      bool on_device, cudaStream_t st) {
+    int rc = use_device(device);
+    if (rc) return rc;
+    if (!src || nbits <= 0) {
+        if (*dst) { CK(cudaDeviceSynchronize()); cudaFree(*dst); }
+        *dst = nullptr; *dst_bits = 0;
+        return LB_OK;
+    }
+    size_t words = (size_t)((nbits + 63) / 64);
+    uint32_t* nb = nullptr;
+    CK(cudaMalloc((void**)&nb, words * 8));
+    CK(cudaMemcpyAsync(nb, src, words * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    if (*dst) { CK(cudaDeviceSynchronize()); cudaFree(*dst); }
+    *dst = nb; *dst_bits = (int64_t)words * 64;
+    return LB_OK;
+}
+
+int lb_index_set_tombstones(lb_index* idx, const uint64_t* bitmap, int64_t nbits) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    return set_bitmap(idx->device, &idx->tomb, &idx->tomb_bits, bitmap, nbits, false, cudaStreamPerThread);
+}
+int lb_index_set_tombstones_device(lb_index* idx, const uint64_t* d_bitmap, int64_t nbits, void* stream) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    return set_bitmap(idx->device, &idx->tomb, &idx->tomb_bits, d_bitmap, nbits, true, (cudaStream_t)stream);
+}
+
+// coarse candidates per query: margin over k absorbs coarse-key rounding; the re-score stage
+// restores the reference's exact values and order.
+static int coarse_k(int k) {
+    int m = k / 4;
+    if (m < 16) m = 16;
+    int kc = k + m;
+    return ((kc + 31) / 32) * 32;
+}
+
+static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const uint64_t* d_allow, float* d_dist,
+                       int64_t* d_lab, cudaStream_t st) {
+    if (nq == 0) return LB_OK;
+    const int kc = coarse_k(k);
+    if (kc > 896) return fail(LB_ERR_UNSUPPORTED, "k too large for the fused selector (k <= 704)");
+    Scratch scr(st);
+    if (idx->size == 0) {
+        uint64_t* merged;
+        CK(scr.get((void**)&merged, 8));
+        CK(launch_unpack_topk(merged, (int)nq, 0, k, 0, d_dist, d_lab, st));
+        return LB_OK;
+    }
+    // queries are processed in chunks so scratch stays bounded
+    const int64_t qchunk = 4096;
+    for (int64_t qo = 0; qo < nq; qo += qchunk) {
+        const int cq = (int)((nq - qo) < qchunk ? (nq - qo) : qchunk);
+        ScanArgs a;
+        a.dtype = idx->dtype; a.metric = idx->metric;
+        a.db = idx->rows; a.aux = idx->aux; a.n_rows = (uint32_t)idx->size; a.dim = idx->dim;
+        a.queries = (const char*)d_q + (size_t)qo * idx->dim * dtype_size(idx->dtype);
+        a.nq = cq;
+        a.tomb = idx->tomb; a.tomb_bits = (uint32_t)(idx->tomb_bits > 0xffffffffll ? 0xffffffffll : idx->tomb_bits);
+        a.allow = (const uint32_t*)d_allow;
+        a.kc = kc;
+        a.tq = (kc <= 128 && cq > 32) ? 64 : (kc <= 384 && cq > 16) ? 32 : 16;
+        if (kc > 384) a.tq = 16; else if (kc > 128 && a.tq == 64) a.tq = 32;
+        a.cap = next_pow2(kc + 128);
+        const int qblocks = (cq + a.tq - 1) / a.tq;
+        int target = 2 * idx->sm_count;
+        int parts = (target + qblocks - 1) / qblocks;
+        int64_t max_parts = (idx->size + 511) / 512;
+        if (parts > max_parts) parts = (int)max_parts;
+        if (parts < 1) parts = 1;
+        int64_t rpp = (idx->size + parts - 1) / parts;
+        rpp = ((rpp + 127) / 128) * 128;
+        parts = (int)((idx->size + rpp - 1) / rpp);
+        a.parts = parts; a.rows_per_part = (uint32_t)rpp;
+        uint64_t *partial, *merged;
+        CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
+        a.partial = partial;
+        CK(launch_dense_scan_simt(a, st));
+        if (parts > 1) {
+            CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
+            CK(launch_merge_partials(partial, parts, cq, kc, merged, st));
+        } else {
+            merged = partial;
+        }
+        RescoreArgs r;
+        r.dtype = idx->dtype; r.metric = idx->metric; r.db = idx->rows; r.n_rows = (uint32_t)idx->size;
+        r.dim = idx->dim; r.queries = a.queries; r.nq = cq; r.packed = merged; r.ids32 = nullptr;
+        r.c = kc; r.k = k; r.tomb = nullptr; r.tomb_bits = 0; r.allow = nullptr; r.id_base = idx->id_base;
+        r.out_d = d_dist + (size_t)qo * k; r.out_l = d_lab + (size_t)qo * k; r.negate_dot = 1;
+        CK(launch_rescore(r, st));
+    }
+    return LB_OK;
+}
+
+int lb_index_search_device(lb_index* idx, const void* d_queries, int64_t nq, int k, const uint64_t* d_allow,
+                           float* d_distances, int64_t* d_labels, void* stream) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    if (k <= 0 || nq < 0) return fail(LB_ERR_INVALID, "k must be positive and nq non-negative");
+    if (nq > 0 && (!d_queries || !d_distances || !d_labels)) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    return search_core(idx, d_queries, nq, k, d_allow, d_distances, d_labels, (cudaStream_t)stream);
+}
+
+int lb_index_search(lb_index* idx, const void* queries, int64_t nq, int k, const uint64_t* allow, float* distances,
+                    int64_t* labels) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    if (k <= 0 || nq < 0) return fail(LB_ERR_INVALID, "k must be positive and nq non-negative");
+    if (nq == 0) return LB_OK;
+    if (!queries || !distances || !labels) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    size_t qb = (size_t)nq * idx->dim * dtype_size(idx->dtype);
+    void* d_q; float* d_d; int64_t* d_l; uint64_t* d_allow = nullptr;
+    CK(scr.get(&d_q, qb));
+    CK(scr.get((void**)&d_d, (size_t)nq * k * 4));
+    CK(scr.get((void**)&d_l, (size_t)nq * k * 8));
+    CK(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, st));
+    if (allow) {
+        size_t words = (size_t)((idx->size + 63) / 64);
+        CK(scr.get((void**)&d_allow, words * 8));
+        CK(cudaMemcpyAsync(d_allow, allow, words * 8, cudaMemcpyHostToDevice, st));
+    }
+    rc = search_core(idx, d_q, nq, k, d_allow, d_d, d_l, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CK(cudaMemcpyAsync(distances, d_d, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(labels, d_l, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+static int rerank_core(lb_index* idx, const void* d_q, int64_t nq, const uint32_t* d_ids, int c, int k,
+                       const uint64_t* d_allow, float* d_dist, int64_t* d_lab, cudaStream_t st) {
+    if (nq == 0) return LB_OK;
+    if (c > 1024) return fail(LB_ERR_UNSUPPORTED, "more than 1024 candidates per query");
+    RescoreArgs r;
+    r.dtype = idx->dtype; r.metric = idx->metric; r.db = idx->rows; r.n_rows = (uint32_t)idx->size;
+    r.dim = idx->dim; r.queries = d_q; r.nq = (int)nq; r.packed = nullptr; r.ids32 = d_ids;
+    r.c = c; r.k = k; r.tomb = idx->tomb;
+    r.tomb_bits = (uint32_t)(idx->tomb_bits > 0xffffffffll ? 0xffffffffll : idx->tomb_bits);
+    r.allow = (const uint32_t*)d_allow; r.id_base = idx->id_base; r.out_d = d_dist; r.out_l = d_lab;
+    r.negate_dot = 1;
+    CK(launch_rescore(r, st));
+    return LB_OK;
+}
+
+int lb_index_rerank_device(lb_index* idx, const void* d_queries, int64_t nq, const uint32_t* d_cand_ids, int c,
+                           int k, const uint64_t* d_allow, float* d_distances, int64_t* d_labels, void* stream) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    if (k <= 0 || nq < 0 || c <= 0) return fail(LB_ERR_INVALID, "k, c must be positive");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    return rerank_core(idx, d_queries, nq, d_cand_ids, c, k, d_allow, d_distances, d_labels, (cudaStream_t)stream);
+}
+
+int lb_index_rerank(lb_index* idx, const void* queries, int64_t nq, const uint32_t* cand_ids, int c, int k,
+                    const uint64_t* allow, float* distances, int64_t* labels) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    if (k <= 0 || nq < 0 || c <= 0) return fail(LB_ERR_INVALID, "k, c must be positive");
+    if (nq == 0) return LB_OK;
+    if (!queries || !cand_ids || !distances || !labels) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    size_t qb = (size_t)nq * idx->dim * dtype_size(idx->dtype);
+    void* d_q; uint32_t* d_ids; float* d_d; int64_t* d_l; uint64_t* d_allow = nullptr;
+    CK(scr.get(&d_q, qb));
+    CK(scr.get((void**)&d_ids, (size_t)nq * c * 4));
+    CK(scr.get((void**)&d_d, (size_t)nq * k * 4));
+    CK(scr.get((void**)&d_l, (size_t)nq * k * 8));
+    CK(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_ids, cand_ids, (size_t)nq * c * 4, cudaMemcpyHostToDevice, st));
+    if (allow) {
+        size_t words = (size_t)((idx->size + 63) / 64);
+        CK(scr.get((void**)&d_allow, words * 8));
+        CK(cudaMemcpyAsync(d_allow, allow, words * 8, cudaMemcpyHostToDevice, st));
+    }
+    rc = rerank_core(idx, d_q, nq, d_ids, c, k, d_allow, d_d, d_l, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CK(cudaMemcpyAsync(distances, d_d, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(labels, d_l, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+int lb_index_distances(lb_index* idx, const void* query, float* out) {
+    if (!idx || !query || !out) return fail(LB_ERR_INVALID, "NULL argument");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    if (idx->size == 0) return LB_OK;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    size_t qb = (size_t)idx->dim * dtype_size(idx->dtype);
+    void* d_q; float* d_o;
+    CK(scr.get(&d_q, qb));
+    CK(scr.get((void**)&d_o, (size_t)idx->size * 4));
+    CK(cudaMemcpyAsync(d_q, query, qb, cudaMemcpyHostToDevice, st));
+    CK(launch_batch_flat(idx->metric, idx->dtype, idx->rows, idx->size, idx->dim, d_q, d_o, 1, st));
+    CK(cudaMemcpyAsync(out, d_o, (size_t)idx->size * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+// ------------------------------------------------------------------ faiss_gpu_* (faiss_gpu.go:16-21)
+void* faiss_gpu_resources_new(int device) {
+    if (use_device(device) != LB_OK) return nullptr;
+    faiss_res* r = new (std::nothrow) faiss_res();
+    if (r) r->device = device;
+    return r;
+}
+void faiss_gpu_resources_free(void* res) { delete (faiss_res*)res; }
+void* faiss_gpu_index_flat_l2_new(void* res, int dim) {
+    if (!res) { fail(LB_ERR_INVALID, "resources is NULL"); return nullptr; }
+    lb_index* idx = nullptr;
+    if (lb_index_create(((faiss_res*)res)->device, dim, LB_F32, LB_METRIC_L2, &idx) != LB_OK) return nullptr;
+    return idx;
+}
+void faiss_gpu_index_flat_l2_free(void* idx) { lb_index_free((lb_index*)idx); }
+int faiss_gpu_index_add(void* idx, int64_t n, float* vectors) { return lb_index_add((lb_index*)idx, vectors, n); }
+int faiss_gpu_index_search(void* idx, int64_t n, float* queries, int k, float* distances, int64_t* labels) {
+    return lb_index_search((lb_index*)idx, queries, n, k, nullptr, distances, labels);
+}
+
+// ------------------------------------------------------------------------------ stateless simd
+int lb_simd_distance_batch_flat(int device, int metric, int dtype, const void* query, const void* flat, int64_t n,
+                                int dim, float* results) {
+    if (n < 0 || dim <= 0) return fail(LB_ERR_INVALID, "bad size");
+    if (n == 0) return LB_OK;  // batch_operations.go:65-67
+    if (!query || !flat || !results) return fail(LB_ERR_INVALID, "NULL buffer");
+    if (!(dtype == DT_U8 ? metric == METRIC_L2 : supported(dtype, metric)))
+        return fail(LB_ERR_UNSUPPORTED, "no kernel for this (metric, dtype)");
+    int rc = use_device(device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    size_t es = dtype_size(dtype);
+    void *d_q, *d_f; float* d_o;
+    CK(scr.get(&d_q, (size_t)dim * es));
+    CK(scr.get(&d_f, (size_t)n * dim * es));
+    CK(scr.get((void**)&d_o, (size_t)n * 4));
+    CK(cudaMemcpyAsync(d_q, query, (size_t)dim * es, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_f, flat, (size_t)n * dim * es, cudaMemcpyHostToDevice, st));
+    CK(launch_batch_flat(metric, dtype, d_f, n, dim, d_q, d_o, 0, st));
+    CK(cudaMemcpyAsync(results, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+int lb_simd_adc_distance_batch(int device, const float* table, const uint8_t* flat_codes, int m, int64_t n,
+                               float* results) {
+    if (!table || !flat_codes) return fail(LB_ERR_INVALID, "simd: empty table or codes");  // batch_operations.go:120
+    if (m <= 0) return fail(LB_ERR_INVALID, "simd: invalid m parameter");                   // :123
+    if (m > 200) return fail(LB_ERR_UNSUPPORTED, "m too large for a shared-memory LUT");
+    if (n <= 0) return LB_OK;
+    int rc = use_device(device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    float *d_t, *d_o; uint8_t* d_c;
+    CK(scr.get((void**)&d_t, (size_t)m * 1024));
+    CK(scr.get((void**)&d_c, (size_t)n * m));
+    CK(scr.get((void**)&d_o, (size_t)n * 4));
+    CK(cudaMemcpyAsync(d_t, table, (size_t)m * 1024, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_c, flat_codes, (size_t)n * m, cudaMemcpyHostToDevice, st));
+    CK(launch_adc_batch(d_t, d_c, m, n, d_o, st));
+    CK(cudaMemcpyAsync(results, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+int lb_select_k(int device, const float* distances, int64_t n, int k, int64_t* out_indices, float* out_distances) {
+    if (k <= 0 || n < 0 || !out_indices) return fail(LB_ERR_INVALID, "bad argument");
+    if (n > 0 && !distances) return fail(LB_ERR_INVALID, "NULL buffer");
+    if (k > 4096) return fail(LB_ERR_UNSUPPORTED, "k > 4096");
+    if (n > 0xfff00000ll) return fail(LB_ERR_UNSUPPORTED, "n too large");
+    int rc = use_device(device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    int chunks = (int)((n + 4095) / 4096);
+    if (chunks < 1) chunks = 1;
+    float *d_d, *d_od; int64_t* d_oi; uint64_t *p, *m;
+    CK(scr.get((void**)&d_d, (size_t)n * 4));
+    CK(scr.get((void**)&d_od, (size_t)k * 4));
+    CK(scr.get((void**)&d_oi, (size_t)k * 8));
+    CK(scr.get((void**)&p, (size_t)chunks * k * 8));
+    CK(scr.get((void**)&m, (size_t)k * 8));
+    if (n > 0) CK(cudaMemcpyAsync(d_d, distances, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(launch_select_k(d_d, n, k, p, m, d_oi, d_od, st));
+    CK(cudaMemcpyAsync(out_indices, d_oi, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+    if (out_distances) CK(cudaMemcpyAsync(out_distances, d_od, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+int lb_merge_topk_device(int device, const float* d_distances, const int64_t* d_labels, int parts, int64_t nq,
+                         int k_in, int k, float* d_out_distances, int64_t* d_out_labels, void* stream) {
+    if (parts <= 0 || k_in <= 0 || k <= 0 || nq < 0) return fail(LB_ERR_INVALID, "bad argument");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if ((int64_t)parts * k_in > 16384) return fail(LB_ERR_UNSUPPORTED, "parts * k_in > 16384");
+    CK(launch_merge_topk(d_distances, d_labels, parts, (int)nq, k_in, k, d_out_distances, d_out_labels,
+                         (cudaStream_t)stream));
+    return LB_OK;
+}
+
+int lb_merge_topk(int device, const float* distances, const int64_t* labels, int parts, int64_t nq, int k_in, int k,
+                  float* out_distances, int64_t* out_labels) {
+    if (parts <= 0 || k_in <= 0 || k <= 0 || nq < 0) return fail(LB_ERR_INVALID, "bad argument");
+    if (nq == 0) return LB_OK;
+    int rc = use_device(device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    size_t cnt = (size_t)parts * nq * k_in;
+    float *d_d, *d_od; int64_t *d_l, *d_ol;
+    CK(scr.get((void**)&d_d, cnt * 4));
+    CK(scr.get((void**)&d_l, cnt * 8));
+    CK(scr.get((void**)&d_od, (size_t)nq * k * 4));
+    CK(scr.get((void**)&d_ol, (size_t)nq * k * 8));
+    CK(cudaMemcpyAsync(d_d, distances, cnt * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_l, labels, cnt * 8, cudaMemcpyHostToDevice, st));
+    rc = lb_merge_topk_device(device, d_d, d_l, parts, nq, k_in, k, d_od, d_ol, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CK(cudaMemcpyAsync(out_distances, d_od, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_labels, d_ol, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+// --------------------------------------------------------------------------------------- PQ
+int lb_pq_create(int device, const void* blob, size_t blob_len, lb_pq** out) {
+    if (!out) return fail(LB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!blob || blob_len < 12) return fail(LB_ERR_INVALID, "invalid PQ data: too short");  // persistence.go:40
+    uint32_t hdr[3];
+    memcpy(hdr, blob, 12);
+    int dims = (int)hdr[0], M = (int)hdr[1], K = (int)hdr[2];
+    if (M == 0 || dims % M != 0) return fail(LB_ERR_INVALID, "invalid PQ parameters in serialized data");  // :48
+    int sub = dims / M;
+    size_t expect = 12 + (size_t)M * K * sub * 4;
+    if (blob_len != expect) return fail(LB_ERR_INVALID, "invalid PQ data: size mismatch");  // :54
+    if (K != 256) return fail(LB_ERR_UNSUPPORTED, "only K = 256 is coherent with simd.ADCDistanceBatch (simd.go:350)");
+    if (M > 200) return fail(LB_ERR_UNSUPPORTED, "M too large for a shared-memory LUT (M <= 200)");
+    int rc = use_device(device);
+    if (rc) return rc;
+    lb_pq* pq = new (std::nothrow) lb_pq();
+    if (!pq) return fail(LB_ERR_OOM, "host allocation failed");
+    pq->device = device; pq->dims = dims; pq->M = M; pq->K = K; pq->sub = sub;
+    pq->sm_count = g_dev[device].sm_count;
+    cudaError_t e = cudaMalloc((void**)&pq->codebooks, (size_t)M * K * sub * 4);
+    if (e != cudaSuccess) { delete pq; return fail_cuda(e, "cudaMalloc(codebooks)"); }
+    e = cudaMemcpy(pq->codebooks, (const char*)blob + 12, (size_t)M * K * sub * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(pq->codebooks); delete pq; return fail_cuda(e, "cudaMemcpy(codebooks)"); }
+    *out = pq;
+    return LB_OK;
+}
+
+void lb_pq_free(lb_pq* pq) {
+    if (!pq) return;
+    if (cudaSetDevice(pq->device) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        if (pq->codebooks) cudaFree(pq->codebooks);
+        if (pq->codes) cudaFree(pq->codes);
+        if (pq->tomb) cudaFree(pq->tomb);
+    }
+    cudaGetLastError();
+    delete pq;
+}
+
+int lb_pq_params(const lb_pq* pq, int* dims, int* m, int* k, int* sub_dim) {
+    if (!pq) return fail(LB_ERR_INVALID, "pq is NULL");
+    if (dims) *dims = pq->dims;
+    if (m) *m = pq->M;
+    if (k) *k = pq->K;
+    if (sub_dim) *sub_dim = pq->sub;
+    return LB_OK;
+}
+
+static int pq_add_common(lb_pq* pq, const uint8_t* src, int64_t n, bool on_device, cudaStream_t st) {
+    if (!pq) return fail(LB_ERR_INVALID, "pq is NULL");
+    if (n < 0) return fail(LB_ERR_INVALID, "n < 0");
+    if (n == 0) return LB_OK;
+    if (!src) return fail(LB_ERR_INVALID, "codes is NULL");
+    int rc = use_device(pq->device);
+    if (rc) return rc;
+    if (pq->size + n > 0xfff00000ll) return fail(LB_ERR_INVALID, "more than 2^32 rows per device handle");
+    rc = grow((void**)&pq->codes, &pq->capacity, pq->size + n, (size_t)pq->M, pq->size, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(pq->codes + (size_t)pq->size * pq->M, src, (size_t)n * pq->M,
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    pq->size += n;
+    if (!on_device) CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+int lb_pq_add_codes(lb_pq* pq, const uint8_t* codes, int64_t n) {
+    return pq_add_common(pq, codes, n, false, cudaStreamPerThread);
+}
+int lb_pq_add_codes_device(lb_pq* pq, const uint8_t* d_codes, int64_t n, void* stream) {
+    return pq_add_common(pq, d_codes, n, true, (cudaStream_t)stream);
+}
+int64_t lb_pq_size(const lb_pq* pq) { return pq ? pq->size : -1; }
+
+int lb_pq_attach_raw(lb_pq* pq, lb_index* raw) {
+    if (!pq) return fail(LB_ERR_INVALID, "pq is NULL");
+    if (raw) {
+        if (raw->dtype != DT_F32 || raw->metric != METRIC_L2 || raw->dim != pq->dims || raw->device != pq->device)
+            return fail(LB_ERR_INVALID, "raw index must be fp32 / L2 / same dims / same device");
+    }
+    pq->raw = raw;
+    return LB_OK;
+}
+
+int lb_pq_set_tombstones(lb_pq* pq, const uint64_t* bitmap, int64_t nbits) {
+    if (!pq) return fail(LB_ERR_INVALID, "pq is NULL");
+    return set_bitmap(pq->device, &pq->tomb, &pq->tomb_bits, bitmap, nbits, false, cudaStreamPerThread);
+}
+
+int lb_pq_build_adc_table(lb_pq* pq, const float* query, float* table) {
+    if (!pq || !query || !table) return fail(LB_ERR_INVALID, "NULL argument");
+    int rc = use_device(pq->device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    float *d_q, *d_t;
+    CK(scr.get((void**)&d_q, (size_t)pq->dims * 4));
+    CK(scr.get((void**)&d_t, (size_t)pq->M * pq->K * 4));
+    CK(cudaMemcpyAsync(d_q, query, (size_t)pq->dims * 4, cudaMemcpyHostToDevice, st));
+    CK(launch_adc_lut(pq->codebooks, pq->M, pq->K, pq->sub, d_q, 1, d_t, st));
+    CK(cudaMemcpyAsync(table, d_t, (size_t)pq->M * pq->K * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+int lb_pq_encode(lb_pq* pq, const float* vectors, int64_t n, uint8_t* codes) {
+    if (!pq) return fail(LB_ERR_INVALID, "pq is NULL");
+    if (n < 0) return fail(LB_ERR_INVALID, "n < 0");
+    if (n == 0) return LB_OK;
+    if (!vectors || !codes) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(pq->device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    float* d_v; uint8_t* d_c;
+    CK(scr.get((void**)&d_v, (size_t)n * pq->dims * 4));
+    CK(scr.get((void**)&d_c, (size_t)n * pq->M));
+    CK(cudaMemcpyAsync(d_v, vectors, (size_t)n * pq->dims * 4, cudaMemcpyHostToDevice, st));
+    CK(launch_pq_encode(pq->codebooks, pq->M, pq->K, pq->sub, d_v, n, d_c, st));
+    CK(cudaMemcpyAsync(codes, d_c, (size_t)n * pq->M, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kprime, const uint64_t* d_allow,
+                          float* d_dist, int64_t* d_lab, cudaStream_t st) {
+    if (nq == 0) return LB_OK;
+    const bool rerank = pq->raw != nullptr;
+    const int kc = rerank ? (kprime > k ? kprime : k) : k;  // ADC keys are exact: no margin needed
+    if (kc > 1024) return fail(LB_ERR_UNSUPPORTED, "k' > 1024");
+    if (rerank && pq->raw->size < pq->size) return fail(LB_ERR_STATE, "raw index has fewer rows than codes");
+    Scratch scr(st);
+    if (pq->size == 0) {
+        uint64_t* merged;
+        CK(scr.get((void**)&merged, 8));
+        CK(launch_unpack_topk(merged, (int)nq, 0, k, 0, d_dist, d_lab, st));
+        return LB_OK;
+    }
+    const int64_t qchunk = 512;
+    for (int64_t qo = 0; qo < nq; qo += qchunk) {
+        const int cq = (int)((nq - qo) < qchunk ? (nq - qo) : qchunk);
+        const float* q = d_q + (size_t)qo * pq->dims;
+        float* luts;
+        CK(scr.get((void**)&luts, (size_t)cq * pq->M * 1024));
+        CK(launch_adc_lut(pq->codebooks, pq->M, pq->K, pq->sub, q, cq, luts, st));
+        PqScanArgs a;
+        a.codes = pq->codes; a.n_rows = (uint32_t)pq->size; a.M = pq->M; a.luts = luts; a.nq = cq;
+        a.tomb = pq->tomb; a.tomb_bits = (uint32_t)(pq->tomb_bits > 0xffffffffll ? 0xffffffffll : pq->tomb_bits);
+        a.allow = (const uint32_t*)d_allow;
+        a.kc = kc; a.cap = next_pow2(kc + 256);
+        int target = 4 * pq->sm_count;
+        int parts = (target + cq - 1) / cq;
+        int64_t max_parts = (pq->size + 2047) / 2048;
+        if (parts > max_parts) parts = (int)max_parts;
+        if (parts < 1) parts = 1;
+        int64_t rpp = (pq->size + parts - 1) / parts;
+        rpp = ((rpp + 255) / 256) * 256;
+        parts = (int)((pq->size + rpp - 1) / rpp);
+        a.parts = parts; a.rows_per_part = (uint32_t)rpp;
+        uint64_t *partial, *merged;
+        CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
+        a.partial = partial;
+        CK(launch_adc_scan(a, st));
+        if (parts > 1) {
+            CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
+            CK(launch_merge_partials(partial, parts, cq, kc, merged, st));
+        } else {
+            merged = partial;
+        }
+        if (rerank) {
+            RescoreArgs r;
+            r.dtype = DT_F32; r.metric = METRIC_L2; r.db = pq->raw->rows; r.n_rows = (uint32_t)pq->raw->size;
+            r.dim = pq->dims; r.queries = q; r.nq = cq; r.packed = merged; r.ids32 = nullptr; r.c = kc; r.k = k;
+            r.tomb = nullptr; r.tomb_bits = 0; r.allow = nullptr; r.id_base = 0;
+            r.out_d = d_dist + (size_t)qo * k; r.out_l = d_lab + (size_t)qo * k; r.negate_dot = 1;
+            CK(launch_rescore(r, st));
+        } else {
+            CK(launch_unpack_topk(merged, cq, kc, k, 0, d_dist + (size_t)qo * k, d_lab + (size_t)qo * k, st));
+        }
+    }
+    return LB_OK;
+}
+
+int lb_pq_search_device(lb_pq* pq, const float* d_queries, int64_t nq, int k, int kprime, const uint64_t* d_allow,
+                        float* d_distances, int64_t* d_labels, void* stream) {
+    if (!pq) return fail(LB_ERR_INVALID, "pq is NULL");
+    if (k <= 0 || nq < 0) return fail(LB_ERR_INVALID, "k must be positive");
+    int rc = use_device(pq->device);
+    if (rc) return rc;
+    return pq_search_core(pq, d_queries, nq, k, kprime, d_allow, d_distances, d_labels, (cudaStream_t)stream);
+}
+
+int lb_pq_search(lb_pq* pq, const float* queries, int64_t nq, int k, int kprime, const uint64_t* allow,
+                 float* distances, int64_t* labels) {
+    if (!pq) return fail(LB_ERR_INVALID, "pq is NULL");
+    if (k <= 0 || nq < 0) return fail(LB_ERR_INVALID, "k must be positive");
+    if (nq == 0) return LB_OK;
+    if (!queries || !distances || !labels) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(pq->device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    float *d_q, *d_d; int64_t* d_l; uint64_t* d_allow = nullptr;
+    CK(scr.get((void**)&d_q, (size_t)nq * pq->dims * 4));
+    CK(scr.get((void**)&d_d, (size_t)nq * k * 4));
+    CK(scr.get((void**)&d_l, (size_t)nq * k * 8));
+    CK(cudaMemcpyAsync(d_q, queries, (size_t)nq * pq->dims * 4, cudaMemcpyHostToDevice, st));
+    if (allow) {
+        size_t words = (size_t)((pq->size + 63) / 64);
+        CK(scr.get((void**)&d_allow, words * 8));
+        CK(cudaMemcpyAsync(d_allow, allow, words * 8, cudaMemcpyHostToDevice, st));
+    }
+    rc = pq_search_core(pq, d_q, nq, k, kprime, d_allow, d_d, d_l, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    CK(cudaMemcpyAsync(distances, d_d, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(labels, d_l, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+// ----------------------------------------------------------------------------------- predicates
+}  // extern "C"
+
+template <typename T, typename F>
+static int filter_common(int device, const T* column, int64_t n, int op, int and_into, uint64_t* bitmap, F launch) {
+    if (n < 0 || op < 0 || op > 5) return fail(LB_ERR_INVALID, "bad argument");
+    if (n == 0) return LB_OK;
+    if (!column || !bitmap) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    size_t words = (size_t)((n + 63) / 64);
+    T* d_c; uint32_t* d_b;
+    CK(scr.get((void**)&d_c, (size_t)n * sizeof(T)));
+    CK(scr.get((void**)&d_b, words * 8));
+    CK(cudaMemcpyAsync(d_c, column, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (and_into) CK(cudaMemcpyAsync(d_b, bitmap, words * 8, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(d_b, 0, words * 8, st));
+    CK(launch(d_c, d_b, st));
+    CK(cudaMemcpyAsync(bitmap, d_b, words * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+extern "C" {
+
+int lb_filter_i64(int device, const int64_t* column, int64_t n, int op, int64_t value, int and_into, uint64_t* bitmap) {
+    return filter_common<int64_t>(device, column, n, op, and_into, bitmap,
+                                  [&](const int64_t* c, uint32_t* b, cudaStream_t st) {
+                                      return launch_filter_i64(c, n, op, value, and_into, b, st);
+                                  });
+}
+int lb_filter_f32(int device, const float* column, int64_t n, int op, float value, int and_into, uint64_t* bitmap) {
+    return filter_common<float>(device, column, n, op, and_into, bitmap,
+                                [&](const float* c, uint32_t* b, cudaStream_t st) {
+                                    return launch_filter_f32(c, n, op, value, and_into, b, st);
+                                });
+}
+
+}  // extern "C"

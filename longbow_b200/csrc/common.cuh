@@ -1,0 +1,240 @@
+// common.cuh -- shared device helpers for liblongbow_b200 (sm_100a only).
+//
+// * exact arithmetic: bit-for-bit the reference's portable Go kernels (Unrolled4x lane order,
+//   separate mul/add roundings, sqrt through double) -- used wherever a value is RETURNED.
+// * (key, id) packing: one u64 compare orders by (distance, id), which is the tie rule the
+//   reference's brute-force heap implies (internal/store/adaptive_index.go:200-211).
+// * warp / block bitonic sorts over shared memory.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lb {
+
+enum { METRIC_L2 = 0, METRIC_COSINE = 1, METRIC_DOT = 2 };
+enum { DT_F32 = 0, DT_F16 = 1, DT_I8 = 2, DT_U8 = 3 };
+
+constexpr uint64_t kInvalid = ~0ull;
+
+// ---------------------------------------------------------------------------------------------
+// Ordered key packing.  ord(f) is monotone in f over all non-NaN floats (negatives included:
+// the dot metric is a negated similarity).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t pack_key(float key, uint32_t id) {
+    return ((uint64_t)float_to_ordered(key) << 32) | id;
+}
+__host__ __device__ __forceinline__ float key_of(uint64_t p) { return ordered_to_float((uint32_t)(p >> 32)); }
+__host__ __device__ __forceinline__ uint32_t id_of(uint64_t p) { return (uint32_t)p; }
+
+__device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ bm, uint32_t i) {
+    return (__ldg(bm + (i >> 5)) >> (i & 31)) & 1u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Element widening (exact for every supported type).
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int kDtype = DT_F32;
+    static constexpr int kVec = 4;  // elements per 16-byte vector
+    __device__ static __forceinline__ float widen(float v) { return v; }
+};
+template <> struct Elem<__half> {
+    static constexpr int kDtype = DT_F16;
+    static constexpr int kVec = 8;
+    __device__ static __forceinline__ float widen(__half v) { return __half2float(v); }
+};
+template <> struct Elem<int8_t> {
+    static constexpr int kDtype = DT_I8;
+    static constexpr int kVec = 16;
+    __device__ static __forceinline__ float widen(int8_t v) { return (float)v; }
+};
+template <> struct Elem<uint8_t> {
+    static constexpr int kDtype = DT_U8;
+    static constexpr int kVec = 16;
+    __device__ static __forceinline__ float widen(uint8_t v) { return (float)v; }
+};
+
+// Unpack one 16-byte vector into kVec floats.
+template <typename T> __device__ __forceinline__ void unpack16(const uint4& v, float* out);
+template <> __device__ __forceinline__ void unpack16<float>(const uint4& v, float* out) {
+    out[0] = __uint_as_float(v.x); out[1] = __uint_as_float(v.y);
+    out[2] = __uint_as_float(v.z); out[3] = __uint_as_float(v.w);
+}
+template <> __device__ __forceinline__ void unpack16<__half>(const uint4& v, float* out) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+        float2 f = __half22float2(h);
+        out[2 * i] = f.x; out[2 * i + 1] = f.y;
+    }
+}
+template <> __device__ __forceinline__ void unpack16<int8_t>(const uint4& v, float* out) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) out[4 * i + b] = (float)(int8_t)((w[i] >> (8 * b)) & 0xff);
+}
+template <> __device__ __forceinline__ void unpack16<uint8_t>(const uint4& v, float* out) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) out[4 * i + b] = (float)((w[i] >> (8 * b)) & 0xff);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact (reference-order) accumulation.  State for one (query,row) pair.
+//   L2:      s[l] += (a-b)*(a-b)           internal/simd/simd.go:365-396, :767-791, simd_baseline.go:13-35
+//   DOT:     s[l] += a*b                    simd.go:453-479, :793-809, simd_baseline.go:37-54
+//   COSINE:  dot[l], na[l], nb[l]           simd.go:399-450, :811-848
+// Elements i = 4m+l go to lane l in increasing m; the remainder (dim % 4) goes to lane 0.
+// __fmul_rn/__fadd_rn/__fsub_rn are never contracted into FMA.
+// ---------------------------------------------------------------------------------------------
+template <int METRIC> struct ExactAcc;
+
+template <> struct ExactAcc<METRIC_L2> {
+    float s[4];
+    __device__ __forceinline__ void init() { s[0] = s[1] = s[2] = s[3] = 0.f; }
+    __device__ __forceinline__ void add(int lane, float a, float b) {
+        float d = __fsub_rn(a, b);
+        s[lane] = __fadd_rn(s[lane], __fmul_rn(d, d));
+    }
+    // squared distance (L2SquaredFloat32, distance_functions.go:195-227)
+    __device__ __forceinline__ float sum() const {
+        return __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[1]), s[2]), s[3]);
+    }
+    // float32(math.Sqrt(float64(sum))) == correctly rounded single sqrt (53 >= 2*24+2 bits)
+    __device__ __forceinline__ float finish() const { return __fsqrt_rn(sum()); }
+};
+template <> struct ExactAcc<METRIC_DOT> {
+    float s[4];
+    __device__ __forceinline__ void init() { s[0] = s[1] = s[2] = s[3] = 0.f; }
+    __device__ __forceinline__ void add(int lane, float a, float b) {
+        s[lane] = __fadd_rn(s[lane], __fmul_rn(a, b));
+    }
+    // raw similarity; callers negate it when it is used as a distance
+    __device__ __forceinline__ float finish() const {
+        return __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[1]), s[2]), s[3]);
+    }
+};
+template <> struct ExactAcc<METRIC_COSINE> {
+    float d[4], na[4], nb[4];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[i] = na[i] = nb[i] = 0.f;
+    }
+    __device__ __forceinline__ void add(int lane, float a, float b) {
+        d[lane] = __fadd_rn(d[lane], __fmul_rn(a, b));
+        na[lane] = __fadd_rn(na[lane], __fmul_rn(a, a));
+        nb[lane] = __fadd_rn(nb[lane], __fmul_rn(b, b));
+    }
+    __device__ __forceinline__ float finish() const {
+        float dot = __fadd_rn(__fadd_rn(__fadd_rn(d[0], d[1]), d[2]), d[3]);
+        float a = __fadd_rn(__fadd_rn(__fadd_rn(na[0], na[1]), na[2]), na[3]);
+        float b = __fadd_rn(__fadd_rn(__fadd_rn(nb[0], nb[1]), nb[2]), nb[3]);
+        if (a == 0.f || b == 0.f) return 1.0f;  // simd.go:446-448
+        float den = (float)sqrt((double)a * (double)b);
+        return __fsub_rn(1.0f, __fdiv_rn(dot, den));
+    }
+};
+
+// Exact distance between a query held as floats (shared or global memory) and one row of T.
+// `vec_ok` = row pointer 16-byte aligned and dim a multiple of Elem<T>::kVec.
+template <typename T, int METRIC>
+__device__ __forceinline__ float exact_pair(const float* __restrict__ q, const T* __restrict__ row, int dim,
+                                            bool vec_ok) {
+    ExactAcc<METRIC> acc;
+    acc.init();
+    constexpr int V = Elem<T>::kVec;
+    int i = 0;
+    if (vec_ok) {
+        const uint4* rv = reinterpret_cast<const uint4*>(row);
+        const int nv = dim / V;
+        for (int v = 0; v < nv; v++) {
+            uint4 raw = __ldg(rv + v);
+            float x[V];
+            unpack16<T>(raw, x);
+#pragma unroll
+            for (int e = 0; e < V; e++) acc.add(e & 3, q[i + e], x[e]);
+            i += V;
+        }
+    } else {
+        for (; i <= dim - 4; i += 4) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc.add(e, q[i + e], Elem<T>::widen(row[i + e]));
+        }
+    }
+    for (; i < dim; i++) acc.add(0, q[i], Elem<T>::widen(row[i]));
+    return acc.finish();
+}
+
+// SQ8: squared L2 over uint8 as int32, returned as float32(int32) (internal/simd/sq8.go:45-66).
+__device__ __forceinline__ float exact_sq8(const float* __restrict__ q, const uint8_t* __restrict__ row, int dim) {
+    int32_t sum = 0;
+    for (int i = 0; i < dim; i++) {
+        int32_t d = (int32_t)q[i] - (int32_t)row[i];
+        sum += d * d;
+    }
+    return (float)sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bitonic sorts over u64 keys in shared memory (ascending).  n must be a power of two.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t* a, int n, int lane) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < (n >> 1); t += 32) {
+                int lo = ((t / stride) * (stride << 1)) + (t % stride);
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                uint64_t x = a[lo], y = a[hi];
+                if ((x > y) == up) { a[lo] = y; a[hi] = x; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* a, int n) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                int lo = ((t / stride) * (stride << 1)) + (t % stride);
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                uint64_t x = a[lo], y = a[hi];
+                if ((x > y) == up) { a[lo] = y; a[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__host__ __device__ __forceinline__ int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace lb

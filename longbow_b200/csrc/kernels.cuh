@@ -1,0 +1,91 @@
+// kernels.cuh -- host-side launch interface between api.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace lb {
+
+void count_launch();  // api.cu: process-wide launch counter (bench evidence)
+
+struct ScanArgs {
+    int dtype, metric;
+    const void* db;          // [n_rows][dim] row-major, element type = dtype
+    const float* aux;        // per-row |x|^2 (L2) or 1/|x| (cosine); may be null for dot
+    uint32_t n_rows;
+    int dim;
+    const void* queries;     // [nq][dim], same dtype
+    int nq;
+    const uint32_t* tomb;    // dense bitmaps viewed as 32-bit words (little endian == u64 layout)
+    uint32_t tomb_bits;
+    const uint32_t* allow;
+    int kc;                  // candidates kept per (part, query)
+    int cap;                 // per-query candidate buffer capacity (power of two >= kc + TN)
+    int tq;                  // queries per CTA: 64, 32 or 16
+    int parts;
+    uint32_t rows_per_part;  // multiple of 128
+    uint64_t* partial;       // [parts][nq][kc]
+};
+
+struct RescoreArgs {
+    int dtype, metric;
+    const void* db;
+    uint32_t n_rows;
+    int dim;
+    const void* queries;
+    int nq;
+    const uint64_t* packed;  // [nq][c] packed candidates, or null
+    const uint32_t* ids32;   // [nq][c] raw VectorIDs, or null
+    int c, k;
+    const uint32_t* tomb;
+    uint32_t tomb_bits;
+    const uint32_t* allow;
+    int64_t id_base;
+    float* out_d;            // [nq][k]
+    int64_t* out_l;          // [nq][k]
+    int negate_dot;          // 1: dot returned as a distance (negated)
+};
+
+size_t dense_scan_simt_smem(int tq, int cap);
+cudaError_t launch_dense_scan_simt(const ScanArgs& a, cudaStream_t st);
+cudaError_t launch_row_aux(int dtype, const void* db, int64_t n, int dim, int metric, float* aux, int64_t row0,
+                           cudaStream_t st);
+cudaError_t launch_merge_partials(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged,
+                                  cudaStream_t st);
+cudaError_t launch_rescore(const RescoreArgs& a, cudaStream_t st);
+cudaError_t launch_batch_flat(int metric, int dtype, const void* db, int64_t n, int dim, const void* query,
+                              float* out, int negate_dot, cudaStream_t st);
+cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_partial, uint64_t* scratch_merged,
+                            int64_t* out_idx, float* out_d, cudaStream_t st);
+cudaError_t launch_merge_topk(const float* in_d, const int64_t* in_l, int parts, int nq, int k_in, int k,
+                              float* out_d, int64_t* out_l, cudaStream_t st);
+
+// ---- PQ (kernels_pq.cu)
+struct PqScanArgs {
+    const uint8_t* codes;    // [n][M] row-major
+    uint32_t n_rows;
+    int M;
+    const float* luts;       // [nq][M*256]
+    int nq;
+    const uint32_t* tomb;
+    uint32_t tomb_bits;
+    const uint32_t* allow;
+    int kc, cap;
+    int parts;
+    uint32_t rows_per_part;
+    uint64_t* partial;       // [parts][nq][kc]
+};
+cudaError_t launch_adc_lut(const float* codebooks, int M, int K, int sub, const float* queries, int nq, float* luts,
+                           cudaStream_t st);
+cudaError_t launch_adc_scan(const PqScanArgs& a, cudaStream_t st);
+cudaError_t launch_adc_batch(const float* table, const uint8_t* codes, int M, int64_t n, float* out, cudaStream_t st);
+cudaError_t launch_pq_encode(const float* codebooks, int M, int K, int sub, const float* vecs, int64_t n,
+                             uint8_t* codes, cudaStream_t st);
+cudaError_t launch_unpack_topk(const uint64_t* merged, int nq, int kc, int k, int64_t id_base, float* out_d,
+                               int64_t* out_l, cudaStream_t st);
+
+// ---- predicates (kernels_filter.cu)
+cudaError_t launch_filter_i64(const int64_t* col, int64_t n, int op, int64_t val, int and_into, uint32_t* bitmap,
+                              cudaStream_t st);
+cudaError_t launch_filter_f32(const float* col, int64_t n, int op, float val, int and_into, uint32_t* bitmap,
+                              cudaStream_t st);
+
+}  // namespace lb

@@ -1,0 +1,586 @@
+// kernels_dense.cu -- dense (uncompressed) distance + fused top-k kernels, SIMT path.
+//
+// Stages of a dense search:
+//   S1 coarse scan   : tile of queries x stream of DB rows -> approximate ranking key per pair,
+//                      fused per-query top-kc selection in shared memory (no distance matrix
+//                      in HBM) -> partial[part][q][kc] packed (key,id)
+//   S2 merge         : per query, parts*kc -> kc candidates
+//   S3 exact re-score: candidates re-evaluated with the reference's own arithmetic
+//                      (common.cuh ExactAcc), sorted by (distance,id) -> top-k
+// S1 here is the general SIMT kernel (any dim, any dtype, unaligned rows).  The tcgen05
+// kernels in dense_tc.cu produce the same partial[] format for the aligned fp16 / int8 cases.
+#include "kernels.cuh"
+
+namespace lb {
+
+// ---------------------------------------------------------------------------------------------
+// Row auxiliaries used by coarse keys: aux[r] = |x_r|^2 (L2) or 1/|x_r| (cosine; 0 for a
+// zero row, which makes the coarse key 0 == cosine distance 1.0, simd.go:446-448).
+// One warp per row.  Accuracy only affects the coarse ranking, never a returned value.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void row_aux_kernel(const T* __restrict__ db, int64_t n, int dim, int metric,
+                               float* __restrict__ aux, int64_t row0) {
+    int64_t r = row0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const T* row = db + r * dim;
+    float s = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        float v = Elem<T>::widen(row[i]);
+        s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) aux[r] = (metric == METRIC_COSINE) ? (s > 0.f ? rsqrtf(s) : 0.f) : s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// S1: SIMT coarse scan with fused selection.
+//   grid  = (parts, ceil(nq / TQ)); block = 256 threads
+//   tile  = TQ queries x TN rows, K chunks of KC elements staged (widened to fp32) in smem
+//   thread micro-tile = (TQ/16) queries x 8 rows
+// ---------------------------------------------------------------------------------------------
+constexpr int TN = 128;
+constexpr int KC = 32;
+constexpr int NT = 256;
+
+template <typename T, int METRIC, int TQ>
+__global__ void __launch_bounds__(NT)
+dense_scan_simt(const T* __restrict__ db, const float* __restrict__ aux, uint32_t n_rows, int dim,
+                const T* __restrict__ queries, int nq, const uint32_t* __restrict__ tomb,
+                uint32_t tomb_bits, const uint32_t* __restrict__ allow, int kc, int cap,
+                uint32_t rows_per_part, uint64_t* __restrict__ partial) {
+    constexpr int MQ = TQ / 16;  // queries per thread
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* As = reinterpret_cast<float*>(smem_raw);  // [KC][TQ]
+    float* Bs = As + KC * TQ;                        // [KC][TN]
+    float* tau = Bs + KC * TN;                       // [TQ]
+    int* cnt = reinterpret_cast<int*>(tau + TQ);     // [TQ]
+    uint64_t* cand = reinterpret_cast<uint64_t*>(cnt + TQ);  // [TQ][cap]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.y * TQ;
+    const uint32_t row_begin = blockIdx.x * rows_per_part;
+    const uint32_t row_end = min(n_rows, row_begin + rows_per_part);
+
+    for (int i = tid; i < TQ; i += NT) { tau[i] = INFINITY; cnt[i] = 0; }
+
+    constexpr int V = Elem<T>::kVec;
+    const bool vec_ok = (dim % V == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
+    __syncthreads();
+
+    for (uint32_t r0 = row_begin; r0 < row_end; r0 += TN) {
+        float acc[MQ][8];
+#pragma unroll
+        for (int i = 0; i < MQ; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+
+        for (int k0 = 0; k0 < dim; k0 += KC) {
+            // ---- stage A (queries) and B (rows) chunks, widened, transposed to [kk][row]
+            if (vec_ok) {
+                constexpr int VPC = KC / V;  // 16-byte vectors per row chunk
+                for (int idx = tid; idx < TQ * VPC; idx += NT) {
+                    int q = idx % TQ, kv = idx / TQ;
+                    int kk = kv * V;
+                    float x[V];
+                    if (q0 + q < nq && k0 + kk < dim) {
+                        uint4 raw = __ldg(reinterpret_cast<const uint4*>(queries + (size_t)(q0 + q) * dim + k0 + kk));
+                        unpack16<T>(raw, x);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < V; e++) x[e] = 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < V; e++) As[(kk + e) * TQ + q] = x[e];
+                }
+                for (int idx = tid; idx < TN * VPC; idx += NT) {
+                    int r = idx % TN, kv = idx / TN;
+                    int kk = kv * V;
+                    float x[V];
+                    if (r0 + r < row_end && k0 + kk < dim) {
+                        uint4 raw = __ldg(reinterpret_cast<const uint4*>(db + (size_t)(r0 + r) * dim + k0 + kk));
+                        unpack16<T>(raw, x);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < V; e++) x[e] = 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < V; e++) Bs[(kk + e) * TN + r] = x[e];
+                }
+            } else {
+                for (int idx = tid; idx < TQ * KC; idx += NT) {
+                    int kk = idx % KC, q = idx / KC;
+                    float v = 0.f;
+                    if (q0 + q < nq && k0 + kk < dim) v = Elem<T>::widen(queries[(size_t)(q0 + q) * dim + k0 + kk]);
+                    As[kk * TQ + q] = v;
+                }
+                for (int idx = tid; idx < TN * KC; idx += NT) {
+                    int kk = idx % KC, r = idx / KC;
+                    float v = 0.f;
+                    if (r0 + r < row_end && k0 + kk < dim) v = Elem<T>::widen(db[(size_t)(r0 + r) * dim + k0 + kk]);
+                    Bs[kk * TN + r] = v;
+                }
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int kk = 0; kk < KC; kk++) {
+                float a[MQ], b[8];
+                if constexpr (MQ == 4) {
+                    float4 av = *reinterpret_cast<const float4*>(&As[kk * TQ + ty * 4]);
+                    a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < MQ; i++) a[i] = As[kk * TQ + ty * MQ + i];
+                }
+                float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk * TN + tx * 4]);
+                float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk * TN + 64 + tx * 4]);
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+                b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+                for (int i = 0; i < MQ; i++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if constexpr (METRIC == METRIC_L2) {
+                            float d = a[i] - b[j];  // difference form: no cancellation near d = 0
+                            acc[i][j] = fmaf(d, d, acc[i][j]);
+                        } else {
+                            acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                        }
+                    }
+            }
+            __syncthreads();
+        }
+
+        // ---- fused selection: threshold filter, rare append to the query's candidate buffer
+#pragma unroll
+        for (int i = 0; i < MQ; i++) {
+            const int ql = ty * MQ + i;
+            if (q0 + ql >= nq) continue;
+            const float t = tau[ql];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t row = r0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                if (row >= row_end) continue;
+                float key;
+                if constexpr (METRIC == METRIC_L2) key = acc[i][j];
+                else if constexpr (METRIC == METRIC_COSINE) key = -acc[i][j] * __ldg(aux + row);
+                else key = -acc[i][j];
+                if (key < t) {
+                    if (tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) continue;
+                    if (allow != nullptr && !bit_set(allow, row)) continue;
+                    int pos = atomicAdd(&cnt[ql], 1);
+                    if (pos < cap) cand[(size_t)ql * cap + pos] = pack_key(key, row);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- compaction: keep the kc best, tighten the threshold
+        for (int ql = warp; ql < TQ; ql += NT / 32) {
+            int c = min(cnt[ql], cap);
+            if (c > cap - TN) {
+                uint64_t* buf = cand + (size_t)ql * cap;
+                int n2 = next_pow2(c);
+                for (int t2 = c + lane; t2 < n2; t2 += 32) buf[t2] = kInvalid;
+                __syncwarp();
+                warp_bitonic_sort(buf, n2, lane);
+                if (lane == 0) {
+                    int keep = min(c, kc);
+                    cnt[ql] = keep;
+                    tau[ql] = (c >= kc) ? key_of(buf[kc - 1]) : INFINITY;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- final compaction + write-out
+    for (int ql = warp; ql < TQ; ql += NT / 32) {
+        if (q0 + ql >= nq) continue;
+        int c = min(cnt[ql], cap);
+        uint64_t* buf = cand + (size_t)ql * cap;
+        int n2 = next_pow2(max(c, 2));
+        for (int t2 = c + lane; t2 < n2; t2 += 32) buf[t2] = kInvalid;
+        __syncwarp();
+        warp_bitonic_sort(buf, n2, lane);
+        uint64_t* out = partial + ((size_t)blockIdx.x * nq + (q0 + ql)) * kc;
+        for (int t2 = lane; t2 < kc; t2 += 32) out[t2] = (t2 < c) ? buf[t2] : kInvalid;
+    }
+}
+
+size_t dense_scan_simt_smem(int tq, int cap) {
+    return (size_t)(KC * tq + KC * TN + 2 * tq) * 4 + (size_t)tq * cap * 8;
+}
+
+template <typename T, int METRIC, int TQ>
+static cudaError_t launch_scan_tq(const ScanArgs& a, cudaStream_t st) {
+    auto kern = dense_scan_simt<T, METRIC, TQ>;
+    size_t smem = dense_scan_simt_smem(TQ, a.cap);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(a.parts, (a.nq + TQ - 1) / TQ);
+    kern<<<grid, NT, smem, st>>>((const T*)a.db, a.aux, a.n_rows, a.dim, (const T*)a.queries, a.nq, a.tomb,
+                                 a.tomb_bits, a.allow, a.kc, a.cap, a.rows_per_part, a.partial);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename T, int METRIC>
+static cudaError_t launch_scan_metric(const ScanArgs& a, cudaStream_t st) {
+    switch (a.tq) {
+        case 64: return launch_scan_tq<T, METRIC, 64>(a, st);
+        case 32: return launch_scan_tq<T, METRIC, 32>(a, st);
+        default: return launch_scan_tq<T, METRIC, 16>(a, st);
+    }
+}
+
+template <typename T>
+static cudaError_t launch_scan_dtype(const ScanArgs& a, cudaStream_t st) {
+    switch (a.metric) {
+        case METRIC_L2: return launch_scan_metric<T, METRIC_L2>(a, st);
+        case METRIC_COSINE: return launch_scan_metric<T, METRIC_COSINE>(a, st);
+        default: return launch_scan_metric<T, METRIC_DOT>(a, st);
+    }
+}
+
+cudaError_t launch_dense_scan_simt(const ScanArgs& a, cudaStream_t st) {
+    switch (a.dtype) {
+        case DT_F32: return launch_scan_dtype<float>(a, st);
+        case DT_F16: return launch_scan_dtype<__half>(a, st);
+        case DT_I8: return launch_scan_dtype<int8_t>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_row_aux(int dtype, const void* db, int64_t n, int dim, int metric, float* aux, int64_t row0,
+                           cudaStream_t st) {
+    if (n <= row0) return cudaSuccess;
+    int64_t rows = n - row0;
+    unsigned blocks = (unsigned)((rows + 7) / 8);
+    switch (dtype) {
+        case DT_F32: row_aux_kernel<float><<<blocks, 256, 0, st>>>((const float*)db, n, dim, metric, aux, row0); break;
+        case DT_F16: row_aux_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)db, n, dim, metric, aux, row0); break;
+        case DT_I8: row_aux_kernel<int8_t><<<blocks, 256, 0, st>>>((const int8_t*)db, n, dim, metric, aux, row0); break;
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// S2: merge partial lists.  grid = nq, block = 256.  Streams parts*kc entries through a
+// 4096-entry shared buffer, keeping the best kc after each refill.
+// ---------------------------------------------------------------------------------------------
+constexpr int MERGE_BUF = 4096;
+
+__global__ void __launch_bounds__(256)
+merge_partials_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int kc,
+                      uint64_t* __restrict__ merged) {
+    __shared__ uint64_t buf[MERGE_BUF];
+    const int q = blockIdx.x;
+    const int total = parts * kc;
+    int have = 0;  // entries [0,have) hold the best so far (sorted)
+    int next = 0;  // next flat entry index to read
+    while (next < total || have == 0) {
+        int room = MERGE_BUF - have;
+        int take = min(room, total - next);
+        for (int t = threadIdx.x; t < take; t += blockDim.x) {
+            int e = next + t;
+            int p = e / kc, j = e % kc;
+            buf[have + t] = partial[((size_t)p * nq + q) * kc + j];
+        }
+        int filled = have + take;
+        int n2 = next_pow2(max(filled, 2));
+        for (int t = filled + threadIdx.x; t < n2; t += blockDim.x) buf[t] = kInvalid;
+        __syncthreads();
+        block_bitonic_sort(buf, n2);
+        have = min(filled, kc);
+        next += take;
+        if (take == 0) break;
+    }
+    for (int t = threadIdx.x; t < kc; t += blockDim.x)
+        merged[(size_t)q * kc + t] = (t < have) ? buf[t] : kInvalid;
+}
+
+cudaError_t launch_merge_partials(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged,
+                                  cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    merge_partials_kernel<<<nq, 256, 0, st>>>(partial, parts, nq, kc, merged);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// S3: exact re-score of candidate ids + final (distance,id) sort -> top-k.
+//   grid = nq; block = next_pow2(c) threads (>= 32, <= 1024); one thread per candidate.
+// Candidate sources:
+//   packed   : u64 (key,id) list from S2 (kInvalid = empty)
+//   ids32    : uint32 VectorIDs from the host graph walk (re-rank path); out-of-range,
+//              tombstoned or predicate-failing ids are dropped here (parallel_search.go:183-229)
+// Also evaluates the certification test for the coarse path: the k-th exact
+// distance must be below the coarse bound of everything that was NOT a candidate.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int METRIC>
+__global__ void rescore_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T* __restrict__ queries,
+                               int nq, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ids32,
+                               int c, int k, const uint32_t* __restrict__ tomb, uint32_t tomb_bits,
+                               const uint32_t* __restrict__ allow, int64_t id_base, float* __restrict__ out_d,
+                               int64_t* __restrict__ out_l, int negate_dot) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n2 = blockDim.x;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [n2]
+    float* qf = reinterpret_cast<float*>(keys + n2);          // [dim]
+    const int q = blockIdx.x;
+    const T* qrow = queries + (size_t)q * dim;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) qf[i] = Elem<T>::widen(qrow[i]);
+    __syncthreads();
+
+    uint64_t mine = kInvalid;
+    if ((int)threadIdx.x < c) {
+        uint32_t id = 0xffffffffu;
+        bool ok = false;
+        if (packed != nullptr) {
+            uint64_t p = packed[(size_t)q * c + threadIdx.x];
+            if (p != kInvalid) { id = id_of(p); ok = id < n_rows; }
+        } else {
+            id = ids32[(size_t)q * c + threadIdx.x];
+            ok = id < n_rows;
+            if (ok && allow != nullptr && !bit_set(allow, id)) ok = false;
+            if (ok && tomb != nullptr && id < tomb_bits && bit_set(tomb, id)) ok = false;
+        }
+        if (ok) {
+            const T* row = db + (size_t)id * dim;
+            const bool vec_ok = (dim % Elem<T>::kVec == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+            float d = exact_pair<T, METRIC>(qf, row, dim, vec_ok);
+            if (METRIC == METRIC_DOT && negate_dot) d = -d;
+            if (d < INFINITY) mine = pack_key(d, id);  // NaN / +Inf are never returned
+        }
+    }
+    keys[threadIdx.x] = mine;
+    __syncthreads();
+    block_bitonic_sort(keys, n2);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        uint64_t p = (j < n2) ? keys[j] : kInvalid;
+        bool valid = p != kInvalid;
+        out_d[(size_t)q * k + j] = valid ? key_of(p) : 3.402823466e+38f;
+        out_l[(size_t)q * k + j] = valid ? (int64_t)id_of(p) + id_base : -1;
+    }
+}
+
+template <typename T>
+static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
+    int n2 = next_pow2(max(a.c, 32));
+    if (n2 > 1024) return cudaErrorInvalidValue;
+    size_t smem = (size_t)n2 * 8 + (size_t)a.dim * 4;
+#define LB_RS(M)                                                                                            \
+    {                                                                                                       \
+        auto kern = rescore_kernel<T, M>;                                                                   \
+        if (smem > 48 * 1024) {                                                                             \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                 \
+        }                                                                                                   \
+        kern<<<a.nq, n2, smem, st>>>((const T*)a.db, a.n_rows, a.dim, (const T*)a.queries, a.nq, a.packed,  \
+                                     a.ids32, a.c, a.k, a.tomb, a.tomb_bits, a.allow, a.id_base, a.out_d,   \
+                                     a.out_l, a.negate_dot);                                                \
+    }
+    switch (a.metric) {
+        case METRIC_L2: LB_RS(METRIC_L2) break;
+        case METRIC_COSINE: LB_RS(METRIC_COSINE) break;
+        default: LB_RS(METRIC_DOT) break;
+    }
+#undef LB_RS
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rescore(const RescoreArgs& a, cudaStream_t st) {
+    if (a.nq <= 0) return cudaSuccess;
+    switch (a.dtype) {
+        case DT_F32: return launch_rescore_t<float>(a, st);
+        case DT_F16: return launch_rescore_t<__half>(a, st);
+        case DT_I8: return launch_rescore_t<int8_t>(a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One query x n rows -> n exact distances (simd.*DistanceBatch* semantics: dot is RAW here).
+// One thread per row; the query sits in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int METRIC>
+__global__ void batch_flat_kernel(const T* __restrict__ db, int64_t n, int dim, const T* __restrict__ query,
+                                  float* __restrict__ out, int negate_dot) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* qf = reinterpret_cast<float*>(smem_raw);
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) qf[i] = Elem<T>::widen(query[i]);
+    __syncthreads();
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const T* row = db + r * dim;
+    const bool vec_ok = (dim % Elem<T>::kVec == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    float d = exact_pair<T, METRIC>(qf, row, dim, vec_ok);
+    if (METRIC == METRIC_DOT && negate_dot) d = -d;
+    out[r] = d;
+}
+
+__global__ void batch_flat_sq8_kernel(const uint8_t* __restrict__ db, int64_t n, int dim,
+                                      const uint8_t* __restrict__ query, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* qf = reinterpret_cast<float*>(smem_raw);
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) qf[i] = (float)query[i];
+    __syncthreads();
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    out[r] = exact_sq8(qf, db + r * dim, dim);
+}
+
+cudaError_t launch_batch_flat(int metric, int dtype, const void* db, int64_t n, int dim, const void* query,
+                              float* out, int negate_dot, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    size_t smem = (size_t)dim * 4;
+#define LB_BF(T, M) batch_flat_kernel<T, M><<<blocks, 128, smem, st>>>((const T*)db, n, dim, (const T*)query, out, negate_dot)
+    if (dtype == DT_U8) {
+        if (metric != METRIC_L2) return cudaErrorInvalidValue;
+        batch_flat_sq8_kernel<<<blocks, 128, smem, st>>>((const uint8_t*)db, n, dim, (const uint8_t*)query, out);
+    } else if (dtype == DT_F32) {
+        if (metric == METRIC_L2) LB_BF(float, METRIC_L2); else if (metric == METRIC_COSINE) LB_BF(float, METRIC_COSINE); else LB_BF(float, METRIC_DOT);
+    } else if (dtype == DT_F16) {
+        if (metric == METRIC_L2) LB_BF(__half, METRIC_L2); else if (metric == METRIC_COSINE) LB_BF(__half, METRIC_COSINE); else LB_BF(__half, METRIC_DOT);
+    } else if (dtype == DT_I8) {
+        if (metric == METRIC_L2) LB_BF(int8_t, METRIC_L2); else if (metric == METRIC_DOT) LB_BF(int8_t, METRIC_DOT); else return cudaErrorInvalidValue;
+    } else {
+        return cudaErrorInvalidValue;
+    }
+#undef LB_BF
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// select_k over one distance array (Arrow compute "select_k_neighbors"), and the shard merge.
+// Both reduce to: build packed (distance, index) keys, block-sort chunks, keep k.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+select_k_chunks_kernel(const float* __restrict__ d, int64_t n, int kc, uint64_t* __restrict__ partial) {
+    __shared__ uint64_t buf[MERGE_BUF];
+    int64_t base = (int64_t)blockIdx.x * MERGE_BUF;
+    for (int t = threadIdx.x; t < MERGE_BUF; t += blockDim.x) {
+        int64_t i = base + t;
+        uint64_t p = kInvalid;
+        if (i < n) {
+            float v = d[i];
+            if (v == v) p = pack_key(v, (uint32_t)i);
+        }
+        buf[t] = p;
+    }
+    __syncthreads();
+    block_bitonic_sort(buf, MERGE_BUF);
+    for (int t = threadIdx.x; t < kc; t += blockDim.x) partial[(size_t)blockIdx.x * kc + t] = buf[t];
+}
+
+__global__ void unpack_topk_kernel(const uint64_t* __restrict__ merged, int nq, int kc, int k, int64_t id_base,
+                                   float* __restrict__ out_d, int64_t* __restrict__ out_l) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * k) return;
+    int q = i / k, j = i % k;
+    uint64_t p = (j < kc) ? merged[(size_t)q * kc + j] : kInvalid;
+    bool valid = p != kInvalid;
+    if (out_d) out_d[i] = valid ? key_of(p) : 3.402823466e+38f;
+    out_l[i] = valid ? (int64_t)id_of(p) + id_base : -1;
+}
+
+cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_partial, uint64_t* scratch_merged,
+                            int64_t* out_idx, float* out_d, cudaStream_t st) {
+    int kc = k;
+    int chunks = (int)((n + MERGE_BUF - 1) / MERGE_BUF);
+    if (chunks == 0) chunks = 1;
+    select_k_chunks_kernel<<<chunks, 256, 0, st>>>(d, n, kc, scratch_partial);
+    count_launch();
+    merge_partials_kernel<<<1, 256, 0, st>>>(scratch_partial, chunks, 1, kc, scratch_merged);
+    count_launch();
+    unpack_topk_kernel<<<(k + 127) / 128, 128, 0, st>>>(scratch_merged, 1, kc, k, 0, out_d, out_idx);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// Shard merge: (distance,label) lists with int64 labels.  Lists are short (parts * k_in), so one
+// block per query sorts (distance, slot) keys and then maps slots back to labels.
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(const float* __restrict__ in_d, const int64_t* __restrict__ in_l, int parts, int nq, int k_in,
+                  int k, float* __restrict__ out_d, int64_t* __restrict__ out_l) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int total = parts * k_in;
+    const int n2 = next_pow2(max(total, 2));
+    uint64_t* hi = reinterpret_cast<uint64_t*>(smem_raw);  // [n2] (ordered distance << 32 | slot)
+    const int q = blockIdx.x;
+    // Two-key order (distance, label): labels are int64, so sort by distance first with the slot as
+    // payload, then fix ties by label with a rank pass over equal-distance runs (runs are tiny).
+    for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+        uint64_t p = kInvalid;
+        if (t < total) {
+            int pp = t / k_in, j = t % k_in;
+            size_t o = ((size_t)pp * nq + q) * k_in + j;
+            if (in_l[o] >= 0) p = ((uint64_t)float_to_ordered(in_d[o]) << 32) | (uint32_t)t;
+        }
+        hi[t] = p;
+    }
+    __syncthreads();
+    block_bitonic_sort(hi, n2);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        uint64_t p = (j < n2) ? hi[j] : kInvalid;
+        if (p == kInvalid) {
+            out_d[(size_t)q * k + j] = 3.402823466e+38f;
+            out_l[(size_t)q * k + j] = -1;
+            continue;
+        }
+        // rank within the run of equal distances by label
+        uint32_t dkey = (uint32_t)(p >> 32);
+        int lo = j, hi_i = j;
+        while (lo > 0 && (uint32_t)(hi[lo - 1] >> 32) == dkey) lo--;
+        while (hi_i + 1 < n2 && hi[hi_i + 1] != kInvalid && (uint32_t)(hi[hi_i + 1] >> 32) == dkey) hi_i++;
+        auto label_of = [&](int pos) {
+            int t = (int)(uint32_t)hi[pos];
+            int pp = t / k_in, jj = t % k_in;
+            return in_l[((size_t)pp * nq + q) * k_in + jj];
+        };
+        int64_t my = label_of(j);
+        if (lo != hi_i) {
+            // the (j - lo)-th smallest label of the run
+            int want = j - lo;
+            for (int a = lo; a <= hi_i; a++) {
+                int64_t la = label_of(a);
+                int rank = 0;
+                for (int b = lo; b <= hi_i; b++) {
+                    int64_t lb_ = label_of(b);
+                    rank += (lb_ < la) || (lb_ == la && b < a);
+                }
+                if (rank == want) { my = la; break; }
+            }
+        }
+        out_d[(size_t)q * k + j] = ordered_to_float(dkey);
+        out_l[(size_t)q * k + j] = my;
+    }
+}
+
+cudaError_t launch_merge_topk(const float* in_d, const int64_t* in_l, int parts, int nq, int k_in, int k,
+                              float* out_d, int64_t* out_l, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    int total = parts * k_in;
+    int n2 = next_pow2(total < 2 ? 2 : total);
+    size_t smem = (size_t)n2 * 8;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    merge_topk_kernel<<<nq, 256, smem, st>>>(in_d, in_l, parts, nq, k_in, k, out_d, out_l);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace lb

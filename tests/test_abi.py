@@ -1,0 +1,109 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/longbow_b200.h declares, and fails loudly (no CPU fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "longbow_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:lb|faiss_gpu)_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    from longbow_b200 import _lib
+    names = _declared()
+    assert len(names) >= 40
+    lib = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_six_faiss_symbols_present():
+    # internal/gpu/faiss_gpu.go:16-21
+    from longbow_b200 import _lib
+    lib = _lib.load()
+    for n in ("faiss_gpu_resources_new", "faiss_gpu_resources_free", "faiss_gpu_index_flat_l2_new",
+              "faiss_gpu_index_flat_l2_free", "faiss_gpu_index_add", "faiss_gpu_index_search"):
+        assert getattr(lib, n) is not None
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_gpu():
+    from longbow_b200 import _lib, gpu
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.lb_index_create(0, 128, 0, 0, C.byref(h))
+    assert rc == _lib.LB_ERR_NO_DEVICE and not h.value
+    assert b"no CPU fallback" in lib.lb_last_error()
+    assert lib.faiss_gpu_resources_new(0) is None
+    with pytest.raises(RuntimeError, match="failed to initialize GPU resources"):
+        gpu.NewIndexWithConfig(gpu.GPUConfig(0, 128))
+    with pytest.raises(_lib.LongbowError):
+        gpu.DenseIndex(128)
+
+
+def test_argument_validation_before_device():
+    from longbow_b200 import _lib, gpu
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.lb_index_create(0, -1, 0, 0, C.byref(h)) == _lib.LB_ERR_INVALID
+    assert lib.lb_index_create(0, 16, 2, 1, C.byref(h)) == _lib.LB_ERR_UNSUPPORTED  # int8 cosine: no kernel
+    assert lib.lb_index_create(0, 16, 9, 0, C.byref(h)) == _lib.LB_ERR_UNSUPPORTED
+    assert lib.lb_pq_create(0, b"\0" * 4, 4, C.byref(h)) == _lib.LB_ERR_INVALID  # persistence.go:40
+    with pytest.raises(ValueError, match="dimension must be positive"):  # gpu_test.go:49-55
+        gpu.NewIndexWithConfig(gpu.GPUConfig(0, -1))
+    lib.lb_index_free(None)  # no-op
+    lib.faiss_gpu_index_flat_l2_free(None)
+    lib.faiss_gpu_resources_free(None)
+
+
+def test_pack_bitmap_layout():
+    from longbow_b200.gpu import pack_bitmap
+    m = np.zeros(130, bool)
+    m[[0, 63, 64, 129]] = True
+    w = pack_bitmap(m)
+    assert w.dtype == np.uint64 and w.size == 3
+    assert w[0] == (1 | (1 << 63)) and w[1] == 1 and w[2] == 2
+
+
+def test_pq_blob_roundtrip_host():
+    # internal/pq/persistence.go:15-80 format; parsing errors surface before any device work
+    import struct
+    from longbow_b200 import pq
+    with pytest.raises(ValueError, match="too short"):
+        pq.PQEncoder.Deserialize(b"123")
+    with pytest.raises(ValueError, match="invalid PQ parameters"):
+        pq.PQEncoder.Deserialize(struct.pack("<III", 10, 3, 256) + b"\0" * 16)
+    with pytest.raises(ValueError, match="size mismatch"):
+        pq.PQEncoder.Deserialize(struct.pack("<III", 8, 2, 256) + b"\0" * 16)
+
+
+def test_simd_mirror_validation():
+    from longbow_b200 import simd
+    q = np.zeros(4, np.float32)
+    with pytest.raises(simd.SimdError, match="results length mismatch"):
+        simd.EuclideanDistanceBatchFlat(q, np.zeros(8, np.float32), 2, 4, np.zeros(3, np.float32))
+    with pytest.raises(simd.SimdError, match="flatVectors too small"):
+        simd.EuclideanDistanceBatchFlat(q, np.zeros(4, np.float32), 2, 4, np.zeros(2, np.float32))
+    with pytest.raises(simd.SimdError, match="query dimension mismatch"):
+        simd.EuclideanDistanceBatchFlat(np.zeros(3, np.float32), np.zeros(8, np.float32), 2, 4, np.zeros(2, np.float32))
+    with pytest.raises(simd.SimdError, match="invalid m"):
+        simd.ADCDistanceBatch(np.zeros(256, np.float32), np.zeros(4, np.uint8), 0, np.zeros(1, np.float32))
+    simd.EuclideanDistanceBatchFlat(q, np.zeros(0, np.float32), 0, 4, np.zeros(0, np.float32))  # n == 0: no-op

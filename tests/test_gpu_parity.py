@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Run on the B200 box with ``pytest -m gpu``."""
+import threading
+
+import numpy as np
+import pytest
+
+from tests.util import assert_topk_equal, make_db, random_bitmap
+
+pytestmark = pytest.mark.gpu
+
+L2, COS, DOT = 0, 1, 2
+
+
+@pytest.fixture(scope="module")
+def lbgpu():
+    from longbow_b200 import gpu
+    return gpu
+
+
+COMBOS = [(np.float32, L2), (np.float32, COS), (np.float32, DOT),
+          (np.float16, L2), (np.float16, COS), (np.float16, DOT),
+          (np.int8, L2), (np.int8, DOT)]
+
+
+# ------------------------------------------------------------------ reference known answers via the drop-in ABI
+def test_faiss_abi_gpu_smoke_kat(lbgpu):
+    # internal/gpu/gpu_test.go:12-47
+    idx = lbgpu.NewIndexWithConfig(lbgpu.GPUConfig(DeviceID=0, Dimension=128))
+    vectors = (np.arange(128 * 10, dtype=np.float32) * np.float32(0.01))
+    idx.Add(list(range(10)), vectors)
+    ids, dist = idx.Search(vectors[:128], 5)
+    assert len(ids) == 5 and len(dist) == 5
+    assert ids[0] == 0 and dist[0] < 0.01
+    assert list(ids) == [0, 1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        idx.Search(vectors[:64], 5)
+    with pytest.raises(ValueError):
+        idx.Add([1], vectors[:100])
+    idx.Close()
+    idx.Close()  # idempotent, faiss_gpu.go:151-153
+    with pytest.raises(RuntimeError, match="closed"):
+        idx.Search(vectors[:128], 5)
+
+
+def test_simd_kats_on_gpu():
+    # internal/simd/simd_dispatch_test.go:56-132, simd_test.go:146-194
+    from longbow_b200 import simd
+    q = np.array([1, 2, 3, 4], np.float32)
+    out = np.zeros(2, np.float32)
+    simd.EuclideanDistanceBatch(q, [np.array([5, 6, 7, 8], np.float32), q.copy()], out)
+    assert out[0] == 8.0 and out[1] == 0.0
+    simd.DotProductBatch(q, [np.array([5, 6, 7, 8], np.float32)], out)
+    assert out[0] == 70.0
+    simd.CosineDistanceBatch(np.zeros(4, np.float32), [q], out)
+    assert out[0] == 1.0  # zero vector: exactly 1.0
+    simd.CosineDistanceBatch(q, [-q], out)
+    assert abs(out[0] - 2.0) <= 1e-5
+    o3 = np.zeros(3, np.float32)
+    simd.EuclideanDistanceBatch(q, [None, np.zeros(3, np.float32), q], o3)  # nil / wrong length -> MaxFloat32
+    assert o3[0] == simd.MaxFloat32 and o3[1] == simd.MaxFloat32 and o3[2] == 0.0
+    a = np.array([10, 20], np.int8)
+    b = np.array([[10, 30]], np.int8)
+    o1 = np.zeros(1, np.float32)
+    simd._flat(simd.MetricEuclidean, a, b, 1, 2, o1, 0)
+    assert o1[0] == 10.0
+    u = np.array([0, 255, 3], np.uint8)
+    simd.EuclideanDistanceSQ8Batch(u, [np.array([255, 0, 1], np.uint8)], o1)
+    assert o1[0] == float(255 * 255 * 2 + 4)
+
+
+# ------------------------------------------------------------------ dense brute force
+@pytest.mark.parametrize("dtype,metric", COMBOS)
+@pytest.mark.parametrize("n,dim,nq,k", [(5000, 128, 33, 10), (3000, 96, 70, 100), (700, 7, 5, 3), (1030, 33, 17, 10)])
+def test_dense_search_parity(lbgpu, oracle, dtype, metric, n, dim, nq, k):
+    rng = np.random.default_rng(1000 + n + dim + metric)
+    db = make_db(rng, n, dim, dtype)
+    q = make_db(rng, nq, dim, dtype)
+    if metric == COS and dtype != np.int8:
+        db[[3, n // 2, n - 1]] = 0  # zero rows: cosine distance exactly 1.0
+        q[0] = 0
+    idx = lbgpu.DenseIndex(dim, dtype, metric)
+    idx.add(db[: n // 3])
+    idx.add(db[n // 3:])  # two appends (growth path)
+    assert len(idx) == n
+    gd, gl = idx.search(q, k)
+    wd, wl = oracle.search(metric, db, q, k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, f"{dtype.__name__} metric={metric}")
+    idx.close()
+
+
+@pytest.mark.parametrize("dtype,metric", [(np.float32, L2), (np.float16, COS), (np.int8, DOT)])
+def test_dense_search_bitmaps(lbgpu, oracle, dtype, metric):
+    rng = np.random.default_rng(77)
+    n, dim, nq, k = 6000, 64, 40, 10
+    db, q = make_db(rng, n, dim, dtype), make_db(rng, nq, dim, dtype)
+    tomb = random_bitmap(rng, n, 0.05)
+    allow = random_bitmap(rng, n, 0.30)
+    idx = lbgpu.DenseIndex(dim, dtype, metric)
+    idx.add(db)
+    idx.set_tombstones(tomb)
+    gd, gl = idx.search(q, k, allow=allow)
+    wd, wl = oracle.search(metric, db, q, k, tomb=lbgpu.pack_bitmap(tomb), allow=lbgpu.pack_bitmap(allow))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "bitmaps")
+    assert not tomb[gl[gl >= 0]].any() and allow[gl[gl >= 0]].all()
+    # almost everything filtered: fewer than k survivors -> -1 / FLT_MAX padding
+    allow2 = np.zeros(n, bool)
+    allow2[[5, 17, 4000]] = True
+    idx.set_tombstones(None)
+    gd, gl = idx.search(q, k, allow=allow2)
+    wd, wl = oracle.search(metric, db, q, k, allow=lbgpu.pack_bitmap(allow2))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "sparse allow")
+    assert (gl[:, 3:] == -1).all() and (gd[:, 3:] == np.finfo(np.float32).max).all()
+    idx.close()
+
+
+def test_dense_ties_and_edges(lbgpu, oracle):
+    # duplicates: ties resolved by id (adaptive_index.go:200-211 keeps the lowest ids)
+    dim = 16
+    base = np.random.default_rng(5).random((50, dim), dtype=np.float32)
+    db = np.concatenate([base, base, base])  # every row three times
+    idx = lbgpu.DenseIndex(dim, np.float32, L2)
+    idx.add(db)
+    gd, gl = idx.search(base[:7], 6)
+    wd, wl = oracle.search(L2, db, base[:7], 6)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "ties")
+    assert (gl[:, 0] == np.arange(7)).all() and (gl[:, 1] == np.arange(7) + 50).all()
+    # k larger than the index
+    gd, gl = idx.search(base[:2], 200)
+    wd, wl = oracle.search(L2, db, base[:2], 200)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "k > n")
+    # empty query batch / empty index
+    d0, l0 = idx.search(np.zeros((0, dim), np.float32), 5)
+    assert d0.shape == (0, 5)
+    e = lbgpu.DenseIndex(dim, np.float32, L2)
+    d1, l1 = e.search(base[:3], 4)
+    assert (l1 == -1).all() and (d1 == np.finfo(np.float32).max).all()
+    e.close()
+    idx.close()
+
+
+def test_id_base_and_distances(lbgpu, oracle):
+    rng = np.random.default_rng(9)
+    db, q = make_db(rng, 900, 40, np.float32), make_db(rng, 4, 40, np.float32)
+    idx = lbgpu.DenseIndex(40, np.float32, L2)
+    idx.add(db)
+    idx.set_id_base(10_000_000_000)
+    gd, gl = idx.search(q, 5)
+    wd, wl = oracle.search(L2, db, q, 5, id_base=10_000_000_000)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "id_base")
+    assert np.array_equal(idx.distances(q[0]), oracle.batch_flat(L2, q[0], db))
+    idx.close()
+
+
+def test_concurrent_search_threads(lbgpu, oracle):
+    # faiss_gpu.go:40,108: Search takes a read lock -> many concurrent callers
+    rng = np.random.default_rng(11)
+    db = make_db(rng, 4000, 64, np.float32)
+    idx = lbgpu.DenseIndex(64, np.float32, L2)
+    idx.add(db)
+    qs = [make_db(np.random.default_rng(100 + t), 8, 64, np.float32) for t in range(8)]
+    want = [oracle.search(L2, db, q, 10) for q in qs]
+    got = [None] * 8
+
+    def work(t):
+        for _ in range(5):
+            got[t] = idx.search(qs[t], 10)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for t in range(8):
+        assert_topk_equal(got[t][0], got[t][1], want[t][0], want[t][1], 0.0, f"thread {t}")
+    idx.close()
+
+
+# ------------------------------------------------------------------ simd flat batch (all dtypes)
+@pytest.mark.parametrize("dtype,metric", COMBOS)
+@pytest.mark.parametrize("dim", [1, 3, 7, 8, 15, 16, 31, 32, 64, 128, 256, 384, 512, 768, 1024, 1536])
+def test_batch_flat_exact(oracle, dtype, metric, dim):
+    from longbow_b200 import simd
+    rng = np.random.default_rng(dim * 7 + metric)
+    flat, q = make_db(rng, 37, dim, dtype), make_db(rng, 1, dim, dtype)[0]
+    out = np.empty(37, np.float32)
+    simd._flat(metric, q, flat, 37, dim, out, 0)
+    want = oracle.batch_flat(metric, q, flat)
+    if metric == DOT:
+        want = -want  # oracle reports the distance (negated); simd.DotProductBatch is raw
+    assert np.array_equal(out, want)
+
+
+# ------------------------------------------------------------------ re-rank (HNSW candidate lists)
+@pytest.mark.parametrize("dtype,metric", [(np.float32, L2), (np.float16, L2), (np.float32, COS)])
+def test_rerank_parity(lbgpu, oracle, dtype, metric):
+    rng = np.random.default_rng(5001)
+    n, dim, nq, c, k = 20000, 96, 64, 128, 10
+    db, q = make_db(rng, n, dim, dtype), make_db(rng, nq, dim, dtype)
+    cand = rng.integers(0, n, (nq, c)).astype(np.uint32)
+    cand[0, :5] = [n, n + 7, 0xFFFFFFFF, 3, 3]  # location misses + a duplicate
+    tomb, allow = random_bitmap(rng, n, 0.05), random_bitmap(rng, n, 0.30)
+    idx = lbgpu.DenseIndex(dim, dtype, metric)
+    idx.add(db)
+    gd, gl = idx.rerank(q, cand, k)
+    c64 = cand.astype(np.int64)
+    c64[c64 >= n] = -1
+    wd, wl = oracle.rerank(metric, db, q, c64, k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "rerank")
+    idx.set_tombstones(tomb)
+    gd, gl = idx.rerank(q, cand, k, allow=allow)
+    wd, wl = oracle.rerank(metric, db, q, c64, k, tomb=lbgpu.pack_bitmap(tomb), allow=lbgpu.pack_bitmap(allow))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "rerank+bitmaps")
+    from longbow_b200 import store
+    rr = store.RerankBatch(idx, q[1], cand[1], 5)
+    assert [r.ID for r in rr] == [int(x) for x in gl[1, :5] if x >= 0][:len(rr)]
+    idx.close()
+
+
+# ------------------------------------------------------------------ PQ
+def _pq_setup(rng, n, M, sub):
+    cb = rng.standard_normal((M, 256, sub)).astype(np.float32)
+    codes = rng.integers(0, 256, (n, M), dtype=np.uint8)
+    return cb, codes
+
+
+@pytest.mark.parametrize("M,sub", [(96, 8), (8, 4), (5, 3), (32, 16)])
+def test_adc_table_and_batch_bit_exact(oracle, M, sub):
+    from longbow_b200 import pq, simd
+    rng = np.random.default_rng(3000 + M)
+    cb, codes = _pq_setup(rng, 1000, M, sub)
+    enc = pq.PQEncoder(M * sub, M, 256, cb)
+    q = rng.standard_normal(M * sub).astype(np.float32)
+    table = enc.BuildADCTable(q)
+    assert np.array_equal(table, oracle.adc_table(q, cb))
+    out = np.empty(1000, np.float32)
+    enc.ADCDistanceBatch(table, codes, out)
+    assert np.array_equal(out, oracle.adc_batch(table, codes))
+    out2 = np.empty(1000, np.float32)
+    simd.ADCDistanceBatch(table, codes.reshape(-1), M, out2)
+    assert np.array_equal(out2, out)
+    vecs = rng.standard_normal((200, M * sub)).astype(np.float32)
+    assert np.array_equal(enc.EncodeBatch(vecs), oracle.pq_encode(vecs, cb))
+    blob = enc.Serialize()
+    enc2 = pq.PQEncoder.Deserialize(blob)
+    assert np.array_equal(enc2.BuildADCTable(q), table)
+    enc.close(); enc2.close()
+
+
+@pytest.mark.parametrize("M,sub,n", [(96, 8, 30000), (16, 4, 5000)])
+def test_pq_search_bit_exact(lbgpu, oracle, M, sub, n):
+    from longbow_b200 import pq
+    rng = np.random.default_rng(3100 + M)
+    cb, codes = _pq_setup(rng, n, M, sub)
+    dim = M * sub
+    raw = oracle.pq_decode(codes, cb) + rng.normal(0, 0.05, (n, dim)).astype(np.float32)
+    q = rng.standard_normal((9, dim)).astype(np.float32)
+    enc = pq.PQEncoder(dim, M, 256, cb)
+    enc.add_codes(codes[: n // 2]); enc.add_codes(codes[n // 2:])
+    # ADC-only top-k
+    gd, gl = enc.search(q, 10)
+    wd, wl = oracle.pq_search(cb, codes, None, q, 10, 0)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "adc top-k")
+    # with fp32 re-rank of k' = 100 candidates
+    rawidx = lbgpu.DenseIndex(dim, np.float32, L2)
+    rawidx.add(raw)
+    enc.attach_raw(rawidx)
+    gd, gl = enc.search(q, 10, 100)
+    wd, wl = oracle.pq_search(cb, codes, raw, q, 10, 100)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "adc + rerank")
+    # bitmaps
+    tomb, allow = random_bitmap(rng, n, 0.05), random_bitmap(rng, n, 0.3)
+    enc.set_tombstones(tomb)
+    gd, gl = enc.search(q, 10, 100, allow=allow)
+    wd, wl = oracle.pq_search(cb, codes, raw, q, 10, 100, tomb=lbgpu.pack_bitmap(tomb), allow=lbgpu.pack_bitmap(allow))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "adc + rerank + bitmaps")
+    enc.close(); rawidx.close()
+
+
+# ------------------------------------------------------------------ merge / select / filters
+def test_merge_and_select(oracle):
+    from longbow_b200 import store
+    rng = np.random.default_rng(4)
+    parts, nq, k_in, k = 8, 50, 10, 10
+    d = np.sort(rng.random((parts, nq, k_in), dtype=np.float32), axis=2)
+    d[rng.random(d.shape) < 0.2] = 0.5  # many exact ties
+    d = np.sort(d, axis=2)
+    l = rng.permutation(parts * nq * k_in).reshape(parts, nq, k_in).astype(np.int64) + (1 << 33)
+    l[3, :, 7:] = -1
+    gd, gl = store.MergeShardResults(d, l, k)
+    wd, wl = oracle.merge(d, l, k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "merge")
+    x = rng.random(100000, dtype=np.float32)
+    x[500] = x[7]
+    gi, gd2 = store.SelectTopKNeighbors(x, 25)
+    wd2, wi = oracle.select_k(x, 25)
+    assert np.array_equal(gi, wi) and np.array_equal(gd2, wd2)
+
+
+def test_filter_bitmaps(oracle):
+    from longbow_b200 import store
+    rng = np.random.default_rng(8)
+    n = 100_003
+    ci = rng.integers(-5, 5, n).astype(np.int64)
+    cf = rng.standard_normal(n).astype(np.float32)
+    for op, fn in enumerate([np.equal, np.not_equal, np.greater, np.greater_equal, np.less, np.less_equal]):
+        bm = store.GenerateFilterBitset(ci, op, 1)
+        want = np.packbits(np.pad(fn(ci, 1), (0, (-n) % 64)), bitorder="little").view(np.uint64)
+        assert np.array_equal(bm, want), op
+        bm2 = store.GenerateFilterBitset(cf, op, 0.25, bitmap=bm)
+        want2 = np.packbits(np.pad(fn(ci, 1) & fn(cf, np.float32(0.25)), (0, (-n) % 64)), bitorder="little").view(np.uint64)
+        assert np.array_equal(bm2, want2), op
+    # internal/store/bitmap_filter_test.go:94-153: 3 rows, category == "B" -> only row 1 (dictionary code 1)
+    cat = np.array([0, 1, 2], np.int64)
+    assert store.GenerateFilterBitset(cat, 0, 1)[0] == 0b010
+
+
+def test_brute_force_index_mirror(oracle):
+    from longbow_b200 import store
+    rng = np.random.default_rng(1001)
+    db = rng.random((1500, 128), dtype=np.float32)
+    q = rng.random(128, dtype=np.float32)
+    bf = store.BruteForceIndex(128)
+    assert bf.SearchVectors(q, 10) is None  # empty index -> nil, adaptive_index.go:172-174
+    bf.AddBatch(db)
+    res = bf.SearchVectors(q, 10)
+    wd, wl = oracle.search(L2, db, q[None, :], 10)
+    assert [r.ID for r in res] == list(wl[0]) and [np.float32(r.Score) for r in res] == list(wd[0])
+    with pytest.raises(TypeError):
+        bf.SearchVectors(q.astype(np.float64), 10)
+    bf.Close()
