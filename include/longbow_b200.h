@@ -191,6 +191,12 @@ int lb_filter_f32(int device, const float *column, int64_t n, int op, float valu
 
 /* Count of kernel launches issued by this library in this process (bench evidence). */
 int64_t lb_kernel_launch_count(void);
+/* Profiling hook for bench.py's roofline: when enabled, every search brackets its dominant
+ * kernel (the coarse distance scan: dense or ADC) with CUDA events on the launching stream.
+ * lb_prof_read waits for the recorded events, returns their summed duration and count and
+ * (reset != 0) clears them. */
+int lb_prof_enable(int on);
+int lb_prof_read(double *total_ms, int64_t *launches, int reset);
 
 #ifdef __cplusplus
 }

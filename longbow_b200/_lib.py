@@ -67,6 +67,8 @@ SIGNATURES = {
     "lb_filter_i64": (i32, [i32, vp, i64, i32, i64, i32, vp]),
     "lb_filter_f32": (i32, [i32, vp, i64, i32, fp, i32, vp]),
     "lb_kernel_launch_count": (i64, []),
+    "lb_prof_enable": (i32, [i32]),
+    "lb_prof_read": (i32, [C.POINTER(C.c_double), C.POINTER(i64), i32]),
 }
 
 _lib = None
@@ -102,3 +104,14 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().lb_kernel_launch_count())
+
+
+def prof_enable(on: bool) -> None:
+    load().lb_prof_enable(int(on))
+
+
+def prof_read(reset: bool = True):
+    """(total_ms, launches) of the dominant scan kernel since the last reset."""
+    ms, n = C.c_double(), i64()
+    load().lb_prof_read(C.byref(ms), C.byref(n), int(reset))
+    return ms.value, n.value

@@ -87,6 +87,28 @@ struct Scratch {
     }
 };
 
+// ---- dominant-kernel timing (lb_prof_*)
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+struct ProfScope {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t st;
+    explicit ProfScope(cudaStream_t s) : st(s) {
+        if (g_prof_on.load(std::memory_order_relaxed)) {
+            if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, st);
+            else e0 = e1 = nullptr;
+        }
+    }
+    ~ProfScope() {
+        if (e0 && e1) {
+            cudaEventRecord(e1, st);
+            std::lock_guard<std::mutex> g(g_prof_mu);
+            g_prof_events.emplace_back(e0, e1);
+        }
+    }
+};
+
 }  // namespace lb
 
 using namespace lb;
@@ -159,6 +181,31 @@ static bool supported(int dtype, int metric) {
 extern "C" {
 
 const char* lb_last_error(void) { return t_err.c_str(); }
+
+int lb_prof_enable(int on) {
+    g_prof_on.store(on ? 1 : 0);
+    return LB_OK;
+}
+int lb_prof_read(double* total_ms, int64_t* launches, int reset) {
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    double tot = 0;
+    int64_t n = 0;
+    for (auto& pr : g_prof_events) {
+        float ms = 0;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            tot += ms;
+            n++;
+        }
+    }
+    cudaGetLastError();
+    if (reset) {
+        for (auto& pr : g_prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        g_prof_events.clear();
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return LB_OK;
+}
 int64_t lb_kernel_launch_count(void) { return g_launches.load(); }
 
 int lb_device_info(int device, int* sm_count, size_t* total_mem, char* name, size_t name_len) {
@@ -337,7 +384,10 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         uint64_t *partial, *merged;
         CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
         a.partial = partial;
-        CK(launch_dense_scan_simt(a, st));
+        {
+            ProfScope prof(st);
+            CK(launch_dense_scan_simt(a, st));
+        }
         if (parts > 1) {
             CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
             CK(launch_merge_partials(partial, parts, cq, kc, merged, st));
@@ -754,7 +804,10 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
         uint64_t *partial, *merged;
         CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
         a.partial = partial;
-        CK(launch_adc_scan(a, st));
+        {
+            ProfScope prof(st);
+            CK(launch_adc_scan(a, st));
+        }
         if (parts > 1) {
             CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
             CK(launch_merge_partials(partial, parts, cq, kc, merged, st));

@@ -210,8 +210,10 @@ def test_rerank_parity(lbgpu, oracle, dtype, metric):
     wd, wl = oracle.rerank(metric, db, q, c64, k, tomb=lbgpu.pack_bitmap(tomb), allow=lbgpu.pack_bitmap(allow))
     assert_topk_equal(gd, gl, wd, wl, 0.0, "rerank+bitmaps")
     from longbow_b200 import store
-    rr = store.RerankBatch(idx, q[1], cand[1], 5)
-    assert [r.ID for r in rr] == [int(x) for x in gl[1, :5] if x >= 0][:len(rr)]
+    rr = store.RerankBatch(idx, q[1], cand[1], 5)  # tombstones still set, no predicate
+    wd1, wl1 = oracle.rerank(metric, db, q[1:2], c64[1:2], 5, tomb=lbgpu.pack_bitmap(tomb))
+    assert [r.ID for r in rr] == [int(x) for x in wl1[0] if x >= 0]
+    assert [np.float32(r.Distance) for r in rr] == [x for x, i in zip(wd1[0], wl1[0]) if i >= 0]
     idx.close()
 
 
