@@ -191,6 +191,10 @@ int lb_filter_f32(int device, const float *column, int64_t n, int op, float valu
 
 /* Count of kernel launches issued by this library in this process (bench evidence). */
 int64_t lb_kernel_launch_count(void);
+/* Test / diagnostic knobs.  "dense_scan": 0 = auto (tensor-core scan when the index is eligible:
+ * fp16 or int8, 16-byte row pitch), 1 = force the SIMT scan, 2 = force the tensor-core scan
+ * (LB_ERR_UNSUPPORTED if not eligible).  Both scans feed the same exact re-score stage. */
+int lb_set_option(const char *name, int value);
 /* Profiling hook for bench.py's roofline: when enabled, every search brackets its dominant
  * kernel (the coarse distance scan: dense or ADC) with CUDA events on the launching stream.
  * lb_prof_read waits for the recorded events, returns their summed duration and count and

@@ -67,6 +67,7 @@ SIGNATURES = {
     "lb_filter_i64": (i32, [i32, vp, i64, i32, i64, i32, vp]),
     "lb_filter_f32": (i32, [i32, vp, i64, i32, fp, i32, vp]),
     "lb_kernel_launch_count": (i64, []),
+    "lb_set_option": (i32, [C.c_char_p, i32]),
     "lb_prof_enable": (i32, [i32]),
     "lb_prof_read": (i32, [C.POINTER(C.c_double), C.POINTER(i64), i32]),
 }
@@ -104,6 +105,10 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().lb_kernel_launch_count())
+
+
+def set_option(name: str, value: int) -> None:
+    check(load().lb_set_option(name.encode(), int(value)))
 
 
 def prof_enable(on: bool) -> None:

@@ -87,6 +87,9 @@ struct Scratch {
     }
 };
 
+// ---- options (lb_set_option)
+static std::atomic<int> g_opt_dense_scan{0};  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
+
 // ---- dominant-kernel timing (lb_prof_*)
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
@@ -156,7 +159,7 @@ static int grow(void** buf, int64_t* cap, int64_t need, size_t row_bytes, int64_
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(rows)");
     float* na = nullptr;
     if (aux) {
-        e = cudaMalloc((void**)&na, (size_t)ncap * sizeof(float));
+        e = cudaMalloc((void**)&na, ((size_t)ncap + 256) * sizeof(float));  // +256: tile-tail reads
         if (e != cudaSuccess) { cudaFree(nb); return fail_cuda(e, "cudaMalloc(aux)"); }
     }
     CK(cudaDeviceSynchronize());
@@ -181,6 +184,16 @@ static bool supported(int dtype, int metric) {
 extern "C" {
 
 const char* lb_last_error(void) { return t_err.c_str(); }
+
+int lb_set_option(const char* name, int value) {
+    if (!name) return fail(LB_ERR_INVALID, "name is NULL");
+    if (strcmp(name, "dense_scan") == 0) {
+        if (value < 0 || value > 2) return fail(LB_ERR_INVALID, "dense_scan: 0 auto, 1 simt, 2 tensor-core");
+        g_opt_dense_scan.store(value);
+        return LB_OK;
+    }
+    return fail(LB_ERR_INVALID, "unknown option");
+}
 
 int lb_prof_enable(int on) {
     g_prof_on.store(on ? 1 : 0);
@@ -258,7 +271,7 @@ int lb_index_reserve(lb_index* idx, int64_t n_rows) {
     float* na = nullptr;
     cudaError_t e = cudaMalloc(&nb, (size_t)n_rows * rb);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(rows)");
-    e = cudaMalloc((void**)&na, (size_t)n_rows * 4);
+    e = cudaMalloc((void**)&na, ((size_t)n_rows + 256) * 4);  // +256: tile-tail reads
     if (e != cudaSuccess) { cudaFree(nb); return fail_cuda(e, "cudaMalloc(aux)"); }
     CK(cudaDeviceSynchronize());
     if (idx->size > 0) {
@@ -368,23 +381,37 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         a.tomb = idx->tomb; a.tomb_bits = (uint32_t)(idx->tomb_bits > 0xffffffffll ? 0xffffffffll : idx->tomb_bits);
         a.allow = (const uint32_t*)d_allow;
         a.kc = kc;
-        a.tq = (kc <= 128 && cq > 32) ? 64 : (kc <= 384 && cq > 16) ? 32 : 16;
-        if (kc > 384) a.tq = 16; else if (kc > 128 && a.tq == 64) a.tq = 32;
-        a.cap = next_pow2(kc + 128);
-        const int qblocks = (cq + a.tq - 1) / a.tq;
-        int target = 2 * idx->sm_count;
-        int parts = (target + qblocks - 1) / qblocks;
-        int64_t max_parts = (idx->size + 511) / 512;
-        if (parts > max_parts) parts = (int)max_parts;
-        if (parts < 1) parts = 1;
-        int64_t rpp = (idx->size + parts - 1) / parts;
-        rpp = ((rpp + 127) / 128) * 128;
-        parts = (int)((idx->size + rpp - 1) / rpp);
-        a.parts = parts; a.rows_per_part = (uint32_t)rpp;
+        const int mode = g_opt_dense_scan.load(std::memory_order_relaxed);
+        const bool tc_ok = dense_tc_eligible(idx->dtype, idx->dim, idx->rows, a.queries, kc);
+        if (mode == 2 && !tc_ok) return fail(LB_ERR_UNSUPPORTED, "tensor-core scan not eligible for this index");
+        const bool use_tc = tc_ok && mode != 1;
         uint64_t *partial, *merged;
-        CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
-        a.partial = partial;
-        {
+        int parts;
+        if (use_tc) {
+            size_t cand_bytes;
+            dense_scan_tc_plan(cq, a.n_rows, idx->sm_count, kc, &parts, &cand_bytes);
+            uint64_t* cand;
+            CK(scr.get((void**)&cand, cand_bytes));
+            CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
+            a.parts = parts; a.partial = partial; a.tq = 128; a.cap = 0; a.rows_per_part = 0;
+            ProfScope prof(st);
+            CK(launch_dense_scan_tc(a, idx->sm_count, cand, st));
+        } else {
+            a.tq = (kc <= 128 && cq > 32) ? 64 : (kc <= 384 && cq > 16) ? 32 : 16;
+            if (kc > 384) a.tq = 16; else if (kc > 128 && a.tq == 64) a.tq = 32;
+            a.cap = next_pow2(kc + 128);
+            const int qblocks = (cq + a.tq - 1) / a.tq;
+            int target = 2 * idx->sm_count;
+            parts = (target + qblocks - 1) / qblocks;
+            int64_t max_parts = (idx->size + 511) / 512;
+            if (parts > max_parts) parts = (int)max_parts;
+            if (parts < 1) parts = 1;
+            int64_t rpp = (idx->size + parts - 1) / parts;
+            rpp = ((rpp + 127) / 128) * 128;
+            parts = (int)((idx->size + rpp - 1) / rpp);
+            a.parts = parts; a.rows_per_part = (uint32_t)rpp;
+            CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
+            a.partial = partial;
             ProfScope prof(st);
             CK(launch_dense_scan_simt(a, st));
         }

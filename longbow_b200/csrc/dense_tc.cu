@@ -1,0 +1,412 @@
+// dense_tc.cu -- S1 coarse scan on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   D[128 queries x 256 rows] += Q[128 x K] * X[256 x K]^T      (K-major both, 128-byte swizzle)
+//
+// Warp-specialised persistent kernel, one CTA per SM:
+//   warp 0      TMA producer   : cp.async.bulk.tensor tiles of Q and X into a 4-stage smem ring
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (M=128, N=256), accumulators in TMEM
+//   warp 2      TMEM allocator : 512 columns = 2 accumulator stages of 256 fp32/s32 columns
+//   warps 4..7  epilogue       : tcgen05.ld a TMEM lane (= one query) per thread, turn dot products
+//                                into ranking keys, threshold-filter them against the query's
+//                                running k-th best, append survivors to the query's candidate
+//                                list; warp-cooperative bitonic compaction when a list fills.
+// The 128 x 256 distance tile never leaves the SM: HBM only sees the database once per batch.
+//
+// Work split: query block b (128 queries) x group g; CTA (b, g) streams row tiles g, g+G, g+2G ...
+// so the CTAs of all query blocks touch the same row tile at about the same time and X is read
+// from HBM once and from L2 by the others.  Output: partial[g][q][kc] packed (key, row), the same
+// format the SIMT scan produces; merge + exact re-score follow (kernels_dense.cu).
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace lb {
+
+enum { KIND_F16 = 0, KIND_I8 = 1, KIND_TF32 = 2 };
+
+template <int KIND> struct TcTraits;
+template <> struct TcTraits<KIND_F16> {
+    static constexpr int kElem = 2, kBlockK = 64;                      // 64 halves = 128 B per row per stage
+    static constexpr uint32_t kIdescFmt = (1u << 4) | (0u << 7) | (0u << 10);  // D=f32, A=B=f16
+};
+template <> struct TcTraits<KIND_I8> {
+    static constexpr int kElem = 1, kBlockK = 128;
+    static constexpr uint32_t kIdescFmt = (2u << 4) | (1u << 7) | (1u << 10);  // D=s32, A=B=s8
+};
+template <> struct TcTraits<KIND_TF32> {
+    static constexpr int kElem = 4, kBlockK = 32;
+    static constexpr uint32_t kIdescFmt = (1u << 4) | (2u << 7) | (2u << 10);  // D=f32, A=B=tf32
+};
+
+constexpr int TC_M = 128;       // queries per CTA (TMEM lanes)
+constexpr int TC_N = 256;       // rows per tile (TMEM columns per accumulator stage)
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_M * 128;   // 16 KiB
+constexpr int TC_B_BYTES = TC_N * 128;   // 32 KiB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a lost arrival traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if constexpr (KIND == KIND_F16) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    } else if constexpr (KIND == KIND_I8) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);  // start address       bits [0,14)
+    d |= (uint64_t)1 << 16;                    // leading byte offset bits [16,30) (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset  bits [32,46): 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                    // descriptor version  bits [46,48) = 1 on sm_100
+    d |= (uint64_t)2 << 61;                    // layout type         bits [61,64) = SWIZZLE_128B
+    return d;
+}
+
+struct TcArgs {
+    const float* aux;
+    uint32_t n_rows;
+    int nq;
+    int k_blocks;       // ceil(dim / kBlockK)
+    int groups;         // G: CTAs per query block
+    int n_row_tiles;    // ceil(n_rows / 256)
+    const uint32_t* tomb;
+    uint32_t tomb_bits;
+    const uint32_t* allow;
+    int kc, cap;
+    uint64_t* cand;     // [grid][128][cap] per-(CTA, query) candidate lists (global, L2-resident)
+    uint64_t* partial;  // [G][nq][kc]
+};
+
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int METRIC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const TcArgs a) {
+    using TR = TcTraits<KIND>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const uint32_t scratch_off = TC_STAGES * TC_STAGE_BYTES;
+    uint64_t* scratch_all = reinterpret_cast<uint64_t*>(base_ptr + scratch_off);  // [4][cap]
+    const uint32_t bar_base = base + scratch_off + 4u * a.cap * 8u;
+    // barriers: full[4], empty[4], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + scratch_off + 4u * a.cap * 8u + 8u * (2 * TC_STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = blockIdx.x / a.groups, g = blockIdx.x % a.groups;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int rt = g; rt < a.n_row_tiles; rt += a.groups) {
+                for (int kb = 0; kb < a.k_blocks; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+                    const uint32_t sa = base + stage * TC_STAGE_BYTES;
+                    tma_load_2d(sa, &map_q, full_bar(stage), kb * TR::kBlockK, qb * TC_M);
+                    tma_load_2d(sa + TC_A_BYTES, &map_db, full_bar(stage), kb * TR::kBlockK, rt * TC_N);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            const uint32_t idesc = TR::kIdescFmt | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int rt = g; rt < a.n_row_tiles; rt += a.groups) {
+                mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * TC_N;
+                for (int kb = 0; kb < a.k_blocks; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * TC_STAGE_BYTES;
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)  // 4 x (UMMA_K * elem = 32 B) per 128-byte swizzle row
+                        tc_mma<KIND>(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+                    tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(tfull_bar(as));  // accumulator complete -> epilogue
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue: fused top-k =======================
+        const int ew = warp - 4;         // TMEM lane quarter this warp may read
+        const int tq = ew * 32 + lane;   // query (TMEM lane) of this thread
+        const int q = qb * TC_M + tq;
+        const int cap = a.cap, kc = a.kc;
+        uint64_t* mybuf = a.cand + ((size_t)blockIdx.x * TC_M + tq) * cap;
+        uint64_t* scratch = scratch_all + (size_t)ew * cap;
+        int cnt = 0;
+        float tau = (q < a.nq) ? INFINITY : -INFINITY;  // padding queries never select
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int rt = g; rt < a.n_row_tiles; rt += a.groups) {
+            const uint32_t row0 = (uint32_t)rt * TC_N;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * TC_N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TC_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                float ax[32];
+                if constexpr (METRIC != METRIC_DOT) {
+                    const float4* ap = reinterpret_cast<const float4*>(a.aux + row0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float4 t = __ldg(ap + j);
+                        ax[4 * j] = t.x; ax[4 * j + 1] = t.y; ax[4 * j + 2] = t.z; ax[4 * j + 3] = t.w;
+                    }
+                }
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    float dot;
+                    if constexpr (KIND == KIND_I8) dot = (float)(int32_t)v[j];
+                    else dot = __uint_as_float(v[j]);
+                    float key;
+                    if constexpr (METRIC == METRIC_L2) key = fmaf(-2.f, dot, ax[j]);
+                    else if constexpr (METRIC == METRIC_COSINE) key = -dot * ax[j];
+                    else key = -dot;
+                    if (key < tau) {
+                        const uint32_t row = row0 + c0 + j;
+                        bool ok = row < a.n_rows;
+                        if (ok && a.tomb != nullptr && row < a.tomb_bits && bit_set(a.tomb, row)) ok = false;
+                        if (ok && a.allow != nullptr && !bit_set(a.allow, row)) ok = false;
+                        if (ok && cnt < cap) mybuf[cnt++] = pack_key(key, row);
+                    }
+                }
+            }
+            // release the accumulator stage before any (slow) compaction
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+
+            // warp-cooperative compaction of every list that could overflow on the next tile
+            unsigned need = __ballot_sync(0xffffffffu, cnt > cap - TC_N);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const int c = __shfl_sync(0xffffffffu, cnt, src);
+                const uint64_t bp = __shfl_sync(0xffffffffu, (unsigned long long)mybuf, src);
+                uint64_t* buf = reinterpret_cast<uint64_t*>(bp);
+                const int n2 = next_pow2(c);
+                __syncwarp();  // order the owner's appends before the other lanes' reads
+                for (int t = lane; t < n2; t += 32) scratch[t] = (t < c) ? __ldcg(buf + t) : kInvalid;
+                __syncwarp();
+                warp_bitonic_sort(scratch, n2, lane);
+                for (int t = lane; t < kc && t < c; t += 32) __stcg(buf + t, scratch[t]);
+                const float nt = (c >= kc) ? key_of(scratch[kc - 1]) : INFINITY;
+                __syncwarp();
+                if (lane == src) { cnt = min(c, kc); tau = nt; }
+            }
+        }
+        // final: sort every list, emit its best kc
+        for (int src = 0; src < 32; src++) {
+            const int c = __shfl_sync(0xffffffffu, cnt, src);
+            const uint64_t bp = __shfl_sync(0xffffffffu, (unsigned long long)mybuf, src);
+            const int qq = __shfl_sync(0xffffffffu, q, src);
+            if (qq >= a.nq) continue;  // warp-uniform
+            uint64_t* buf = reinterpret_cast<uint64_t*>(bp);
+            const int n2 = next_pow2(max(c, 2));
+            __syncwarp();
+            for (int t = lane; t < n2; t += 32) scratch[t] = (t < c) ? __ldcg(buf + t) : kInvalid;
+            __syncwarp();
+            warp_bitonic_sort(scratch, n2, lane);
+            uint64_t* out = a.partial + ((size_t)g * a.nq + qq) * kc;
+            for (int t = lane; t < kc; t += 32) out[t] = (t < c) ? scratch[t] : kInvalid;
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap* m, int kind, const void* ptr, uint64_t rows, int dim, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const int elem = kind == KIND_F16 ? 2 : kind == KIND_I8 ? 1 : 4;
+    const int block_k = 128 / elem;
+    CUtensorMapDataType dt = kind == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                             : kind == KIND_I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * elem};
+    cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+bool dense_tc_eligible(int dtype, int dim, const void* db, const void* queries, int kc) {
+    const int elem = dtype == DT_F16 ? 2 : dtype == DT_I8 ? 1 : dtype == DT_F32 ? 4 : 0;
+    if (elem == 0) return false;
+    if (dtype == DT_F32) return false;  // fp32 stays on the SIMT scan this round (TF32 needs wider margins)
+    if (((size_t)dim * elem) % 16 != 0) return false;                    // TMA row pitch
+    if ((reinterpret_cast<uintptr_t>(db) | reinterpret_cast<uintptr_t>(queries)) & 15) return false;
+    if (kc + TC_N > 1024) return false;
+    return get_encode() != nullptr;
+}
+
+// groups (= number of partial lists per query) and the size of the candidate scratch
+void dense_scan_tc_plan(int nq, uint32_t n_rows, int sm_count, int kc, int* groups_out, size_t* cand_bytes) {
+    const int cap = next_pow2(kc + TC_N);
+    const int nqb = (nq + TC_M - 1) / TC_M;
+    const int n_row_tiles = (int)((n_rows + TC_N - 1) / TC_N);
+    int groups = sm_count / nqb;
+    if (groups < 1) groups = 1;
+    if (groups > n_row_tiles) groups = n_row_tiles;
+    *groups_out = groups;
+    *cand_bytes = (size_t)nqb * groups * TC_M * cap * 8;
+}
+
+cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand, cudaStream_t st) {
+    const int kind = s.dtype == DT_F16 ? KIND_F16 : s.dtype == DT_I8 ? KIND_I8 : KIND_TF32;
+    const int elem = kind == KIND_F16 ? 2 : kind == KIND_I8 ? 1 : 4;
+    const int block_k = 128 / elem;
+    CUtensorMap mq, mdb;
+    if (!make_map(&mq, kind, s.queries, (uint64_t)s.nq, s.dim, TC_M)) return cudaErrorInvalidValue;
+    if (!make_map(&mdb, kind, s.db, (uint64_t)s.n_rows, s.dim, TC_N)) return cudaErrorInvalidValue;
+    TcArgs a;
+    a.aux = s.aux; a.n_rows = s.n_rows; a.nq = s.nq;
+    a.k_blocks = (s.dim + block_k - 1) / block_k;
+    a.n_row_tiles = (int)((s.n_rows + TC_N - 1) / TC_N);
+    const int nqb = (s.nq + TC_M - 1) / TC_M;
+    int groups;
+    size_t cand_bytes;
+    dense_scan_tc_plan(s.nq, s.n_rows, sm_count, s.kc, &groups, &cand_bytes);
+    if (groups != s.parts) return cudaErrorInvalidValue;  // partial[] was sized for s.parts lists
+    a.groups = groups;
+    a.tomb = s.tomb; a.tomb_bits = s.tomb_bits; a.allow = s.allow;
+    a.kc = s.kc; a.cap = next_pow2(s.kc + TC_N);
+    a.cand = cand; a.partial = s.partial;
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 4 * (size_t)a.cap * 8 + 8 * (2 * TC_STAGES + 4) + 16;
+    const dim3 grid(nqb * groups);
+#define LB_TC(KIND_, METRIC_)                                                                                  \
+    {                                                                                                          \
+        auto kern = dense_scan_tc<KIND_, METRIC_>;                                                             \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        if (e != cudaSuccess) return e;                                                                        \
+        kern<<<grid, TC_THREADS, smem, st>>>(mq, mdb, a);                                                      \
+    }
+    if (kind == KIND_F16) {
+        if (s.metric == METRIC_L2) LB_TC(KIND_F16, METRIC_L2) else if (s.metric == METRIC_COSINE) LB_TC(KIND_F16, METRIC_COSINE) else LB_TC(KIND_F16, METRIC_DOT)
+    } else if (kind == KIND_I8) {
+        if (s.metric == METRIC_L2) LB_TC(KIND_I8, METRIC_L2) else LB_TC(KIND_I8, METRIC_DOT)
+    } else {
+        return cudaErrorInvalidValue;
+    }
+#undef LB_TC
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace lb

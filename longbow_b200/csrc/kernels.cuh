@@ -58,6 +58,11 @@ cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_
 cudaError_t launch_merge_topk(const float* in_d, const int64_t* in_l, int parts, int nq, int k_in, int k,
                               float* out_d, int64_t* out_l, cudaStream_t st);
 
+// ---- tensor-core scan (dense_tc.cu)
+bool dense_tc_eligible(int dtype, int dim, const void* db, const void* queries, int kc);
+void dense_scan_tc_plan(int nq, uint32_t n_rows, int sm_count, int kc, int* groups_out, size_t* cand_bytes);
+cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand, cudaStream_t st);
+
 // ---- PQ (kernels_pq.cu)
 struct PqScanArgs {
     const uint8_t* codes;    // [n][M] row-major

@@ -329,3 +329,48 @@ def test_brute_force_index_mirror(oracle):
     with pytest.raises(TypeError):
         bf.SearchVectors(q.astype(np.float64), 10)
     bf.Close()
+
+
+# ------------------------------------------------------------------ tensor-core scan vs SIMT scan vs oracle
+@pytest.fixture
+def scan_mode():
+    from longbow_b200 import _lib
+    yield lambda m: _lib.set_option("dense_scan", m)
+    _lib.set_option("dense_scan", 0)
+
+
+@pytest.mark.parametrize("dtype,metric", [(np.float16, COS), (np.float16, L2), (np.float16, DOT), (np.int8, DOT), (np.int8, L2)])
+@pytest.mark.parametrize("n,dim,nq,k", [(70001, 768, 300, 100), (40000, 64, 129, 10), (9000, 208, 40, 32), (300, 128, 5, 10)])
+def test_tensor_core_scan_parity(lbgpu, oracle, scan_mode, dtype, metric, n, dim, nq, k):
+    rng = np.random.default_rng(2000 + n + metric)
+    db, q = make_db(rng, n, dim, dtype), make_db(rng, nq, dim, dtype)
+    if metric == COS:
+        db[[3, n // 2, n - 1]] = 0
+    idx = lbgpu.DenseIndex(dim, dtype, metric)
+    idx.add(db)
+    wd, wl = oracle.search(metric, db, q, k)
+    for mode in (2, 1):  # forced tensor-core, forced SIMT
+        scan_mode(mode)
+        gd, gl = idx.search(q, k)
+        assert_topk_equal(gd, gl, wd, wl, 0.0, f"mode={mode} {dtype.__name__} metric={metric}")
+    # bitmaps through the tensor-core epilogue
+    scan_mode(2)
+    tomb, allow = random_bitmap(rng, n, 0.05), random_bitmap(rng, n, 0.30)
+    idx.set_tombstones(tomb)
+    gd, gl = idx.search(q[:50], k, allow=allow)
+    wd, wl = oracle.search(metric, db, q[:50], k, tomb=lbgpu.pack_bitmap(tomb), allow=lbgpu.pack_bitmap(allow))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "tc + bitmaps")
+    idx.close()
+
+
+def test_tensor_core_ineligible_is_loud(lbgpu, scan_mode):
+    from longbow_b200 import LongbowError
+    idx = lbgpu.DenseIndex(7, np.float16, COS)  # 14-byte rows: TMA pitch not a multiple of 16
+    idx.add(np.ones((10, 7), np.float16))
+    scan_mode(2)
+    with pytest.raises(LongbowError):
+        idx.search(np.ones((1, 7), np.float16), 3)
+    scan_mode(0)
+    d, l = idx.search(np.ones((1, 7), np.float16), 3)  # auto falls to the SIMT scan
+    assert list(l[0]) == [0, 1, 2]
+    idx.close()
