@@ -136,7 +136,31 @@ struct TcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int METRIC>
+// Sort one candidate list (c entries in global memory, capacity 32*R) in registers; write its best
+// kc back in place (or to `dst`); return the new threshold (key of entry kc-1, +inf if c < kc).
+template <int R>
+__device__ __forceinline__ float compact_list(const uint64_t* buf, uint64_t* dst, int c, int kc, int lane) {
+    uint64_t v[R];
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(buf + lane * R);
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+        const int i = lane * R + r;
+        ulonglong2 t = make_ulonglong2(kInvalid, kInvalid);
+        if (i < c) t = __ldcg(src + (r >> 1));
+        v[r] = t.x;
+        v[r + 1] = (i + 1 < c) ? t.y : kInvalid;
+    }
+    warp_sort_regs<R>(v, lane);
+    if (lane * R < kc) {  // kc is a multiple of 32, so whole lanes are in or out
+        ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst + lane * R);
+#pragma unroll
+        for (int r = 0; r < R; r += 2) __stcg(d2 + (r >> 1), make_ulonglong2(v[r], v[r + 1]));
+    }
+    const uint64_t last = __shfl_sync(0xffffffffu, v[R - 1], kc / R - 1);
+    return (c >= kc) ? key_of(last) : INFINITY;
+}
+
+template <int KIND, int METRIC, int CAP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const TcArgs a) {
     using TR = TcTraits<KIND>;
@@ -144,15 +168,14 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* base_ptr = smem_raw + (base - raw);
-    const uint32_t scratch_off = TC_STAGES * TC_STAGE_BYTES;
-    uint64_t* scratch_all = reinterpret_cast<uint64_t*>(base_ptr + scratch_off);  // [4][cap]
-    const uint32_t bar_base = base + scratch_off + 4u * a.cap * 8u;
+    const uint32_t bar_off = TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t bar_base = base + bar_off;
     // barriers: full[4], empty[4], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + scratch_off + 4u * a.cap * 8u + 8u * (2 * TC_STAGES + 4));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (2 * TC_STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x / a.groups, g = blockIdx.x % a.groups;
@@ -218,9 +241,9 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int ew = warp - 4;         // TMEM lane quarter this warp may read
         const int tq = ew * 32 + lane;   // query (TMEM lane) of this thread
         const int q = qb * TC_M + tq;
-        const int cap = a.cap, kc = a.kc;
+        constexpr int cap = CAP, R = CAP / 32;
+        const int kc = a.kc;
         uint64_t* mybuf = a.cand + ((size_t)blockIdx.x * TC_M + tq) * cap;
-        uint64_t* scratch = scratch_all + (size_t)ew * cap;
         int cnt = 0;
         float tau = (q < a.nq) ? INFINITY : -INFINITY;  // padding queries never select
         int as = 0;
@@ -274,15 +297,9 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 const int src = __ffs(need) - 1;
                 need &= need - 1;
                 const int c = __shfl_sync(0xffffffffu, cnt, src);
-                const uint64_t bp = __shfl_sync(0xffffffffu, (unsigned long long)mybuf, src);
-                uint64_t* buf = reinterpret_cast<uint64_t*>(bp);
-                const int n2 = next_pow2(c);
+                uint64_t* buf = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
                 __syncwarp();  // order the owner's appends before the other lanes' reads
-                for (int t = lane; t < n2; t += 32) scratch[t] = (t < c) ? __ldcg(buf + t) : kInvalid;
-                __syncwarp();
-                warp_bitonic_sort(scratch, n2, lane);
-                for (int t = lane; t < kc && t < c; t += 32) __stcg(buf + t, scratch[t]);
-                const float nt = (c >= kc) ? key_of(scratch[kc - 1]) : INFINITY;
+                const float nt = compact_list<R>(buf, buf, c, kc, lane);
                 __syncwarp();
                 if (lane == src) { cnt = min(c, kc); tau = nt; }
             }
@@ -290,18 +307,11 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         // final: sort every list, emit its best kc
         for (int src = 0; src < 32; src++) {
             const int c = __shfl_sync(0xffffffffu, cnt, src);
-            const uint64_t bp = __shfl_sync(0xffffffffu, (unsigned long long)mybuf, src);
             const int qq = __shfl_sync(0xffffffffu, q, src);
+            const uint64_t* buf = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
             if (qq >= a.nq) continue;  // warp-uniform
-            uint64_t* buf = reinterpret_cast<uint64_t*>(bp);
-            const int n2 = next_pow2(max(c, 2));
             __syncwarp();
-            for (int t = lane; t < n2; t += 32) scratch[t] = (t < c) ? __ldcg(buf + t) : kInvalid;
-            __syncwarp();
-            warp_bitonic_sort(scratch, n2, lane);
-            uint64_t* out = a.partial + ((size_t)g * a.nq + qq) * kc;
-            for (int t = lane; t < kc; t += 32) out[t] = (t < c) ? scratch[t] : kInvalid;
-            __syncwarp();
+            compact_list<R>(buf, a.partial + ((size_t)g * a.nq + qq) * kc, c, kc, lane);
         }
     }
 
@@ -358,7 +368,8 @@ bool dense_tc_eligible(int dtype, int dim, const void* db, const void* queries, 
 
 // groups (= number of partial lists per query) and the size of the candidate scratch
 void dense_scan_tc_plan(int nq, uint32_t n_rows, int sm_count, int kc, int* groups_out, size_t* cand_bytes) {
-    const int cap = next_pow2(kc + TC_N);
+    int cap = next_pow2(kc + TC_N);
+    if (cap < 512) cap = 512;
     const int nqb = (nq + TC_M - 1) / TC_M;
     const int n_row_tiles = (int)((n_rows + TC_N - 1) / TC_N);
     int groups = sm_count / nqb;
@@ -387,15 +398,20 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     a.groups = groups;
     a.tomb = s.tomb; a.tomb_bits = s.tomb_bits; a.allow = s.allow;
     a.kc = s.kc; a.cap = next_pow2(s.kc + TC_N);
+    if (a.cap < 512) a.cap = 512;
     a.cand = cand; a.partial = s.partial;
-    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 4 * (size_t)a.cap * 8 + 8 * (2 * TC_STAGES + 4) + 16;
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 8 * (2 * TC_STAGES + 4) + 16;
     const dim3 grid(nqb * groups);
-#define LB_TC(KIND_, METRIC_)                                                                                  \
+#define LB_TC1(KIND_, METRIC_, CAP_)                                                                           \
     {                                                                                                          \
-        auto kern = dense_scan_tc<KIND_, METRIC_>;                                                             \
+        auto kern = dense_scan_tc<KIND_, METRIC_, CAP_>;                                                       \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
         if (e != cudaSuccess) return e;                                                                        \
         kern<<<grid, TC_THREADS, smem, st>>>(mq, mdb, a);                                                      \
+    }
+#define LB_TC(KIND_, METRIC_)                                                                                  \
+    {                                                                                                          \
+        if (a.cap == 512) LB_TC1(KIND_, METRIC_, 512) else LB_TC1(KIND_, METRIC_, 1024)                        \
     }
     if (kind == KIND_F16) {
         if (s.metric == METRIC_L2) LB_TC(KIND_F16, METRIC_L2) else if (s.metric == METRIC_COSINE) LB_TC(KIND_F16, METRIC_COSINE) else LB_TC(KIND_F16, METRIC_DOT)
@@ -405,6 +421,7 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
         return cudaErrorInvalidValue;
     }
 #undef LB_TC
+#undef LB_TC1
     count_launch();
     return cudaGetLastError();
 }

@@ -340,7 +340,7 @@ def scan_mode():
 
 
 @pytest.mark.parametrize("dtype,metric", [(np.float16, COS), (np.float16, L2), (np.float16, DOT), (np.int8, DOT), (np.int8, L2)])
-@pytest.mark.parametrize("n,dim,nq,k", [(70001, 768, 300, 100), (40000, 64, 129, 10), (9000, 208, 40, 32), (300, 128, 5, 10)])
+@pytest.mark.parametrize("n,dim,nq,k", [(70001, 768, 300, 100), (40000, 64, 129, 10), (9000, 208, 40, 32), (300, 128, 5, 10), (20000, 128, 40, 300)])
 def test_tensor_core_scan_parity(lbgpu, oracle, scan_mode, dtype, metric, n, dim, nq, k):
     rng = np.random.default_rng(2000 + n + metric)
     db, q = make_db(rng, n, dim, dtype), make_db(rng, nq, dim, dtype)
