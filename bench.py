@@ -139,6 +139,10 @@ def main():
     ap.add_argument("--rows", type=int, default=N_ROWS, help="debug only: a smaller DB invalidates the number")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    wd = int(os.environ.get("LB_WATCHDOG", "0"))
+    if wd > 0:  # debug: dump all Python stacks and exit if the run wedges
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -160,7 +164,12 @@ def main():
     steps = args.steps
     n_rows = args.rows
 
+    def log(msg):
+        if os.environ.get("LB_VERBOSE"):
+            print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
+
     db, qs = make_data(n_rows, NQ, warm + steps)
+    log("data ready")
     lo, hi = shard_range(n_rows, rank, world)
     sidx = ShardedIndex(DIM, np.float16, _lib.METRIC_COSINE, n_rows, rank, world, local)
     sidx.index.reserve(hi - lo)
@@ -175,9 +184,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm ("value")
+    log("index resident")
     for s in range(warm):
         sidx.search_device(d_qs[s], K, out_d, out_l)
     barrier()
+    log("warm-up done")
     sampler = ClockSampler(local)
     sampler.start()
     _lib.prof_read(reset=True)
@@ -193,13 +204,15 @@ def main():
     launches = _lib.launch_count() - l0
     _lib.prof_enable(False)
     scan_ms, scan_n = _lib.prof_read(reset=True)
+    log(f"timed region done: {ms:.2f} ms")
     if sampler.summary()["samples"] < 5:  # timed region too short for NVML: keep sampling the same load
         t_end = time.time() + 1.0
         while time.time() < t_end:
-            sidx.search_device(d_qs[warm], K, out_d, out_l)
+            sidx.search_device(d_qs[warm + steps - 1], K, out_d, out_l)
             torch.cuda.synchronize()
     sampler.stop_flag = True
-    sampler.join()
+    sampler.join(timeout=5)
+    log("clock sampler joined")
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

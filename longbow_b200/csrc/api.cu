@@ -389,7 +389,9 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         int parts;
         if (use_tc) {
             size_t cand_bytes;
-            dense_scan_tc_plan(cq, a.n_rows, idx->sm_count, kc, &parts, &cand_bytes);
+            int groups;
+            dense_scan_tc_plan(cq, a.n_rows, idx->sm_count, kc, &groups, &cand_bytes);
+            parts = 2 * groups;  // two epilogue groups (candidate lists) per CTA
             uint64_t* cand;
             CK(scr.get((void**)&cand, cand_bytes));
             CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));

@@ -6,10 +6,11 @@
 //   warp 0      TMA producer   : cp.async.bulk.tensor tiles of Q and X into a 4-stage smem ring
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma (M=128, N=256), accumulators in TMEM
 //   warp 2      TMEM allocator : 512 columns = 2 accumulator stages of 256 fp32/s32 columns
-//   warps 4..7  epilogue       : tcgen05.ld a TMEM lane (= one query) per thread, turn dot products
+//   warps 4..11 epilogue       : two groups of 4 warps alternate tiles; tcgen05.ld a TMEM lane
+//                                (= one query) per thread, turn dot products
 //                                into ranking keys, threshold-filter them against the query's
 //                                running k-th best, append survivors to the query's candidate
-//                                list; warp-cooperative bitonic compaction when a list fills.
+//                                list; warp-cooperative radix-select compaction when a list fills.
 // The 128 x 256 distance tile never leaves the SM: HBM only sees the database once per batch.
 //
 // Work split: query block b (128 queries) x group g; CTA (b, g) streams row tiles g, g+G, g+2G ...
@@ -44,7 +45,7 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_M * 128;   // 16 KiB
 constexpr int TC_B_BYTES = TC_N * 128;   // 32 KiB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;   // 4 control warps + 2 epilogue groups of 4 warps
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,16 +59,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded spin: a lost arrival traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: a lost arrival traps (kernel error) after 2 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
+    uint64_t t0 = 0;
     for (uint32_t spins = 0; !ok; spins++) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (spins > (1u << 24)) __trap();
+        if (!ok && (spins & 255u) == 255u) {
+            const uint64_t now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -136,10 +147,14 @@ struct TcArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Sort one candidate list (c entries in global memory, capacity 32*R) in registers; write its best
-// kc back in place (or to `dst`); return the new threshold (key of entry kc-1, +inf if c < kc).
+// Selection compaction of one candidate list (c entries in global memory, capacity 32*R, entries in
+// increasing row order): keep exactly its kc smallest by (key, row) -- radix-select the kc-th key
+// MSB-first over the 32-bit ordered key, break ties at that key by list position (== row order) --
+// and write them back, order preserved, to dst.  Returns the new threshold (the kc-th key; +inf if
+// c < kc, in which case everything is kept).  ~4x fewer instructions than sorting the list.
 template <int R>
-__device__ __forceinline__ float compact_list(const uint64_t* buf, uint64_t* dst, int c, int kc, int lane) {
+__device__ __forceinline__ float select_compact(const uint64_t* buf, uint64_t* dst, int c, int kc, int lane,
+                                                int* kept_out) {
     uint64_t v[R];
     const ulonglong2* src = reinterpret_cast<const ulonglong2*>(buf + lane * R);
 #pragma unroll
@@ -150,14 +165,68 @@ __device__ __forceinline__ float compact_list(const uint64_t* buf, uint64_t* dst
         v[r] = t.x;
         v[r + 1] = (i + 1 < c) ? t.y : kInvalid;
     }
-    warp_sort_regs<R>(v, lane);
-    if (lane * R < kc) {  // kc is a multiple of 32, so whole lanes are in or out
-        ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst + lane * R);
+    uint32_t T = 0xffffffffu;  // keep everything valid when c < kc
+    if (c >= kc) {
+        T = 0;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; bit--) {
+            const uint32_t test = T | (1u << bit);
+            int less = 0;
 #pragma unroll
-        for (int r = 0; r < R; r += 2) __stcg(d2 + (r >> 1), make_ulonglong2(v[r], v[r + 1]));
+            for (int r = 0; r < R; r++) less += ((uint32_t)(v[r] >> 32) < test);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) less += __shfl_xor_sync(0xffffffffu, less, o);
+            if (less < kc) T = test;  // fewer than kc keys below `test`: the kc-th key is >= test
+        }
     }
-    const uint64_t last = __shfl_sync(0xffffffffu, v[R - 1], kc / R - 1);
-    return (c >= kc) ? key_of(last) : INFINITY;
+    // keep key < T, plus the first (kc - #less) entries with key == T in list order
+    int n_less = 0, n_tie = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const uint32_t h = (uint32_t)(v[r] >> 32);
+        n_less += (h < T) && (v[r] != kInvalid);
+        n_tie += (h == T) && (v[r] != kInvalid);
+    }
+    int tot_less = n_less, tie_before = n_tie;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot_less += __shfl_xor_sync(0xffffffffu, tot_less, o);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {  // inclusive scan of tie counts
+        const int up = __shfl_up_sync(0xffffffffu, tie_before, o);
+        if (lane >= o) tie_before += up;
+    }
+    tie_before -= n_tie;  // exclusive
+    const int tie_keep = (c >= kc) ? (kc - tot_less) : 0x7fffffff;
+    // stable compaction
+    int mine = 0;
+    uint32_t keep_mask = 0;
+    {
+        int t_seen = tie_before;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t h = (uint32_t)(v[r] >> 32);
+            const bool valid = v[r] != kInvalid;
+            bool keep = valid && (h < T);
+            if (valid && h == T) { keep = t_seen < tie_keep; t_seen++; }
+            keep_mask |= (keep ? 1u : 0u) << r;
+            mine += keep;
+        }
+    }
+    int off = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, off, o);
+        if (lane >= o) off += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, off, 31);
+    off -= mine;
+    __syncwarp();  // every lane has loaded its slice before anyone overwrites the list in place
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (keep_mask & (1u << r)) __stcg(dst + off++, v[r]);
+    }
+    *kept_out = total;
+    return (c >= kc) ? ordered_to_float(T) : INFINITY;
 }
 
 template <int KIND, int METRIC, int CAP>
@@ -168,7 +237,8 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* base_ptr = smem_raw + (base - raw);
-    const uint32_t bar_off = TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t slot_off = TC_STAGES * TC_STAGE_BYTES;               // [8 warps][32 x 32] words
+    const uint32_t bar_off = slot_off + 8u * 32u * 32u * 4u;
     const uint32_t bar_base = base + bar_off;
     // barriers: full[4], empty[4], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -238,19 +308,27 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
     } else if (warp >= 4) {
         // ================================ epilogue: fused top-k =======================
-        const int ew = warp - 4;         // TMEM lane quarter this warp may read
+        // Two groups of four warps; group e owns accumulator stage e (tiles e, e+2, e+4 ... of this CTA)
+        // and its own candidate lists, so both SMSP issue slots per quarter stay busy.
+        const int grp = (warp - 4) >> 2;
+        const int ew = (warp - 4) & 3;   // TMEM lane quarter this warp may read (== warp % 4)
         const int tq = ew * 32 + lane;   // query (TMEM lane) of this thread
         const int q = qb * TC_M + tq;
         constexpr int cap = CAP, R = CAP / 32;
         const int kc = a.kc;
-        uint64_t* mybuf = a.cand + ((size_t)blockIdx.x * TC_M + tq) * cap;
+        const int part = g * 2 + grp;
+        uint64_t* mybuf = a.cand + (((size_t)blockIdx.x * 2 + grp) * TC_M + tq) * cap;
+        uint32_t* slot = reinterpret_cast<uint32_t*>(base_ptr + slot_off) + (size_t)(warp - 4) * 1024;
         int cnt = 0;
         float tau = (q < a.nq) ? INFINITY : -INFINITY;  // padding queries never select
-        int as = 0;
+        const int as = grp;
         uint32_t aphase = 0;
-        for (int rt = g; rt < a.n_row_tiles; rt += a.groups) {
+        int it = 0;
+        for (int rt = g; rt < a.n_row_tiles; rt += a.groups, it++) {
+            if ((it & 1) != grp) continue;
             const uint32_t row0 = (uint32_t)rt * TC_N;
             mbar_wait(tfull_bar(as), aphase);
+            aphase ^= 1u;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * TC_N;
 #pragma unroll 1
@@ -267,6 +345,8 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     }
                 }
                 tmem_wait_ld();
+                // fast filter: ~2 instructions per key, no side effects
+                bool any = false;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     float dot;
@@ -276,22 +356,34 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     if constexpr (METRIC == METRIC_L2) key = fmaf(-2.f, dot, ax[j]);
                     else if constexpr (METRIC == METRIC_COSINE) key = -dot * ax[j];
                     else key = -dot;
-                    if (key < tau) {
+                    v[j] = __float_as_uint(key);
+                    any |= (key < tau);
+                }
+                if (any) {
+                    // slow path (rare after warm-up): park the keys in shared memory, walk the hits
+                    uint32_t hits = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        slot[j * 32 + lane] = v[j];
+                        hits |= (__uint_as_float(v[j]) < tau ? 1u : 0u) << j;
+                    }
+                    while (hits) {
+                        const int j = __ffs(hits) - 1;
+                        hits &= hits - 1;
                         const uint32_t row = row0 + c0 + j;
                         bool ok = row < a.n_rows;
                         if (ok && a.tomb != nullptr && row < a.tomb_bits && bit_set(a.tomb, row)) ok = false;
                         if (ok && a.allow != nullptr && !bit_set(a.allow, row)) ok = false;
-                        if (ok && cnt < cap) mybuf[cnt++] = pack_key(key, row);
+                        if (ok && cnt < cap) mybuf[cnt++] = pack_key(__uint_as_float(slot[j * 32 + lane]), row);
                     }
                 }
             }
-            // release the accumulator stage before any (slow) compaction
+            // release the accumulator stage before any compaction
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
-            if (++as == 2) { as = 0; aphase ^= 1u; }
 
-            // warp-cooperative compaction of every list that could overflow on the next tile
+            // warp-cooperative compaction of every list that could overflow on its next tile
             unsigned need = __ballot_sync(0xffffffffu, cnt > cap - TC_N);
             while (need) {
                 const int src = __ffs(need) - 1;
@@ -299,19 +391,23 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 const int c = __shfl_sync(0xffffffffu, cnt, src);
                 uint64_t* buf = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
                 __syncwarp();  // order the owner's appends before the other lanes' reads
-                const float nt = compact_list<R>(buf, buf, c, kc, lane);
+                int kept;
+                const float nt = select_compact<R>(buf, buf, c, kc, lane, &kept);
                 __syncwarp();
-                if (lane == src) { cnt = min(c, kc); tau = nt; }
+                if (lane == src) { cnt = kept; tau = nt; }
             }
         }
-        // final: sort every list, emit its best kc
+        // final: reduce every list to its best kc (unordered; the merge kernel sorts) and emit it
         for (int src = 0; src < 32; src++) {
             const int c = __shfl_sync(0xffffffffu, cnt, src);
             const int qq = __shfl_sync(0xffffffffu, q, src);
             const uint64_t* buf = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
             if (qq >= a.nq) continue;  // warp-uniform
             __syncwarp();
-            compact_list<R>(buf, a.partial + ((size_t)g * a.nq + qq) * kc, c, kc, lane);
+            uint64_t* out = a.partial + ((size_t)part * a.nq + qq) * kc;
+            int kept;
+            select_compact<R>(buf, out, c, kc, lane, &kept);
+            for (int t = kept + lane; t < kc; t += 32) out[t] = kInvalid;
         }
     }
 
@@ -376,7 +472,7 @@ void dense_scan_tc_plan(int nq, uint32_t n_rows, int sm_count, int kc, int* grou
     if (groups < 1) groups = 1;
     if (groups > n_row_tiles) groups = n_row_tiles;
     *groups_out = groups;
-    *cand_bytes = (size_t)nqb * groups * TC_M * cap * 8;
+    *cand_bytes = (size_t)nqb * groups * 2 * TC_M * cap * 8;  // two epilogue groups per CTA
 }
 
 cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand, cudaStream_t st) {
@@ -394,13 +490,13 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     int groups;
     size_t cand_bytes;
     dense_scan_tc_plan(s.nq, s.n_rows, sm_count, s.kc, &groups, &cand_bytes);
-    if (groups != s.parts) return cudaErrorInvalidValue;  // partial[] was sized for s.parts lists
+    if (2 * groups != s.parts) return cudaErrorInvalidValue;  // partial[] was sized for s.parts lists
     a.groups = groups;
     a.tomb = s.tomb; a.tomb_bits = s.tomb_bits; a.allow = s.allow;
     a.kc = s.kc; a.cap = next_pow2(s.kc + TC_N);
     if (a.cap < 512) a.cap = 512;
     a.cand = cand; a.partial = s.partial;
-    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 8 * (2 * TC_STAGES + 4) + 16;
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 8 * 32 * 32 * 4 + 8 * (2 * TC_STAGES + 4) + 16;
     const dim3 grid(nqb * groups);
 #define LB_TC1(KIND_, METRIC_, CAP_)                                                                           \
     {                                                                                                          \
