@@ -203,7 +203,7 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - l0
     _lib.prof_enable(False)
-    scan_ms, scan_n = _lib.prof_read(reset=True)
+    scan_ms, scan_n, scan_units = _lib.prof_read(reset=True)
     log(f"timed region done: {ms:.2f} ms")
     if sampler.summary()["samples"] < 5:  # timed region too short for NVML: keep sampling the same load
         t_end = time.time() + 1.0
@@ -271,7 +271,8 @@ def main():
         peak_tf = peaks.get("bf16_tflops", 1590.0)
         peak_src = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1.59 PFLOP/s"
         rows_local = hi - lo
-        flops_per_launch = 2.0 * NQ * rows_local * DIM
+        # algorithmic flops of the bracketed launches: 2 * D per (query, row) pair they scanned
+        flops_per_launch = 2.0 * DIM * scan_units / max(scan_n, 1)
         avg_scan_ms = scan_ms / max(scan_n, 1)
         achieved = flops_per_launch / (avg_scan_ms * 1e-3) / 1e12 if scan_n else None
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -279,7 +280,8 @@ def main():
                 "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "kernel": "coarse distance scan + fused top-k (dense_scan)", "avg_launch_ms": avg_scan_ms,
                 "launches_timed": scan_n, "share_of_step": scan_ms / ms if ms else None,
-                "scan_gbs": rows_local * DIM * 2 / (avg_scan_ms * 1e-3) / 1e9 if scan_n else None,
+                "rows_per_launch": scan_units / max(scan_n, 1) / NQ,
+                "scan_gbs": scan_units / max(scan_n, 1) / NQ * DIM * 2 / (avg_scan_ms * 1e-3) / 1e9 if scan_n else None,
                 "hbm_peak_gbs": hbm_peak}
         out = {
             "metric": METRIC_NAME, "value": NQ * steps / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,

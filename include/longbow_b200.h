@@ -193,14 +193,16 @@ int lb_filter_f32(int device, const float *column, int64_t n, int op, float valu
 int64_t lb_kernel_launch_count(void);
 /* Test / diagnostic knobs.  "dense_scan": 0 = auto (tensor-core scan when the index is eligible:
  * fp16 or int8, 16-byte row pitch), 1 = force the SIMT scan, 2 = force the tensor-core scan
- * (LB_ERR_UNSUPPORTED if not eligible).  Both scans feed the same exact re-score stage. */
+ * (LB_ERR_UNSUPPORTED if not eligible).  Both scans feed the same exact re-score stage.
+ * "tc_boot": 1 (default) = bootstrap-threshold pre-scan for the tensor-core path, 0 = off.
+ * "tc_debug": timing probes of the tensor-core scan; results are INVALID when non-zero. */
 int lb_set_option(const char *name, int value);
 /* Profiling hook for bench.py's roofline: when enabled, every search brackets its dominant
  * kernel (the coarse distance scan: dense or ADC) with CUDA events on the launching stream.
- * lb_prof_read waits for the recorded events, returns their summed duration and count and
- * (reset != 0) clears them. */
+ * lb_prof_read waits for the recorded events, returns their summed duration, their count and the
+ * (queries x rows) pairs those launches scanned, and (reset != 0) clears them. */
 int lb_prof_enable(int on);
-int lb_prof_read(double *total_ms, int64_t *launches, int reset);
+int lb_prof_read(double *total_ms, int64_t *launches, double *units, int reset);
 
 #ifdef __cplusplus
 }

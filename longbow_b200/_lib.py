@@ -69,7 +69,7 @@ SIGNATURES = {
     "lb_kernel_launch_count": (i64, []),
     "lb_set_option": (i32, [C.c_char_p, i32]),
     "lb_prof_enable": (i32, [i32]),
-    "lb_prof_read": (i32, [C.POINTER(C.c_double), C.POINTER(i64), i32]),
+    "lb_prof_read": (i32, [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double), i32]),
 }
 
 _lib = None
@@ -116,7 +116,7 @@ def prof_enable(on: bool) -> None:
 
 
 def prof_read(reset: bool = True):
-    """(total_ms, launches) of the dominant scan kernel since the last reset."""
-    ms, n = C.c_double(), i64()
-    load().lb_prof_read(C.byref(ms), C.byref(n), int(reset))
-    return ms.value, n.value
+    """(total_ms, launches, query-row pairs scanned) of the dominant scan kernel since the last reset."""
+    ms, n, u = C.c_double(), i64(), C.c_double()
+    load().lb_prof_read(C.byref(ms), C.byref(n), C.byref(u), int(reset))
+    return ms.value, n.value, u.value

@@ -88,16 +88,20 @@ struct Scratch {
 };
 
 // ---- options (lb_set_option)
-static std::atomic<int> g_opt_dense_scan{0};  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
+static std::atomic<int> g_opt_dense_scan{0};
+static std::atomic<int> g_opt_tc_debug{0};
+static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off (A/B timing)    // timing probes of the tensor-core scan (results invalid when != 0)  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
 
 // ---- dominant-kernel timing (lb_prof_*)
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static double g_prof_units = 0;  // sum over bracketed launches of (queries x rows) scanned
 struct ProfScope {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaStream_t st;
-    explicit ProfScope(cudaStream_t s) : st(s) {
+    double units;
+    ProfScope(cudaStream_t s, double u) : st(s), units(u) {
         if (g_prof_on.load(std::memory_order_relaxed)) {
             if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, st);
             else e0 = e1 = nullptr;
@@ -108,6 +112,7 @@ struct ProfScope {
             cudaEventRecord(e1, st);
             std::lock_guard<std::mutex> g(g_prof_mu);
             g_prof_events.emplace_back(e0, e1);
+            g_prof_units += units;
         }
     }
 };
@@ -120,7 +125,8 @@ using namespace lb;
 struct lb_index {
     int device, dim, dtype, metric;
     void* rows = nullptr;  // [capacity][dim]
-    float* aux = nullptr;  // [capacity]
+    float* aux = nullptr;  // [capacity + 256] coarse-key auxiliaries
+    float* nrm = nullptr;  // [capacity] cosine only: exact |x|^2 in reference lane order
     int64_t size = 0, capacity = 0;
     uint32_t* tomb = nullptr;
     int64_t tomb_bits = 0, tomb_cap_words = 0;
@@ -144,7 +150,8 @@ struct faiss_res {
     int device;
 };
 
-static int grow(void** buf, int64_t* cap, int64_t need, size_t row_bytes, int64_t used, float** aux) {
+static int grow(void** buf, int64_t* cap, int64_t need, size_t row_bytes, int64_t used, float** aux,
+                float** nrm = nullptr) {
     if (need <= *cap) return LB_OK;
     int64_t ncap = *cap + (*cap >> 1);
     if (ncap < need) ncap = need;
@@ -162,14 +169,21 @@ static int grow(void** buf, int64_t* cap, int64_t need, size_t row_bytes, int64_
         e = cudaMalloc((void**)&na, ((size_t)ncap + 256) * sizeof(float));  // +256: tile-tail reads
         if (e != cudaSuccess) { cudaFree(nb); return fail_cuda(e, "cudaMalloc(aux)"); }
     }
+    float* nn = nullptr;
+    if (nrm) {
+        e = cudaMalloc((void**)&nn, (size_t)ncap * sizeof(float));
+        if (e != cudaSuccess) { cudaFree(nb); if (na) cudaFree(na); return fail_cuda(e, "cudaMalloc(nrm)"); }
+    }
     CK(cudaDeviceSynchronize());
     if (used > 0) {
         CK(cudaMemcpy(nb, *buf, (size_t)used * row_bytes, cudaMemcpyDeviceToDevice));
         if (aux) CK(cudaMemcpy(na, *aux, (size_t)used * sizeof(float), cudaMemcpyDeviceToDevice));
+        if (nrm) CK(cudaMemcpy(nn, *nrm, (size_t)used * sizeof(float), cudaMemcpyDeviceToDevice));
     }
     if (*buf) cudaFree(*buf);
     *buf = nb;
     if (aux) { if (*aux) cudaFree(*aux); *aux = na; }
+    if (nrm) { if (*nrm) cudaFree(*nrm); *nrm = nn; }
     *cap = ncap;
     return LB_OK;
 }
@@ -192,6 +206,14 @@ int lb_set_option(const char* name, int value) {
         g_opt_dense_scan.store(value);
         return LB_OK;
     }
+    if (strcmp(name, "tc_boot") == 0) {
+        g_opt_tc_boot.store(value ? 1 : 0);
+        return LB_OK;
+    }
+    if (strcmp(name, "tc_debug") == 0) {
+        g_opt_tc_debug.store(value);
+        return LB_OK;
+    }
     return fail(LB_ERR_INVALID, "unknown option");
 }
 
@@ -199,7 +221,7 @@ int lb_prof_enable(int on) {
     g_prof_on.store(on ? 1 : 0);
     return LB_OK;
 }
-int lb_prof_read(double* total_ms, int64_t* launches, int reset) {
+int lb_prof_read(double* total_ms, int64_t* launches, double* units, int reset) {
     std::lock_guard<std::mutex> g(g_prof_mu);
     double tot = 0;
     int64_t n = 0;
@@ -211,9 +233,11 @@ int lb_prof_read(double* total_ms, int64_t* launches, int reset) {
         }
     }
     cudaGetLastError();
+    if (units) *units = g_prof_units;
     if (reset) {
         for (auto& pr : g_prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         g_prof_events.clear();
+        g_prof_units = 0;
     }
     if (total_ms) *total_ms = tot;
     if (launches) *launches = n;
@@ -254,6 +278,7 @@ void lb_index_free(lb_index* idx) {
         cudaDeviceSynchronize();
         if (idx->rows) cudaFree(idx->rows);
         if (idx->aux) cudaFree(idx->aux);
+        if (idx->nrm) cudaFree(idx->nrm);
         if (idx->tomb) cudaFree(idx->tomb);
     }
     cudaGetLastError();
@@ -273,14 +298,21 @@ int lb_index_reserve(lb_index* idx, int64_t n_rows) {
     if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(rows)");
     e = cudaMalloc((void**)&na, ((size_t)n_rows + 256) * 4);  // +256: tile-tail reads
     if (e != cudaSuccess) { cudaFree(nb); return fail_cuda(e, "cudaMalloc(aux)"); }
+    float* nn = nullptr;
+    if (idx->metric == METRIC_COSINE) {
+        e = cudaMalloc((void**)&nn, (size_t)n_rows * 4);
+        if (e != cudaSuccess) { cudaFree(nb); cudaFree(na); return fail_cuda(e, "cudaMalloc(nrm)"); }
+    }
     CK(cudaDeviceSynchronize());
     if (idx->size > 0) {
         CK(cudaMemcpy(nb, idx->rows, (size_t)idx->size * rb, cudaMemcpyDeviceToDevice));
         CK(cudaMemcpy(na, idx->aux, (size_t)idx->size * 4, cudaMemcpyDeviceToDevice));
+        if (nn) CK(cudaMemcpy(nn, idx->nrm, (size_t)idx->size * 4, cudaMemcpyDeviceToDevice));
     }
     if (idx->rows) cudaFree(idx->rows);
     if (idx->aux) cudaFree(idx->aux);
-    idx->rows = nb; idx->aux = na; idx->capacity = n_rows;
+    if (idx->nrm) cudaFree(idx->nrm);
+    idx->rows = nb; idx->aux = na; idx->nrm = nn; idx->capacity = n_rows;
     return LB_OK;
 }
 
@@ -293,7 +325,8 @@ static int index_add_common(lb_index* idx, const void* src, int64_t n, bool src_
     if (rc) return rc;
     if (idx->size + n > 0xfff00000ll) return fail(LB_ERR_INVALID, "more than 2^32 rows per device handle");
     size_t rb = (size_t)idx->dim * dtype_size(idx->dtype);
-    rc = grow(&idx->rows, &idx->capacity, idx->size + n, rb, idx->size, &idx->aux);
+    rc = grow(&idx->rows, &idx->capacity, idx->size + n, rb, idx->size, &idx->aux,
+              idx->metric == METRIC_COSINE ? &idx->nrm : nullptr);
     if (rc) return rc;
     char* dst = (char*)idx->rows + (size_t)idx->size * rb;
     CK(cudaMemcpyAsync(dst, src, (size_t)n * rb, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
@@ -301,6 +334,8 @@ static int index_add_common(lb_index* idx, const void* src, int64_t n, bool src_
     idx->size += n;
     if (idx->metric != METRIC_DOT)
         CK(launch_row_aux(idx->dtype, idx->rows, idx->size, idx->dim, idx->metric, idx->aux, row0, st));
+    if (idx->metric == METRIC_COSINE)
+        CK(launch_row_norm_exact(idx->dtype, idx->rows, idx->size, idx->dim, idx->nrm, row0, st));
     if (!src_on_device) CK(cudaStreamSynchronize(st));  // cgo: the Go slice may move after return
     return LB_OK;
 }
@@ -388,15 +423,49 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         uint64_t *partial, *merged;
         int parts;
         if (use_tc) {
-            size_t cand_bytes;
-            int groups;
-            dense_scan_tc_plan(cq, a.n_rows, idx->sm_count, kc, &groups, &cand_bytes);
-            parts = 2 * groups;  // two epilogue groups (candidate lists) per CTA
+            const int n_tiles = (int)((idx->size + 255) / 256);
+            a.tq = 128; a.cap = 0; a.rows_per_part = 0;
+            a.debug = g_opt_tc_debug.load(std::memory_order_relaxed);
+            // Bootstrap: scan a ~3% sample of the rows first; its kc-th best key per query is a valid
+            // upper bound of the global kc-th best, so the main scan starts with a tight threshold
+            // and its epilogue almost never leaves the 3-instruction filter (DESIGN.md "bootstrap").
+            int boot_tiles = 0;
+            if (n_tiles >= 64 && g_opt_tc_boot.load(std::memory_order_relaxed)) {
+                boot_tiles = n_tiles / 32;
+                if (boot_tiles < 16) boot_tiles = 16;
+                if (boot_tiles > 256) boot_tiles = 256;
+            }
+            size_t cand_bytes, cb2 = 0;
+            int gm, gb = 0;
+            dense_scan_tc_plan(cq, n_tiles - boot_tiles, idx->sm_count, kc, &gm, &cand_bytes);
+            if (boot_tiles) dense_scan_tc_plan(cq, boot_tiles, idx->sm_count, kc, &gb, &cb2);
             uint64_t* cand;
-            CK(scr.get((void**)&cand, cand_bytes));
+            CK(scr.get((void**)&cand, cand_bytes > cb2 ? cand_bytes : cb2));
+            const int extra = boot_tiles ? 1 : 0;
+            parts = 2 * gm + extra;
             CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
-            a.parts = parts; a.partial = partial; a.tq = 128; a.cap = 0; a.rows_per_part = 0;
-            ProfScope prof(st);
+            a.partial = partial;
+            if (boot_tiles) {
+                uint64_t *pboot, *kth;
+                float* tau;
+                CK(scr.get((void**)&pboot, (size_t)2 * gb * cq * kc * 8));
+                CK(scr.get((void**)&tau, (size_t)cq * 4));
+                CK(scr.get((void**)&kth, (size_t)cq * 8));
+                ScanArgs b = a;
+                b.parts = 2 * gb; b.partial = pboot; b.tile_begin = 0; b.tile_end = boot_tiles; b.part_offset = 0;
+                CK(launch_dense_scan_tc(b, idx->sm_count, cand, st));
+                // merged sample candidates -> slot 0 of partial[]; its kc-th value -> tau
+                if (merge_select_fits(2 * gb, kc)) {
+                    CK(launch_merge_select(pboot, 2 * gb, cq, kc, partial, kth, st));
+                    CK(launch_tau_from_kth(kth, cq, 1, 0, tau, st));
+                } else {
+                    CK(launch_merge_partials(pboot, 2 * gb, cq, kc, partial, st));  // sorted
+                    CK(launch_tau_from_kth(partial, cq, kc, kc - 1, tau, st));
+                }
+                a.tau_init = tau;
+            }
+            a.parts = 2 * gm; a.tile_begin = boot_tiles; a.tile_end = n_tiles; a.part_offset = extra;
+            ProfScope prof(st, (double)cq * (double)(idx->size - (int64_t)boot_tiles * 256));
             CK(launch_dense_scan_tc(a, idx->sm_count, cand, st));
         } else {
             a.tq = (kc <= 128 && cq > 32) ? 64 : (kc <= 384 && cq > 16) ? 32 : 16;
@@ -414,16 +483,19 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
             a.parts = parts; a.rows_per_part = (uint32_t)rpp;
             CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
             a.partial = partial;
-            ProfScope prof(st);
+            ProfScope prof(st, (double)cq * (double)idx->size);
             CK(launch_dense_scan_simt(a, st));
         }
         if (parts > 1) {
             CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
-            CK(launch_merge_partials(partial, parts, cq, kc, merged, st));
+            // the re-score stage sorts its kc exact distances, so an unordered top-kc is enough
+            if (merge_select_fits(parts, kc)) CK(launch_merge_select(partial, parts, cq, kc, merged, nullptr, st));
+            else CK(launch_merge_partials(partial, parts, cq, kc, merged, st));
         } else {
             merged = partial;
         }
         RescoreArgs r;
+        r.nrm = idx->nrm;
         r.dtype = idx->dtype; r.metric = idx->metric; r.db = idx->rows; r.n_rows = (uint32_t)idx->size;
         r.dim = idx->dim; r.queries = a.queries; r.nq = cq; r.packed = merged; r.ids32 = nullptr;
         r.c = kc; r.k = k; r.tomb = nullptr; r.tomb_bits = 0; r.allow = nullptr; r.id_base = idx->id_base;
@@ -477,6 +549,7 @@ static int rerank_core(lb_index* idx, const void* d_q, int64_t nq, const uint32_
     if (nq == 0) return LB_OK;
     if (c > 1024) return fail(LB_ERR_UNSUPPORTED, "more than 1024 candidates per query");
     RescoreArgs r;
+    r.nrm = idx->nrm;
     r.dtype = idx->dtype; r.metric = idx->metric; r.db = idx->rows; r.n_rows = (uint32_t)idx->size;
     r.dim = idx->dim; r.queries = d_q; r.nq = (int)nq; r.packed = nullptr; r.ids32 = d_ids;
     r.c = c; r.k = k; r.tomb = idx->tomb;
@@ -834,7 +907,7 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
         CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
         a.partial = partial;
         {
-            ProfScope prof(st);
+            ProfScope prof(st, (double)cq * (double)pq->size);
             CK(launch_adc_scan(a, st));
         }
         if (parts > 1) {

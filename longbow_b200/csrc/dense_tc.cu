@@ -71,10 +71,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !ok; spins++) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok && (spins & 255u) == 255u) {
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");  // sleep (<= 1 ms) instead of spinning
+        if (!ok && (spins & 15u) == 15u) {
             const uint64_t now = global_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 2000000000ull) __trap();
@@ -144,6 +144,10 @@ struct TcArgs {
     int kc, cap;
     uint64_t* cand;     // [grid][128][cap] per-(CTA, query) candidate lists (global, L2-resident)
     uint64_t* partial;  // [G][nq][kc]
+    int debug;          // timing probes only (results invalid): 1 no epilogue work, 2 reuse B tile, 4 reuse A tile
+    int tile_begin, tile_end;  // row tiles [begin, end) scanned by this launch
+    int part_offset;           // first partial[] slot written by this launch
+    const float* tau_init;     // per-query starting threshold (bootstrap), or null
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -167,9 +171,23 @@ __device__ __forceinline__ float select_compact(const uint64_t* buf, uint64_t* d
     }
     uint32_t T = 0xffffffffu;  // keep everything valid when c < kc
     if (c >= kc) {
-        T = 0;
+        // bits shared by every valid key need no search: start below the common prefix
+        uint32_t all_and = 0xffffffffu, all_or = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (v[r] != kInvalid) { all_and &= (uint32_t)(v[r] >> 32); all_or |= (uint32_t)(v[r] >> 32); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            all_and &= __shfl_xor_sync(0xffffffffu, all_and, o);
+            all_or |= __shfl_xor_sync(0xffffffffu, all_or, o);
+        }
+        const uint32_t diff = all_and ^ all_or;
+        const int top = diff ? (31 - __clz(diff)) : -1;  // highest bit where keys differ
+        T = (top >= 31) ? 0u : (all_and & ~((2u << top) - 1u));
+        if (top < 0) T = all_and;
 #pragma unroll 1
-        for (int bit = 31; bit >= 0; bit--) {
+        for (int bit = top; bit >= 0; bit--) {
             const uint32_t test = T | (1u << bit);
             int less = 0;
 #pragma unroll
@@ -270,13 +288,15 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int rt = g; rt < a.n_row_tiles; rt += a.groups) {
+            for (int rt = a.tile_begin + g; rt < a.tile_end; rt += a.groups) {
                 for (int kb = 0; kb < a.k_blocks; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+                    const bool first = ((rt - a.tile_begin - g) / a.groups) * a.k_blocks + kb < TC_STAGES;
+                    const bool ld_a = !(a.debug & 4) || first, ld_b = !(a.debug & 2) || first;
+                    mbar_arrive_expect_tx(full_bar(stage), (ld_a ? TC_A_BYTES : 0) + (ld_b ? TC_B_BYTES : 0));
                     const uint32_t sa = base + stage * TC_STAGE_BYTES;
-                    tma_load_2d(sa, &map_q, full_bar(stage), kb * TR::kBlockK, qb * TC_M);
-                    tma_load_2d(sa + TC_A_BYTES, &map_db, full_bar(stage), kb * TR::kBlockK, rt * TC_N);
+                    if (ld_a) tma_load_2d(sa, &map_q, full_bar(stage), kb * TR::kBlockK, qb * TC_M);
+                    if (ld_b) tma_load_2d(sa + TC_A_BYTES, &map_db, full_bar(stage), kb * TR::kBlockK, rt * TC_N);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -287,7 +307,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             const uint32_t idesc = TR::kIdescFmt | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int rt = g; rt < a.n_row_tiles; rt += a.groups) {
+            for (int rt = a.tile_begin + g; rt < a.tile_end; rt += a.groups) {
                 mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * TC_N;
@@ -316,15 +336,20 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int q = qb * TC_M + tq;
         constexpr int cap = CAP, R = CAP / 32;
         const int kc = a.kc;
-        const int part = g * 2 + grp;
+        const int part = a.part_offset + g * 2 + grp;
         uint64_t* mybuf = a.cand + (((size_t)blockIdx.x * 2 + grp) * TC_M + tq) * cap;
         uint32_t* slot = reinterpret_cast<uint32_t*>(base_ptr + slot_off) + (size_t)(warp - 4) * 1024;
         int cnt = 0;
-        float tau = (q < a.nq) ? INFINITY : -INFINITY;  // padding queries never select
+        float tau = -INFINITY;  // padding queries never select
+        if (q < a.nq) tau = (a.tau_init != nullptr) ? __ldg(a.tau_init + q) : INFINITY;
+        if (a.debug & 8) tau = -0.14f;  // probe: pretend a tight threshold is already known
+        const uint32_t n_rows = a.n_rows, tomb_bits = a.tomb_bits;
+        const uint32_t* __restrict__ tomb = a.tomb;
+        const uint32_t* __restrict__ allow = a.allow;
         const int as = grp;
         uint32_t aphase = 0;
         int it = 0;
-        for (int rt = g; rt < a.n_row_tiles; rt += a.groups, it++) {
+        for (int rt = a.tile_begin + g; rt < a.tile_end; rt += a.groups, it++) {
             if ((it & 1) != grp) continue;
             const uint32_t row0 = (uint32_t)rt * TC_N;
             mbar_wait(tfull_bar(as), aphase);
@@ -332,7 +357,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * TC_N;
 #pragma unroll 1
-            for (int c0 = 0; c0 < TC_N; c0 += 32) {
+            for (int c0 = 0; c0 < ((a.debug & 1) ? 0 : TC_N); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 float ax[32];
@@ -345,8 +370,8 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     }
                 }
                 tmem_wait_ld();
-                // fast filter: ~2 instructions per key, no side effects
-                bool any = false;
+                // fast filter: ~3 instructions per key (key, compare, mask), no side effects
+                uint32_t hits = 0;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     float dot;
@@ -357,45 +382,40 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     else if constexpr (METRIC == METRIC_COSINE) key = -dot * ax[j];
                     else key = -dot;
                     v[j] = __float_as_uint(key);
-                    any |= (key < tau);
+                    if (key < tau) hits |= 1u << j;
                 }
-                if (any) {
+                if (hits) {
                     // slow path (rare after warm-up): park the keys in shared memory, walk the hits
-                    uint32_t hits = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        slot[j * 32 + lane] = v[j];
-                        hits |= (__uint_as_float(v[j]) < tau ? 1u : 0u) << j;
-                    }
-                    while (hits) {
+                    for (int j = 0; j < 32; j++) slot[j * 32 + lane] = v[j];
+                    do {
                         const int j = __ffs(hits) - 1;
                         hits &= hits - 1;
                         const uint32_t row = row0 + c0 + j;
-                        bool ok = row < a.n_rows;
-                        if (ok && a.tomb != nullptr && row < a.tomb_bits && bit_set(a.tomb, row)) ok = false;
-                        if (ok && a.allow != nullptr && !bit_set(a.allow, row)) ok = false;
-                        if (ok && cnt < cap) mybuf[cnt++] = pack_key(__uint_as_float(slot[j * 32 + lane]), row);
-                    }
+                        bool ok = row < n_rows;
+                        if (ok && tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) ok = false;
+                        if (ok && allow != nullptr && !bit_set(allow, row)) ok = false;
+                        if (ok) mybuf[cnt++] = pack_key(__uint_as_float(slot[j * 32 + lane]), row);
+                    } while (hits);
+                }
+                // warp-cooperative compaction of every list that could overflow in its next chunk
+                unsigned need = __ballot_sync(0xffffffffu, cnt > cap - 32);
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int c = __shfl_sync(0xffffffffu, cnt, src);
+                    uint64_t* buf = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
+                    __syncwarp();  // order the owner's appends before the other lanes' reads
+                    int kept;
+                    const float nt = select_compact<R>(buf, buf, c, kc, lane, &kept);
+                    __syncwarp();
+                    if (lane == src) { cnt = kept; tau = nt; }
                 }
             }
-            // release the accumulator stage before any compaction
+            // release the accumulator stage
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
-
-            // warp-cooperative compaction of every list that could overflow on its next tile
-            unsigned need = __ballot_sync(0xffffffffu, cnt > cap - TC_N);
-            while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                const int c = __shfl_sync(0xffffffffu, cnt, src);
-                uint64_t* buf = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
-                __syncwarp();  // order the owner's appends before the other lanes' reads
-                int kept;
-                const float nt = select_compact<R>(buf, buf, c, kc, lane, &kept);
-                __syncwarp();
-                if (lane == src) { cnt = kept; tau = nt; }
-            }
         }
         // final: reduce every list to its best kc (unordered; the merge kernel sorts) and emit it
         for (int src = 0; src < 32; src++) {
@@ -417,6 +437,24 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+// Bootstrap threshold: the kc-th best key over the sample rows bounds the global kc-th best from
+// above, so the main scan can start every list at it.  nextafter(+inf) turns the strict '<' of the
+// filter into '<=': a row tying that key with a smaller row id must still get through.
+__global__ void tau_from_kth_kernel(const uint64_t* __restrict__ kth, int nq, int stride, int off,
+                                    float* __restrict__ tau) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint64_t p = kth[(size_t)q * stride + off];
+    tau[q] = (p == kInvalid) ? INFINITY : nextafterf(key_of(p), INFINITY);
+}
+
+cudaError_t launch_tau_from_kth(const uint64_t* kth, int nq, int stride, int off, float* tau, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    tau_from_kth_kernel<<<(nq + 127) / 128, 128, 0, st>>>(kth, nq, stride, off, tau);
+    count_launch();
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------- host side
@@ -463,11 +501,10 @@ bool dense_tc_eligible(int dtype, int dim, const void* db, const void* queries, 
 }
 
 // groups (= number of partial lists per query) and the size of the candidate scratch
-void dense_scan_tc_plan(int nq, uint32_t n_rows, int sm_count, int kc, int* groups_out, size_t* cand_bytes) {
+void dense_scan_tc_plan(int nq, int n_row_tiles, int sm_count, int kc, int* groups_out, size_t* cand_bytes) {
     int cap = next_pow2(kc + TC_N);
     if (cap < 512) cap = 512;
     const int nqb = (nq + TC_M - 1) / TC_M;
-    const int n_row_tiles = (int)((n_rows + TC_N - 1) / TC_N);
     int groups = sm_count / nqb;
     if (groups < 1) groups = 1;
     if (groups > n_row_tiles) groups = n_row_tiles;
@@ -489,13 +526,17 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     const int nqb = (s.nq + TC_M - 1) / TC_M;
     int groups;
     size_t cand_bytes;
-    dense_scan_tc_plan(s.nq, s.n_rows, sm_count, s.kc, &groups, &cand_bytes);
+    a.tile_begin = s.tile_begin;
+    a.tile_end = s.tile_end < 0 ? a.n_row_tiles : s.tile_end;
+    a.part_offset = s.part_offset;
+    a.tau_init = s.tau_init;
+    dense_scan_tc_plan(s.nq, a.tile_end - a.tile_begin, sm_count, s.kc, &groups, &cand_bytes);
     if (2 * groups != s.parts) return cudaErrorInvalidValue;  // partial[] was sized for s.parts lists
     a.groups = groups;
     a.tomb = s.tomb; a.tomb_bits = s.tomb_bits; a.allow = s.allow;
     a.kc = s.kc; a.cap = next_pow2(s.kc + TC_N);
     if (a.cap < 512) a.cap = 512;
-    a.cand = cand; a.partial = s.partial;
+    a.cand = cand; a.partial = s.partial; a.debug = s.debug;
     const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 8 * 32 * 32 * 4 + 8 * (2 * TC_STAGES + 4) + 16;
     const dim3 grid(nqb * groups);
 #define LB_TC1(KIND_, METRIC_, CAP_)                                                                           \

@@ -23,6 +23,10 @@ struct ScanArgs {
     int parts;
     uint32_t rows_per_part;  // multiple of 128
     uint64_t* partial;       // [parts][nq][kc]
+    int debug = 0;           // tensor-core scan timing probes (lb_set_option "tc_debug")
+    // tensor-core scan only: sub-range of 256-row tiles, first partial[] slot, bootstrap thresholds
+    int tile_begin = 0, tile_end = -1, part_offset = 0;
+    const float* tau_init = nullptr;
 };
 
 struct RescoreArgs {
@@ -42,6 +46,7 @@ struct RescoreArgs {
     float* out_d;            // [nq][k]
     int64_t* out_l;          // [nq][k]
     int negate_dot;          // 1: dot returned as a distance (negated)
+    const float* nrm = nullptr;  // cosine only: exact per-row |x|^2 (reference lane order), or null
 };
 
 size_t dense_scan_simt_smem(int tq, int cap);
@@ -49,6 +54,11 @@ cudaError_t launch_dense_scan_simt(const ScanArgs& a, cudaStream_t st);
 cudaError_t launch_row_aux(int dtype, const void* db, int64_t n, int dim, int metric, float* aux, int64_t row0,
                            cudaStream_t st);
 cudaError_t launch_merge_partials(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged,
+                                  cudaStream_t st);
+bool merge_select_fits(int parts, int kc);
+cudaError_t launch_merge_select(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged, uint64_t* kth,
+                                cudaStream_t st);
+cudaError_t launch_row_norm_exact(int dtype, const void* db, int64_t n, int dim, float* nrm, int64_t row0,
                                   cudaStream_t st);
 cudaError_t launch_rescore(const RescoreArgs& a, cudaStream_t st);
 cudaError_t launch_batch_flat(int metric, int dtype, const void* db, int64_t n, int dim, const void* query,
@@ -60,7 +70,8 @@ cudaError_t launch_merge_topk(const float* in_d, const int64_t* in_l, int parts,
 
 // ---- tensor-core scan (dense_tc.cu)
 bool dense_tc_eligible(int dtype, int dim, const void* db, const void* queries, int kc);
-void dense_scan_tc_plan(int nq, uint32_t n_rows, int sm_count, int kc, int* groups_out, size_t* cand_bytes);
+void dense_scan_tc_plan(int nq, int n_row_tiles, int sm_count, int kc, int* groups_out, size_t* cand_bytes);
+cudaError_t launch_tau_from_kth(const uint64_t* kth, int nq, int stride, int off, float* tau, cudaStream_t st);
 cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand, cudaStream_t st);
 
 // ---- PQ (kernels_pq.cu)

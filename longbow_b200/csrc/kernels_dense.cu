@@ -35,6 +35,41 @@ __global__ void row_aux_kernel(const T* __restrict__ db, int64_t n, int dim, int
     if (lane == 0) aux[r] = (metric == METRIC_COSINE) ? (s > 0.f ? rsqrtf(s) : 0.f) : s;
 }
 
+// Exact |x_r|^2 in the reference's 4-lane order (simd.go:399-450 accumulates normB this way inside
+// the cosine loop).  Stored once per row at add time so the cosine re-score only has to run the dot
+// chain; the value is bit-identical to what the reference recomputes for every pair.
+template <typename T>
+__global__ void row_norm_exact_kernel(const T* __restrict__ db, int64_t n, int dim, float* __restrict__ nrm,
+                                      int64_t row0) {
+    int64_t r = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const T* row = db + r * dim;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int i = 0;
+    for (; i <= dim - 4; i += 4) {
+        const float x0 = Elem<T>::widen(row[i]), x1 = Elem<T>::widen(row[i + 1]);
+        const float x2 = Elem<T>::widen(row[i + 2]), x3 = Elem<T>::widen(row[i + 3]);
+        s0 = __fadd_rn(s0, __fmul_rn(x0, x0)); s1 = __fadd_rn(s1, __fmul_rn(x1, x1));
+        s2 = __fadd_rn(s2, __fmul_rn(x2, x2)); s3 = __fadd_rn(s3, __fmul_rn(x3, x3));
+    }
+    for (; i < dim; i++) { const float x = Elem<T>::widen(row[i]); s0 = __fadd_rn(s0, __fmul_rn(x, x)); }
+    nrm[r] = __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
+}
+
+cudaError_t launch_row_norm_exact(int dtype, const void* db, int64_t n, int dim, float* nrm, int64_t row0,
+                                  cudaStream_t st) {
+    if (n <= row0) return cudaSuccess;
+    unsigned blocks = (unsigned)((n - row0 + 127) / 128);
+    switch (dtype) {
+        case DT_F32: row_norm_exact_kernel<float><<<blocks, 128, 0, st>>>((const float*)db, n, dim, nrm, row0); break;
+        case DT_F16: row_norm_exact_kernel<__half><<<blocks, 128, 0, st>>>((const __half*)db, n, dim, nrm, row0); break;
+        case DT_I8: row_norm_exact_kernel<int8_t><<<blocks, 128, 0, st>>>((const int8_t*)db, n, dim, nrm, row0); break;
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // S1: SIMT coarse scan with fused selection.
 //   grid  = (parts, ceil(nq / TQ)); block = 256 threads
@@ -306,6 +341,106 @@ merge_partials_kernel(const uint64_t* __restrict__ partial, int parts, int nq, i
         merged[(size_t)q * kc + t] = (t < have) ? buf[t] : kInvalid;
 }
 
+// ---------------------------------------------------------------------------------------------
+// S2 (selection form): per query, keep the kc smallest of parts*kc packed entries WITHOUT sorting:
+// block-wide MSB-first radix select (8 passes x 8 bits over the packed 64-bit (key,row) value, so
+// ties in the key are resolved by row id), then an unordered compaction.  Entries live in
+// registers (<= 20 per thread).  ~10x fewer instructions than the bitonic merge; the re-score
+// stage sorts its kc exact distances anyway.  Optionally reports the kc-th value (bootstrap).
+// ---------------------------------------------------------------------------------------------
+constexpr int MSEL_E = 20;
+constexpr int MSEL_T = 256;
+
+__global__ void __launch_bounds__(MSEL_T)
+merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int kc, uint64_t* __restrict__ merged,
+                    uint64_t* __restrict__ kth) {
+    __shared__ int hist[256];
+    __shared__ int s_bin, s_before, s_out;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int total = parts * kc;
+    uint64_t v[MSEL_E];
+    int nvalid = 0;
+#pragma unroll
+    for (int e = 0; e < MSEL_E; e++) {
+        const int i = e * MSEL_T + tid;
+        uint64_t x = kInvalid;
+        if (i < total) x = partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)];
+        v[e] = x;
+        nvalid += (x != kInvalid);
+    }
+    if (tid == 0) s_out = 0;
+    // total number of valid entries
+    hist[tid] = 0;
+    __syncthreads();
+    atomicAdd(&hist[0], nvalid);
+    __syncthreads();
+    const int n_valid_total = hist[0];
+    __syncthreads();
+    uint64_t T = kInvalid;  // keep everything valid when there are fewer than kc
+    if (n_valid_total >= kc) {
+        uint64_t prefix = 0;
+        int remaining = kc;  // rank (1-based) of the wanted element inside the current prefix class
+        for (int pass = 0; pass < 8; pass++) {
+            const int shift = 56 - 8 * pass;
+            hist[tid] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < MSEL_E; e++) {
+                const uint64_t x = v[e];
+                const bool in_class = (pass == 0) || ((x >> (shift + 8)) == (prefix >> (shift + 8)));
+                if (x != kInvalid && in_class) atomicAdd(&hist[(int)((x >> shift) & 255)], 1);
+            }
+            __syncthreads();
+            if (tid < 32) {  // warp 0: 8 bins per lane, find the bin holding rank `remaining`
+                int loc[8], sum = 0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) { loc[b] = hist[tid * 8 + b]; sum += loc[b]; }
+                int inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (tid >= o) inc += up;
+                }
+                const int exc = inc - sum;
+                if (remaining > exc && remaining <= inc) {
+                    int acc = exc;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        if (remaining > acc && remaining <= acc + loc[b]) { s_bin = tid * 8 + b; s_before = acc; }
+                        acc += loc[b];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= (uint64_t)s_bin << shift;
+            remaining -= s_before;
+            __syncthreads();
+        }
+        T = prefix;  // the kc-th smallest packed value
+    }
+    // unordered compaction of everything <= T (exactly kc entries when n_valid_total >= kc)
+#pragma unroll
+    for (int e = 0; e < MSEL_E; e++) {
+        if (v[e] != kInvalid && v[e] <= T) {
+            const int pos = atomicAdd(&s_out, 1);
+            if (pos < kc) merged[(size_t)q * kc + pos] = v[e];
+        }
+    }
+    __syncthreads();
+    for (int t = s_out + tid; t < kc; t += MSEL_T) merged[(size_t)q * kc + t] = kInvalid;
+    if (kth != nullptr && tid == 0) kth[q] = T;  // kInvalid when fewer than kc valid entries exist
+}
+
+bool merge_select_fits(int parts, int kc) { return (int64_t)parts * kc <= (int64_t)MSEL_E * MSEL_T; }
+
+cudaError_t launch_merge_select(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged, uint64_t* kth,
+                                cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    merge_select_kernel<<<nq, MSEL_T, 0, st>>>(partial, parts, nq, kc, merged, kth);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_merge_partials(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged,
                                   cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
@@ -329,15 +464,30 @@ __global__ void rescore_kernel(const T* __restrict__ db, uint32_t n_rows, int di
                                int nq, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ids32,
                                int c, int k, const uint32_t* __restrict__ tomb, uint32_t tomb_bits,
                                const uint32_t* __restrict__ allow, int64_t id_base, float* __restrict__ out_d,
-                               int64_t* __restrict__ out_l, int negate_dot) {
+                               int64_t* __restrict__ out_l, int negate_dot, const float* __restrict__ nrm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n2 = blockDim.x;
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [n2]
     float* qf = reinterpret_cast<float*>(keys + n2);          // [dim]
+    __shared__ float s_qn[4];
     const int q = blockIdx.x;
     const T* qrow = queries + (size_t)q * dim;
     for (int i = threadIdx.x; i < dim; i += blockDim.x) qf[i] = Elem<T>::widen(qrow[i]);
     __syncthreads();
+    // cosine with stored row norms: the query's |q|^2 once per block, reference lane order
+    // (lane l sums elements 4m+l; the dim % 4 tail goes to lane 0), simd.go:399-450
+    const bool use_nrm = (METRIC == METRIC_COSINE) && (nrm != nullptr);
+    if (use_nrm) {
+        if (threadIdx.x < 4) {
+            const int l = threadIdx.x;
+            float sacc = 0.f;
+            const int main_end = dim - (dim & 3);
+            for (int i = l; i < main_end; i += 4) sacc = __fadd_rn(sacc, __fmul_rn(qf[i], qf[i]));
+            if (l == 0) for (int i = main_end; i < dim; i++) sacc = __fadd_rn(sacc, __fmul_rn(qf[i], qf[i]));
+            s_qn[l] = sacc;
+        }
+        __syncthreads();
+    }
 
     uint64_t mine = kInvalid;
     if ((int)threadIdx.x < c) {
@@ -355,7 +505,16 @@ __global__ void rescore_kernel(const T* __restrict__ db, uint32_t n_rows, int di
         if (ok) {
             const T* row = db + (size_t)id * dim;
             const bool vec_ok = (dim % Elem<T>::kVec == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-            float d = exact_pair<T, METRIC>(qf, row, dim, vec_ok);
+            float d;
+            if (use_nrm) {
+                const float dot = exact_pair<T, METRIC_DOT>(qf, row, dim, vec_ok);
+                const float na = __fadd_rn(__fadd_rn(__fadd_rn(s_qn[0], s_qn[1]), s_qn[2]), s_qn[3]);
+                const float nb = __ldg(nrm + id);
+                if (na == 0.f || nb == 0.f) d = 1.0f;
+                else d = __fsub_rn(1.0f, __fdiv_rn(dot, (float)sqrt((double)na * (double)nb)));
+            } else {
+                d = exact_pair<T, METRIC>(qf, row, dim, vec_ok);
+            }
             if (METRIC == METRIC_DOT && negate_dot) d = -d;
             if (d < INFINITY) mine = pack_key(d, id);  // NaN / +Inf are never returned
         }
@@ -385,7 +544,7 @@ static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
         }                                                                                                   \
         kern<<<a.nq, n2, smem, st>>>((const T*)a.db, a.n_rows, a.dim, (const T*)a.queries, a.nq, a.packed,  \
                                      a.ids32, a.c, a.k, a.tomb, a.tomb_bits, a.allow, a.id_base, a.out_d,   \
-                                     a.out_l, a.negate_dot);                                                \
+                                     a.out_l, a.negate_dot, a.nrm);                                         \
     }
     switch (a.metric) {
         case METRIC_L2: LB_RS(METRIC_L2) break;

@@ -374,3 +374,25 @@ def test_tensor_core_ineligible_is_loud(lbgpu, scan_mode):
     d, l = idx.search(np.ones((1, 7), np.float16), 3)  # auto falls to the SIMT scan
     assert list(l[0]) == [0, 1, 2]
     idx.close()
+
+
+def test_tensor_core_bootstrap_ties_and_toggle(lbgpu, oracle, scan_mode):
+    # every vector appears 4 times, copies straddle the bootstrap sample / main scan boundary: the
+    # (distance, id) order must survive the bootstrap threshold (it admits ties: nextafter)
+    from longbow_b200 import _lib
+    rng = np.random.default_rng(31)
+    base = make_db(rng, 5000, 128, np.float16)
+    db = np.concatenate([base, base, base, base])
+    q = base[rng.integers(0, 5000, 150)]
+    idx = lbgpu.DenseIndex(128, np.float16, COS)
+    idx.add(db)
+    wd, wl = oracle.search(COS, db, q, 10)
+    scan_mode(2)
+    try:
+        for boot in (1, 0):
+            _lib.set_option("tc_boot", boot)
+            gd, gl = idx.search(q, 10)
+            assert_topk_equal(gd, gl, wd, wl, 0.0, f"boot={boot}")
+    finally:
+        _lib.set_option("tc_boot", 1)
+    idx.close()
