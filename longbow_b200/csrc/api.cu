@@ -426,46 +426,47 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
             const int n_tiles = (int)((idx->size + 255) / 256);
             a.tq = 128; a.cap = 0; a.rows_per_part = 0;
             a.debug = g_opt_tc_debug.load(std::memory_order_relaxed);
-            // Bootstrap: scan a ~3% sample of the rows first; its kc-th best key per query is a valid
-            // upper bound of the global kc-th best, so the main scan starts with a tight threshold
-            // and its epilogue almost never leaves the 3-instruction filter (DESIGN.md "bootstrap").
+            // Bootstrap: the first 32 row tiles (8192 rows) are scanned in "dump keys" mode into a small
+            // [nq][8192] matrix; a radix select gives each query its kc best sample rows and their
+            // kc-th key, a valid upper bound of the global kc-th best.  The main scan starts every
+            // list at that threshold, so its epilogue almost never leaves the 3-instruction filter
+            // (DESIGN.md "bootstrap threshold").
+            // Sample size ~ the rows one candidate list will see in the main scan (so a list expects
+            // fewer than kc survivors), clamped to [8, 128] tiles; small indexes skip the bootstrap.
             int boot_tiles = 0;
-            if (n_tiles >= 64 && g_opt_tc_boot.load(std::memory_order_relaxed)) {
-                boot_tiles = n_tiles / 32;
-                if (boot_tiles < 16) boot_tiles = 16;
-                if (boot_tiles > 256) boot_tiles = 256;
+            size_t cand_bytes;
+            int gm;
+            dense_scan_tc_plan(cq, n_tiles, idx->sm_count, kc, &gm, &cand_bytes);
+            if (g_opt_tc_boot.load(std::memory_order_relaxed)) {
+                int bt = (n_tiles + 2 * gm - 1) / (2 * gm);
+                if (bt < 8) bt = 8;
+                if (bt > 128) bt = 128;
+                if (bt * 4 <= n_tiles) boot_tiles = bt;
             }
-            size_t cand_bytes, cb2 = 0;
-            int gm, gb = 0;
             dense_scan_tc_plan(cq, n_tiles - boot_tiles, idx->sm_count, kc, &gm, &cand_bytes);
-            if (boot_tiles) dense_scan_tc_plan(cq, boot_tiles, idx->sm_count, kc, &gb, &cb2);
             uint64_t* cand;
-            CK(scr.get((void**)&cand, cand_bytes > cb2 ? cand_bytes : cb2));
+            CK(scr.get((void**)&cand, cand_bytes));
             const int extra = boot_tiles ? 1 : 0;
             parts = 2 * gm + extra;
             CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
             a.partial = partial;
             if (boot_tiles) {
-                uint64_t *pboot, *kth;
-                float* tau;
-                CK(scr.get((void**)&pboot, (size_t)2 * gb * cq * kc * 8));
+                const int S = boot_tiles * 256;
+                float *keys, *tau;
+                uint64_t* kth;
+                CK(scr.get((void**)&keys, (size_t)cq * S * 4));
                 CK(scr.get((void**)&tau, (size_t)cq * 4));
                 CK(scr.get((void**)&kth, (size_t)cq * 8));
                 ScanArgs b = a;
-                b.parts = 2 * gb; b.partial = pboot; b.tile_begin = 0; b.tile_end = boot_tiles; b.part_offset = 0;
+                b.parts = 0; b.partial = nullptr; b.tile_begin = 0; b.tile_end = boot_tiles; b.part_offset = 0;
+                b.keys_out = keys; b.keys_ld = S;
                 CK(launch_dense_scan_tc(b, idx->sm_count, cand, st));
-                // merged sample candidates -> slot 0 of partial[]; its kc-th value -> tau
-                if (merge_select_fits(2 * gb, kc)) {
-                    CK(launch_merge_select(pboot, 2 * gb, cq, kc, partial, kth, st));
-                    CK(launch_tau_from_kth(kth, cq, 1, 0, tau, st));
-                } else {
-                    CK(launch_merge_partials(pboot, 2 * gb, cq, kc, partial, st));  // sorted
-                    CK(launch_tau_from_kth(partial, cq, kc, kc - 1, tau, st));
-                }
+                CK(launch_sample_select(keys, S, S, a.n_rows, a.tomb, a.tomb_bits, a.allow, cq, kc, partial, kth, st));
+                CK(launch_tau_from_kth(kth, cq, 1, 0, tau, st));
                 a.tau_init = tau;
             }
             a.parts = 2 * gm; a.tile_begin = boot_tiles; a.tile_end = n_tiles; a.part_offset = extra;
-            ProfScope prof(st, (double)cq * (double)(idx->size - (int64_t)boot_tiles * 256));
+            ProfScope prof(st, (double)cq * (double)(idx->size - (int64_t)boot_tiles * 256));  // main scan only
             CK(launch_dense_scan_tc(a, idx->sm_count, cand, st));
         } else {
             a.tq = (kc <= 128 && cq > 32) ? 64 : (kc <= 384 && cq > 16) ? 32 : 16;

@@ -282,6 +282,79 @@ __device__ __forceinline__ void warp_sort_regs(uint64_t (&v)[R], int lane) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Block-wide k-th smallest of packed (key,row) values held E per thread in registers.
+// MSB-first bitwise search on the 32-bit key (skipping the prefix all keys share), then -- only if
+// the k-th key is tied and not every tie is wanted -- on the row id.  Counting is a warp shuffle
+// reduction plus one shared-memory exchange per bit; no atomics, so degenerate key distributions
+// (all keys in one radix bin) cost the same as uniform ones.
+// Returns kInvalid if fewer than k valid values exist.  s_red: shared int[64].  All threads call.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_sum_i(int x, int* s_red, int tid, int nwarps) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = x;
+    __syncthreads();
+    int t = 0;
+    for (int w = 0; w < nwarps; w++) t += s_red[w];
+    __syncthreads();
+    return t;
+}
+
+template <int E>
+__device__ __forceinline__ uint64_t block_kth_smallest(const uint64_t (&v)[E], int k, int* s_red, int tid, int nwarps) {
+    int nv = 0;
+    uint32_t a_and = 0xffffffffu, a_or = 0u;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        if (v[e] != kInvalid) { nv++; a_and &= (uint32_t)(v[e] >> 32); a_or |= (uint32_t)(v[e] >> 32); }
+    }
+    const int n_valid = block_sum_i(nv, s_red, tid, nwarps);
+    if (n_valid < k) return kInvalid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a_and &= __shfl_xor_sync(0xffffffffu, a_and, o);
+        a_or |= __shfl_xor_sync(0xffffffffu, a_or, o);
+    }
+    if ((tid & 31) == 0) { s_red[tid >> 5] = (int)a_and; s_red[32 + (tid >> 5)] = (int)a_or; }
+    __syncthreads();
+    a_and = 0xffffffffu; a_or = 0u;
+    for (int w = 0; w < nwarps; w++) { a_and &= (uint32_t)s_red[w]; a_or |= (uint32_t)s_red[32 + w]; }
+    __syncthreads();
+    const uint32_t diff = a_and ^ a_or;
+    const int top = diff ? (31 - __clz(diff)) : -1;
+    uint32_t T = (top < 0) ? a_and : (top >= 31 ? 0u : (a_and & ~((2u << top) - 1u)));
+    for (int bit = top; bit >= 0; bit--) {
+        const uint32_t test = T | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) c += (v[e] != kInvalid) && ((uint32_t)(v[e] >> 32) < test);
+        if (block_sum_i(c, s_red, tid, nwarps) < k) T = test;
+    }
+    int c_less = 0, c_tie = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        if (v[e] != kInvalid) {
+            c_less += ((uint32_t)(v[e] >> 32) < T);
+            c_tie += ((uint32_t)(v[e] >> 32) == T);
+        }
+    }
+    const int n_less = block_sum_i(c_less, s_red, tid, nwarps);
+    const int n_tie = block_sum_i(c_tie, s_red, tid, nwarps);
+    const int need = k - n_less;  // 1..n_tie of the tied values, lowest row ids first
+    if (need >= n_tie) return ((uint64_t)T << 32) | 0xffffffffu;
+    uint32_t L = 0;
+    for (int bit = 31; bit >= 0; bit--) {
+        const uint32_t test = L | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            c += (v[e] != kInvalid) && ((uint32_t)(v[e] >> 32) == T) && ((uint32_t)v[e] < test);
+        if (block_sum_i(c, s_red, tid, nwarps) < need) L = test;
+    }
+    return ((uint64_t)T << 32) | L;
+}
+
 __host__ __device__ __forceinline__ int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;

@@ -148,6 +148,8 @@ struct TcArgs {
     int tile_begin, tile_end;  // row tiles [begin, end) scanned by this launch
     int part_offset;           // first partial[] slot written by this launch
     const float* tau_init;     // per-query starting threshold (bootstrap), or null
+    float* keys_out;           // bootstrap sample mode: write raw keys [nq][keys_ld] instead of selecting
+    int keys_ld;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -169,7 +171,18 @@ __device__ __forceinline__ float select_compact(const uint64_t* buf, uint64_t* d
         v[r] = t.x;
         v[r + 1] = (i + 1 < c) ? t.y : kInvalid;
     }
-    uint32_t T = 0xffffffffu;  // keep everything valid when c < kc
+    if (c <= kc) {  // nothing to drop: plain copy (the usual case once the bootstrap threshold is tight)
+        __syncwarp();
+        if (dst != buf) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (lane * R + r < c) __stcg(dst + lane * R + r, v[r]);
+            }
+        }
+        *kept_out = c;
+        return (c == kc) ? INFINITY : INFINITY;
+    }
+    uint32_t T = 0xffffffffu;
     if (c >= kc) {
         // bits shared by every valid key need no search: start below the common prefix
         uint32_t all_and = 0xffffffffu, all_or = 0;
@@ -370,6 +383,28 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     }
                 }
                 tmem_wait_ld();
+                if (a.keys_out != nullptr) {
+                    // bootstrap sample: dump the keys of this 32-column chunk (row-major per query)
+                    if (q < a.nq) {
+                        float4* dst = reinterpret_cast<float4*>(a.keys_out + (size_t)q * a.keys_ld +
+                                                                (row0 - (uint32_t)a.tile_begin * TC_N) + c0);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float k4[4];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                float dot;
+                                if constexpr (KIND == KIND_I8) dot = (float)(int32_t)v[j + e];
+                                else dot = __uint_as_float(v[j + e]);
+                                if constexpr (METRIC == METRIC_L2) k4[e] = fmaf(-2.f, dot, ax[j + e]);
+                                else if constexpr (METRIC == METRIC_COSINE) k4[e] = -dot * ax[j + e];
+                                else k4[e] = -dot;
+                            }
+                            dst[j >> 2] = make_float4(k4[0], k4[1], k4[2], k4[3]);
+                        }
+                    }
+                    continue;
+                }
                 // fast filter: ~3 instructions per key (key, compare, mask), no side effects
                 uint32_t hits = 0;
 #pragma unroll
@@ -418,7 +453,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             if (lane == 0) mbar_arrive(tempty_bar(as));
         }
         // final: reduce every list to its best kc (unordered; the merge kernel sorts) and emit it
-        for (int src = 0; src < 32; src++) {
+        for (int src = 0; src < 32 && a.keys_out == nullptr; src++) {
             const int c = __shfl_sync(0xffffffffu, cnt, src);
             const int qq = __shfl_sync(0xffffffffu, q, src);
             const uint64_t* buf = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
@@ -442,6 +477,57 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 // Bootstrap threshold: the kc-th best key over the sample rows bounds the global kc-th best from
 // above, so the main scan can start every list at it.  nextafter(+inf) turns the strict '<' of the
 // filter into '<=': a row tying that key with a smaller row id must still get through.
+// Bootstrap selection: per query, the kc smallest (key,row) of a dense [nq][S] sample key matrix
+// (rows [0,S) of the index), honouring n_rows and the tombstone / allow bitmaps.  Block-wide
+// MSB-first radix select over the packed 64-bit value; entries live in registers.
+constexpr int SSEL_E = 32;
+__global__ void __launch_bounds__(1024)
+sample_select_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_rows, const uint32_t* __restrict__ tomb,
+                     uint32_t tomb_bits, const uint32_t* __restrict__ allow, int nq, int kc,
+                     uint64_t* __restrict__ out, uint64_t* __restrict__ kth) {
+    __shared__ int s_red[64];
+    __shared__ int s_out;
+    const int q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    uint64_t v[SSEL_E];
+#pragma unroll
+    for (int e = 0; e < SSEL_E; e++) {
+        const uint32_t row = (uint32_t)(e * nt + tid);
+        uint64_t x = kInvalid;
+        if ((int)row < S && row < n_rows) {
+            bool ok = true;
+            if (tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) ok = false;
+            if (ok && allow != nullptr && !bit_set(allow, row)) ok = false;
+            const float k = __ldg(keys + (size_t)q * ld + row);
+            if (ok && k < INFINITY) x = pack_key(k, row);
+        }
+        v[e] = x;
+    }
+    if (tid == 0) s_out = 0;
+    const uint64_t T = block_kth_smallest<SSEL_E>(v, kc, s_red, tid, nt / 32);
+#pragma unroll
+    for (int e = 0; e < SSEL_E; e++) {
+        if (v[e] != kInvalid && v[e] <= T) {
+            const int pos = atomicAdd(&s_out, 1);
+            if (pos < kc) out[(size_t)q * kc + pos] = v[e];
+        }
+    }
+    __syncthreads();
+    for (int t = s_out + tid; t < kc; t += nt) out[(size_t)q * kc + t] = kInvalid;
+    if (tid == 0) kth[q] = T;
+}
+
+cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_rows, const uint32_t* tomb,
+                                 uint32_t tomb_bits, const uint32_t* allow, int nq, int kc, uint64_t* out,
+                                 uint64_t* kth, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    if (S > SSEL_E * 1024) return cudaErrorInvalidValue;
+    int nt = ((S + SSEL_E - 1) / SSEL_E + 31) / 32 * 32;
+    if (nt < 64) nt = 64;
+    sample_select_kernel<<<nq, nt, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, kth);
+    count_launch();
+    return cudaGetLastError();
+}
+
 __global__ void tau_from_kth_kernel(const uint64_t* __restrict__ kth, int nq, int stride, int off,
                                     float* __restrict__ tau) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -530,8 +616,9 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     a.tile_end = s.tile_end < 0 ? a.n_row_tiles : s.tile_end;
     a.part_offset = s.part_offset;
     a.tau_init = s.tau_init;
+    a.keys_out = s.keys_out; a.keys_ld = s.keys_ld;
     dense_scan_tc_plan(s.nq, a.tile_end - a.tile_begin, sm_count, s.kc, &groups, &cand_bytes);
-    if (2 * groups != s.parts) return cudaErrorInvalidValue;  // partial[] was sized for s.parts lists
+    if (s.keys_out == nullptr && 2 * groups != s.parts) return cudaErrorInvalidValue;  // partial[] sized for s.parts lists
     a.groups = groups;
     a.tomb = s.tomb; a.tomb_bits = s.tomb_bits; a.allow = s.allow;
     a.kc = s.kc; a.cap = next_pow2(s.kc + TC_N);

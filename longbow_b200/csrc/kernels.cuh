@@ -27,6 +27,8 @@ struct ScanArgs {
     // tensor-core scan only: sub-range of 256-row tiles, first partial[] slot, bootstrap thresholds
     int tile_begin = 0, tile_end = -1, part_offset = 0;
     const float* tau_init = nullptr;
+    float* keys_out = nullptr;  // bootstrap sample mode: dump raw keys [nq][keys_ld]
+    int keys_ld = 0;
 };
 
 struct RescoreArgs {
@@ -71,6 +73,9 @@ cudaError_t launch_merge_topk(const float* in_d, const int64_t* in_l, int parts,
 // ---- tensor-core scan (dense_tc.cu)
 bool dense_tc_eligible(int dtype, int dim, const void* db, const void* queries, int kc);
 void dense_scan_tc_plan(int nq, int n_row_tiles, int sm_count, int kc, int* groups_out, size_t* cand_bytes);
+cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_rows, const uint32_t* tomb,
+                                 uint32_t tomb_bits, const uint32_t* allow, int nq, int kc, uint64_t* out,
+                                 uint64_t* kth, cudaStream_t st);
 cudaError_t launch_tau_from_kth(const uint64_t* kth, int nq, int stride, int off, float* tau, cudaStream_t st);
 cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand, cudaStream_t st);
 

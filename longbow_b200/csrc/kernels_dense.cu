@@ -354,71 +354,19 @@ constexpr int MSEL_T = 256;
 __global__ void __launch_bounds__(MSEL_T)
 merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int kc, uint64_t* __restrict__ merged,
                     uint64_t* __restrict__ kth) {
-    __shared__ int hist[256];
-    __shared__ int s_bin, s_before, s_out;
+    __shared__ int s_red[64];
+    __shared__ int s_out;
     const int q = blockIdx.x, tid = threadIdx.x;
     const int total = parts * kc;
     uint64_t v[MSEL_E];
-    int nvalid = 0;
 #pragma unroll
     for (int e = 0; e < MSEL_E; e++) {
         const int i = e * MSEL_T + tid;
-        uint64_t x = kInvalid;
-        if (i < total) x = partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)];
-        v[e] = x;
-        nvalid += (x != kInvalid);
+        v[e] = (i < total) ? partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)] : kInvalid;
     }
     if (tid == 0) s_out = 0;
-    // total number of valid entries
-    hist[tid] = 0;
-    __syncthreads();
-    atomicAdd(&hist[0], nvalid);
-    __syncthreads();
-    const int n_valid_total = hist[0];
-    __syncthreads();
-    uint64_t T = kInvalid;  // keep everything valid when there are fewer than kc
-    if (n_valid_total >= kc) {
-        uint64_t prefix = 0;
-        int remaining = kc;  // rank (1-based) of the wanted element inside the current prefix class
-        for (int pass = 0; pass < 8; pass++) {
-            const int shift = 56 - 8 * pass;
-            hist[tid] = 0;
-            __syncthreads();
-#pragma unroll
-            for (int e = 0; e < MSEL_E; e++) {
-                const uint64_t x = v[e];
-                const bool in_class = (pass == 0) || ((x >> (shift + 8)) == (prefix >> (shift + 8)));
-                if (x != kInvalid && in_class) atomicAdd(&hist[(int)((x >> shift) & 255)], 1);
-            }
-            __syncthreads();
-            if (tid < 32) {  // warp 0: 8 bins per lane, find the bin holding rank `remaining`
-                int loc[8], sum = 0;
-#pragma unroll
-                for (int b = 0; b < 8; b++) { loc[b] = hist[tid * 8 + b]; sum += loc[b]; }
-                int inc = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int up = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (tid >= o) inc += up;
-                }
-                const int exc = inc - sum;
-                if (remaining > exc && remaining <= inc) {
-                    int acc = exc;
-#pragma unroll
-                    for (int b = 0; b < 8; b++) {
-                        if (remaining > acc && remaining <= acc + loc[b]) { s_bin = tid * 8 + b; s_before = acc; }
-                        acc += loc[b];
-                    }
-                }
-            }
-            __syncthreads();
-            prefix |= (uint64_t)s_bin << shift;
-            remaining -= s_before;
-            __syncthreads();
-        }
-        T = prefix;  // the kc-th smallest packed value
-    }
-    // unordered compaction of everything <= T (exactly kc entries when n_valid_total >= kc)
+    const uint64_t T = block_kth_smallest<MSEL_E>(v, kc, s_red, tid, MSEL_T / 32);  // kInvalid: keep all valid
+    // unordered compaction of everything <= T (exactly kc entries when at least kc are valid)
 #pragma unroll
     for (int e = 0; e < MSEL_E; e++) {
         if (v[e] != kInvalid && v[e] <= T) {
