@@ -90,6 +90,7 @@ struct Scratch {
 // ---- options (lb_set_option)
 static std::atomic<int> g_opt_dense_scan{0};
 static std::atomic<int> g_opt_tc_debug{0};
+static std::atomic<int> g_opt_tc_boot_tiles{0};  // 0 = auto
 static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off (A/B timing)    // timing probes of the tensor-core scan (results invalid when != 0)  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
 
 // ---- dominant-kernel timing (lb_prof_*)
@@ -208,6 +209,10 @@ int lb_set_option(const char* name, int value) {
     }
     if (strcmp(name, "tc_boot") == 0) {
         g_opt_tc_boot.store(value ? 1 : 0);
+        return LB_OK;
+    }
+    if (strcmp(name, "tc_boot_tiles") == 0) {
+        g_opt_tc_boot_tiles.store(value < 0 ? 0 : value);
         return LB_OK;
     }
     if (strcmp(name, "tc_debug") == 0) {
@@ -438,8 +443,11 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
             int gm;
             dense_scan_tc_plan(cq, n_tiles, idx->sm_count, kc, &gm, &cand_bytes);
             if (g_opt_tc_boot.load(std::memory_order_relaxed)) {
-                int bt = (n_tiles + 2 * gm - 1) / (2 * gm);
-                if (bt < 8) bt = 8;
+                int bt = g_opt_tc_boot_tiles.load(std::memory_order_relaxed);
+                if (bt <= 0) {
+                    bt = (n_tiles + 2 * gm - 1) / (2 * gm);
+                    if (bt < 8) bt = 8;
+                }
                 if (bt > 128) bt = 128;
                 if (bt * 4 <= n_tiles) boot_tiles = bt;
             }
@@ -452,17 +460,21 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
             a.partial = partial;
             if (boot_tiles) {
                 const int S = boot_tiles * 256;
-                float *keys, *tau;
-                uint64_t* kth;
+                float *keys, *tau, *edges;
+                uint32_t* edge_cnt;
+                int* sel_done;
+                CK(scr.get((void**)&sel_done, (size_t)cq * 4));
                 CK(scr.get((void**)&keys, (size_t)cq * S * 4));
                 CK(scr.get((void**)&tau, (size_t)cq * 4));
-                CK(scr.get((void**)&kth, (size_t)cq * 8));
+                CK(scr.get((void**)&edges, (size_t)cq * LB_NEDGE * 4));
+                CK(scr.get((void**)&edge_cnt, (size_t)cq * LB_NEDGE * 4));
                 ScanArgs b = a;
                 b.parts = 0; b.partial = nullptr; b.tile_begin = 0; b.tile_end = boot_tiles; b.part_offset = 0;
                 b.keys_out = keys; b.keys_ld = S;
                 CK(launch_dense_scan_tc(b, idx->sm_count, cand, st));
-                CK(launch_sample_select(keys, S, S, a.n_rows, a.tomb, a.tomb_bits, a.allow, cq, kc, partial, kth, st));
-                CK(launch_tau_from_kth(kth, cq, 1, 0, tau, st));
+                CK(launch_sample_select(keys, S, S, a.n_rows, a.tomb, a.tomb_bits, a.allow, cq, kc, partial, tau, edges,
+                                        edge_cnt, sel_done, st));
+                a.edges = edges; a.edge_cnt = edge_cnt;
                 a.tau_init = tau;
             }
             a.parts = 2 * gm; a.tile_begin = boot_tiles; a.tile_end = n_tiles; a.part_offset = extra;

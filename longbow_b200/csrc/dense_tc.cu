@@ -24,6 +24,7 @@
 namespace lb {
 
 enum { KIND_F16 = 0, KIND_I8 = 1, KIND_TF32 = 2 };
+static_assert(LB_NEDGE == 16, "the epilogue unpacks four uint4 of ladder counters");
 
 template <int KIND> struct TcTraits;
 template <> struct TcTraits<KIND_F16> {
@@ -118,7 +119,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    return r;
+}
+__device__ __forceinline__ void tmem_wait_ld4(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d)::"memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but naming the 32 destination registers of the load it completes as read-write operands:
+// no use of v[] can be scheduled above the wait even when a second tcgen05.ld is already in flight.
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t* v) {
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+          "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+          "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+          "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+        :: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
@@ -150,6 +173,8 @@ struct TcArgs {
     const float* tau_init;     // per-query starting threshold (bootstrap), or null
     float* keys_out;           // bootstrap sample mode: write raw keys [nq][keys_ld] instead of selecting
     int keys_ld;
+    const float* edges;        // [nq][LB_NEDGE] shared threshold ladder (or null)
+    uint32_t* edge_cnt;        // [nq][LB_NEDGE] live rows seen per ladder bucket, all CTAs of the query
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -268,8 +293,8 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* base_ptr = smem_raw + (base - raw);
-    const uint32_t slot_off = TC_STAGES * TC_STAGE_BYTES;               // [8 warps][32 x 32] words
-    const uint32_t bar_off = slot_off + 8u * 32u * 32u * 4u;
+    const uint32_t aux_off = TC_STAGES * TC_STAGE_BYTES;                // [2 groups][2 buffers][TC_N / 2] floats
+    const uint32_t bar_off = aux_off + 2u * 2u * (TC_N / 2) * 4u;
     const uint32_t bar_base = base + bar_off;
     // barriers: full[4], empty[4], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -283,7 +308,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -341,71 +366,91 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
     } else if (warp >= 4) {
         // ================================ epilogue: fused top-k =======================
-        // Two groups of four warps; group e owns accumulator stage e (tiles e, e+2, e+4 ... of this CTA)
-        // and its own candidate lists, so both SMSP issue slots per quarter stay busy.
+        // Two groups of four warps drain EVERY accumulator tile together: group e takes columns
+        // [128e, 128e+128) of the tile (rows row0+128e ...) and keeps its own candidate lists.  A stage is
+        // free again after half a tile's worth of epilogue work, so the drain hides behind the next
+        // tile's MMAs even when the survivor path is busy (per-tile time = max(MMA, (MMA + drain)/2)).
         const int grp = (warp - 4) >> 2;
         const int ew = (warp - 4) & 3;   // TMEM lane quarter this warp may read (== warp % 4)
         const int tq = ew * 32 + lane;   // query (TMEM lane) of this thread
         const int q = qb * TC_M + tq;
         constexpr int cap = CAP, R = CAP / 32;
+        constexpr int HALF = TC_N / 2;
         const int kc = a.kc;
         const int part = a.part_offset + g * 2 + grp;
         uint64_t* mybuf = a.cand + (((size_t)blockIdx.x * 2 + grp) * TC_M + tq) * cap;
-        uint32_t* slot = reinterpret_cast<uint32_t*>(base_ptr + slot_off) + (size_t)(warp - 4) * 1024;
+        float* aux_s = reinterpret_cast<float*>(base_ptr + aux_off) + grp * 2 * HALF;  // two buffers per group
         int cnt = 0;
         float tau = -INFINITY;  // padding queries never select
         if (q < a.nq) tau = (a.tau_init != nullptr) ? __ldg(a.tau_init + q) : INFINITY;
         if (a.debug & 8) tau = -0.14f;  // probe: pretend a tight threshold is already known
+        // Shared progressive threshold.  ed[] is this query's ladder of sample keys (ascending); gcnt[b]
+        // counts the live rows every CTA of this query has met so far with a key in ladder bucket b
+        // (seeded with the sample's own rows).  Whenever the counts up to some edge reach kc, at least
+        // kc live rows are at or below that edge, so it is a valid threshold for everybody: the filter
+        // tightens as 1/(fraction of the index scanned) instead of staying at the sample's kc-th key.
+        const bool shared_tau = (a.edges != nullptr) && (q < a.nq) && !(a.debug & 16);
+        float ed[LB_NEDGE];
+        uint32_t* gcnt = nullptr;
+        if (shared_tau) {
+            gcnt = a.edge_cnt + (size_t)q * LB_NEDGE;
+            const float4* ep = reinterpret_cast<const float4*>(a.edges + (size_t)q * LB_NEDGE);
+#pragma unroll
+            for (int i = 0; i < LB_NEDGE / 4; i++) {
+                const float4 t = __ldg(ep + i);
+                ed[4 * i] = t.x; ed[4 * i + 1] = t.y; ed[4 * i + 2] = t.z; ed[4 * i + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < LB_NEDGE; i++) ed[i] = INFINITY;
+        }
         const uint32_t n_rows = a.n_rows, tomb_bits = a.tomb_bits;
         const uint32_t* __restrict__ tomb = a.tomb;
         const uint32_t* __restrict__ allow = a.allow;
-        const int as = grp;
+        const bool filt = (tomb != nullptr) || (allow != nullptr);
+        const bool dump = a.keys_out != nullptr;
+        int as = 0;
         uint32_t aphase = 0;
-        int it = 0;
-        for (int rt = a.tile_begin + g; rt < a.tile_end; rt += a.groups, it++) {
-            if ((it & 1) != grp) continue;
-            const uint32_t row0 = (uint32_t)rt * TC_N;
+        int abuf = 0;
+        int rt = a.tile_begin + g;
+        // Row auxiliaries (|x|^2 or 1/|x|) of a tile are staged in shared memory one tile ahead: the
+        // global load for the NEXT tile is issued before this tile's accumulator is awaited, so its
+        // L2 latency never sits between a TMEM load and the filter.
+        float axn = 0.f;
+        if constexpr (METRIC != METRIC_DOT) {
+            if (rt < a.tile_end) axn = __ldg(a.aux + (size_t)rt * TC_N + grp * HALF + tq);
+        }
+
+        for (; rt < a.tile_end; rt += a.groups, abuf ^= 1) {
+            const uint32_t row0 = (uint32_t)rt * TC_N + grp * HALF;  // first row of this group's half tile
+            const float* axs = aux_s + abuf * HALF;
+            if constexpr (METRIC != METRIC_DOT) {
+                aux_s[abuf * HALF + tq] = axn;
+                named_bar_sync(1 + grp, 128);  // the group's 4 warps; the other buffer may still be read
+                if (rt + a.groups < a.tile_end)
+                    axn = __ldg(a.aux + (size_t)(rt + a.groups) * TC_N + grp * HALF + tq);
+            }
+            // counters of the shared threshold: loaded (L2, never L1) before the wait, used after the tile
+            uint4 gc[LB_NEDGE / 4];
+            if (shared_tau) {
+#pragma unroll
+                for (int i = 0; i < LB_NEDGE / 4; i++) gc[i] = __ldcg(reinterpret_cast<const uint4*>(gcnt) + i);
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * TC_N + grp * HALF;
             mbar_wait(tfull_bar(as), aphase);
-            aphase ^= 1u;
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * TC_N;
-#pragma unroll 1
-            for (int c0 = 0; c0 < ((a.debug & 1) ? 0 : TC_N); c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
+
+            // one 32-column chunk of this thread's query: keys, filter, rare appends
+            auto process = [&](uint32_t (&v)[32], const int c0) {
                 float ax[32];
                 if constexpr (METRIC != METRIC_DOT) {
-                    const float4* ap = reinterpret_cast<const float4*>(a.aux + row0 + c0);
+                    const float4* ap = reinterpret_cast<const float4*>(axs + c0);  // warp-uniform: broadcast
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        float4 t = __ldg(ap + j);
+                        const float4 t = ap[j];
                         ax[4 * j] = t.x; ax[4 * j + 1] = t.y; ax[4 * j + 2] = t.z; ax[4 * j + 3] = t.w;
                     }
                 }
-                tmem_wait_ld();
-                if (a.keys_out != nullptr) {
-                    // bootstrap sample: dump the keys of this 32-column chunk (row-major per query)
-                    if (q < a.nq) {
-                        float4* dst = reinterpret_cast<float4*>(a.keys_out + (size_t)q * a.keys_ld +
-                                                                (row0 - (uint32_t)a.tile_begin * TC_N) + c0);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float k4[4];
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                float dot;
-                                if constexpr (KIND == KIND_I8) dot = (float)(int32_t)v[j + e];
-                                else dot = __uint_as_float(v[j + e]);
-                                if constexpr (METRIC == METRIC_L2) k4[e] = fmaf(-2.f, dot, ax[j + e]);
-                                else if constexpr (METRIC == METRIC_COSINE) k4[e] = -dot * ax[j + e];
-                                else k4[e] = -dot;
-                            }
-                            dst[j >> 2] = make_float4(k4[0], k4[1], k4[2], k4[3]);
-                        }
-                    }
-                    continue;
-                }
-                // fast filter: ~3 instructions per key (key, compare, mask), no side effects
                 uint32_t hits = 0;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
@@ -419,41 +464,116 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     v[j] = __float_as_uint(key);
                     if (key < tau) hits |= 1u << j;
                 }
-                if (hits) {
-                    // slow path (rare after warm-up): park the keys in shared memory, walk the hits
+                if (dump) {
+                    // bootstrap sample: write the keys of this chunk (row-major per query)
+                    if (q < a.nq) {
+                        float4* dst = reinterpret_cast<float4*>(a.keys_out + (size_t)q * a.keys_ld +
+                                                                (row0 - (uint32_t)a.tile_begin * TC_N) + c0);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) slot[j * 32 + lane] = v[j];
-                    do {
-                        const int j = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        const uint32_t row = row0 + c0 + j;
-                        bool ok = row < n_rows;
-                        if (ok && tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) ok = false;
-                        if (ok && allow != nullptr && !bit_set(allow, row)) ok = false;
-                        if (ok) mybuf[cnt++] = pack_key(__uint_as_float(slot[j * 32 + lane]), row);
-                    } while (hits);
+                        for (int j = 0; j < 32; j += 4)
+                            dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    }
+                    return;
                 }
-                // warp-cooperative compaction of every list that could overflow in its next chunk
-                unsigned need = __ballot_sync(0xffffffffu, cnt > cap - 32);
-                while (need) {
-                    const int src = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int c = __shfl_sync(0xffffffffu, cnt, src);
-                    uint64_t* buf = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
-                    __syncwarp();  // order the owner's appends before the other lanes' reads
-                    int kept;
-                    const float nt = select_compact<R>(buf, buf, c, kc, lane, &kept);
-                    __syncwarp();
-                    if (lane == src) { cnt = kept; tau = nt; }
+                // Survivors are sparse (a fraction of a percent once the threshold is tight) but a warp
+                // filters 1024 keys per chunk, so most chunks have a few.  Walk the columns that hold a
+                // survivor of ANY lane, four per trip (warp-uniform loop, compact code): re-read those
+                // accumulator columns from TMEM with the loads in flight together, and let the lanes that
+                // own a survivor append it.  Columns ascend, so every list stays in increasing row order.
+                uint32_t cols = __reduce_or_sync(0xffffffffu, hits);
+                while (cols) {
+                    int jj[4];
+                    uint32_t dv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        jj[u] = cols ? (__ffs(cols) - 1) : -1;
+                        cols &= cols - 1;  // 0 stays 0
+                        dv[u] = tmem_ld1(taddr + c0 + (jj[u] < 0 ? 0 : jj[u]));
+                    }
+                    tmem_wait_ld4(dv[0], dv[1], dv[2], dv[3]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (jj[u] >= 0 && (hits & (1u << jj[u]))) {
+                            float dot;
+                            if constexpr (KIND == KIND_I8) dot = (float)(int32_t)dv[u];
+                            else dot = __uint_as_float(dv[u]);
+                            float key;
+                            if constexpr (METRIC == METRIC_L2) key = fmaf(-2.f, dot, axs[c0 + jj[u]]);
+                            else if constexpr (METRIC == METRIC_COSINE) key = -dot * axs[c0 + jj[u]];
+                            else key = -dot;
+                            const uint32_t row = row0 + c0 + jj[u];
+                            bool ok = row < n_rows;
+                            if (filt && ok) {
+                                if (tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) ok = false;
+                                if (ok && allow != nullptr && !bit_set(allow, row)) ok = false;
+                            }
+                            if (ok) {
+                                mybuf[cnt++] = pack_key(key, row);
+                                if (shared_tau) {
+                                    int b = 0;
+#pragma unroll
+                                    for (int i = 0; i < LB_NEDGE; i++) b += (ed[i] <= key) ? 1 : 0;
+                                    if (b < LB_NEDGE) atomicAdd(gcnt + b, 1u);
+                                }
+                            }
+                        }
+                    }
+                }
+            };
+
+            if (!(a.debug & 1)) {
+                // TMEM -> registers, double buffered: the load of chunk c+1 is in flight while chunk c is filtered
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+#pragma unroll 1
+                for (int c0 = 0; c0 < HALF; c0 += 64) {
+                    tmem_wait_ld32(va);
+                    tmem_ld32(taddr + c0 + 32, vb);
+                    process(va, c0);
+                    tmem_wait_ld32(vb);
+                    if (c0 + 64 < HALF) tmem_ld32(taddr + c0 + 64, va);
+                    process(vb, c0 + 32);
                 }
             }
-            // release the accumulator stage
+            // release the accumulator stage (the survivor path re-reads TMEM, so only now)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+
+            // refresh the shared threshold from the counters fetched at the top of this tile
+            if (shared_tau) {
+                const uint32_t cv[LB_NEDGE] = {gc[0].x, gc[0].y, gc[0].z, gc[0].w, gc[1].x, gc[1].y, gc[1].z, gc[1].w,
+                                               gc[2].x, gc[2].y, gc[2].z, gc[2].w, gc[3].x, gc[3].y, gc[3].z, gc[3].w};
+                uint32_t cum = 0;
+                float tg = INFINITY;
+                bool found = false;
+#pragma unroll
+                for (int i = 0; i < LB_NEDGE; i++) {  // ascending: the lowest edge whose prefix holds kc rows
+                    cum += cv[i];
+                    const bool hit = cum >= (uint32_t)kc;
+                    tg = (hit && !found) ? ed[i] : tg;
+                    found = found || hit;
+                }
+                tau = fminf(tau, tg);
+            }
+            // warp-cooperative compaction of every list that could overflow during its next half tile
+            unsigned need = __ballot_sync(0xffffffffu, cnt > cap - HALF);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const int c = __shfl_sync(0xffffffffu, cnt, src);
+                uint64_t* buf = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
+                __syncwarp();  // order the owner's appends before the other lanes' reads
+                int kept;
+                const float nt = select_compact<R>(buf, buf, c, kc, lane, &kept);
+                __syncwarp();
+                if (lane == src) { cnt = kept; tau = nt; }
+            }
         }
         // final: reduce every list to its best kc (unordered; the merge kernel sorts) and emit it
-        for (int src = 0; src < 32 && a.keys_out == nullptr; src++) {
+        for (int src = 0; src < 32 && !dump; src++) {
             const int c = __shfl_sync(0xffffffffu, cnt, src);
             const int qq = __shfl_sync(0xffffffffu, q, src);
             const uint64_t* buf = reinterpret_cast<const uint64_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
@@ -481,26 +601,90 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 // (rows [0,S) of the index), honouring n_rows and the tombstone / allow bitmaps.  Block-wide
 // MSB-first radix select over the packed 64-bit value; entries live in registers.
 constexpr int SSEL_E = 32;
+constexpr int SSEL_SUB = 1024;   // sub-sample whose order statistic supplies the pivot
+constexpr int SSEL_COLL = 2048;  // capacity of the collected (<= pivot) set
+
+__device__ __forceinline__ uint32_t sample_key(const float* __restrict__ keys, int ld, int S, uint32_t n_rows,
+                                               const uint32_t* __restrict__ tomb, uint32_t tomb_bits,
+                                               const uint32_t* __restrict__ allow, int q, uint32_t row) {
+    if ((int)row >= S || row >= n_rows) return 0xffffffffu;
+    if (tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) return 0xffffffffu;
+    if (allow != nullptr && !bit_set(allow, row)) return 0xffffffffu;
+    const float k = __ldg(keys + (size_t)q * ld + row);
+    return (k < INFINITY) ? float_to_ordered(k) : 0xffffffffu;  // NaN / +inf never selected
+}
+
+// Fast path.  Thread t holds the ordered keys of rows t, t+nt, t+2nt ... (row ids are implicit, so 32
+// registers hold 32 entries).  Pivot = the r-th smallest of a sub-sample (the threads' first entries),
+// r chosen so that about 4*kc of the S keys fall at or below it; everything <= pivot is collected into
+// shared memory and sorted.  If at least kc were collected, their kc smallest (key,row) are exactly the
+// kc smallest of the whole sample.  Otherwise done[q] stays 0 and the exact kernel below handles q.
 __global__ void __launch_bounds__(1024)
 sample_select_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_rows, const uint32_t* __restrict__ tomb,
                      uint32_t tomb_bits, const uint32_t* __restrict__ allow, int nq, int kc,
-                     uint64_t* __restrict__ out, uint64_t* __restrict__ kth) {
+                     uint64_t* __restrict__ out, float* __restrict__ tau, float* __restrict__ edges,
+                     uint32_t* __restrict__ edge_cnt, const EdgeRanks ranks, int* __restrict__ done) {
+    __shared__ int s_out;
+    __shared__ uint32_t s_sub[SSEL_SUB];
+    __shared__ uint64_t s_coll[SSEL_COLL];
+    const int q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    uint32_t v[SSEL_E];
+#pragma unroll
+    for (int e = 0; e < SSEL_E; e++)
+        v[e] = sample_key(keys, ld, S, n_rows, tomb, tomb_bits, allow, q, (uint32_t)(e * nt + tid));
+    if (tid == 0) { s_out = 0; done[q] = 0; }
+    for (int t = tid; t < SSEL_SUB; t += nt) s_sub[t] = 0xffffffffu;
+    __syncthreads();
+    s_sub[tid] = v[0];
+    __syncthreads();
+    block_bitonic_sort_t<uint32_t>(s_sub, SSEL_SUB);
+    int r = (int)(((int64_t)4 * kc * nt + S - 1) / S);
+    if (r < 12) r = 12;
+    if (r > nt) return;
+    const uint32_t pivot = s_sub[r - 1];
+    if (pivot == 0xffffffffu) return;
+#pragma unroll
+    for (int e = 0; e < SSEL_E; e++) {
+        if (v[e] <= pivot) {
+            const int pos = atomicAdd(&s_out, 1);
+            if (pos < SSEL_COLL) s_coll[pos] = ((uint64_t)v[e] << 32) | (uint32_t)(e * nt + tid);
+        }
+    }
+    __syncthreads();
+    const int c = s_out;
+    if (c < kc || c > SSEL_COLL) return;
+    const int n2 = next_pow2(c);
+    for (int t = c + tid; t < n2; t += nt) s_coll[t] = kInvalid;
+    __syncthreads();
+    block_bitonic_sort(s_coll, n2);
+    for (int t = tid; t < kc; t += nt) out[(size_t)q * kc + t] = s_coll[t];
+    // threshold ladder: the sample keys at the ranks in `ranks` (ascending), bumped one ulp so that the
+    // scan's strict '<' admits ties, and how many sample rows fall into each ladder bucket
+    if (tid < LB_NEDGE) {
+        const int r1 = ranks.r[tid], r0 = tid ? ranks.r[tid - 1] : 0;
+        edges[(size_t)q * LB_NEDGE + tid] = nextafterf(key_of(s_coll[r1 - 1]), INFINITY);
+        edge_cnt[(size_t)q * LB_NEDGE + tid] = (uint32_t)(r1 - r0);
+    }
+    if (tid == 0) { tau[q] = nextafterf(key_of(s_coll[kc - 1]), INFINITY); done[q] = 1; }
+}
+
+// Exact path for the queries the fast path left (fewer than kc sample rows at or below the pivot, too
+// many, or fewer than kc valid rows at all): block-wide MSB-first search over the packed 64-bit value.
+__global__ void __launch_bounds__(1024)
+sample_select_exact_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_rows,
+                           const uint32_t* __restrict__ tomb, uint32_t tomb_bits, const uint32_t* __restrict__ allow,
+                           int nq, int kc, uint64_t* __restrict__ out, float* __restrict__ tau,
+                           float* __restrict__ edges, uint32_t* __restrict__ edge_cnt, const int* __restrict__ done) {
     __shared__ int s_red[64];
     __shared__ int s_out;
     const int q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    if (done[q]) return;
     uint64_t v[SSEL_E];
 #pragma unroll
     for (int e = 0; e < SSEL_E; e++) {
         const uint32_t row = (uint32_t)(e * nt + tid);
-        uint64_t x = kInvalid;
-        if ((int)row < S && row < n_rows) {
-            bool ok = true;
-            if (tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) ok = false;
-            if (ok && allow != nullptr && !bit_set(allow, row)) ok = false;
-            const float k = __ldg(keys + (size_t)q * ld + row);
-            if (ok && k < INFINITY) x = pack_key(k, row);
-        }
-        v[e] = x;
+        const uint32_t k = sample_key(keys, ld, S, n_rows, tomb, tomb_bits, allow, q, row);
+        v[e] = (k == 0xffffffffu) ? kInvalid : (((uint64_t)k << 32) | row);
     }
     if (tid == 0) s_out = 0;
     const uint64_t T = block_kth_smallest<SSEL_E>(v, kc, s_red, tid, nt / 32);
@@ -513,32 +697,45 @@ sample_select_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_r
     }
     __syncthreads();
     for (int t = s_out + tid; t < kc; t += nt) out[(size_t)q * kc + t] = kInvalid;
-    if (tid == 0) kth[q] = T;
+    // degenerate ladder: every edge = the sample's kc-th key (or +inf when the sample holds fewer than kc
+    // live rows); bucket 0 starts at the number of sample rows at or below it
+    const float t0 = (T == kInvalid) ? INFINITY : nextafterf(key_of(T), INFINITY);
+    const int n_sel = s_out < kc ? s_out : kc;
+    if (tid < LB_NEDGE) {
+        edges[(size_t)q * LB_NEDGE + tid] = t0;
+        edge_cnt[(size_t)q * LB_NEDGE + tid] = (tid == 0) ? (uint32_t)n_sel : 0u;
+    }
+    if (tid == 0) tau[q] = t0;
 }
 
 cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_rows, const uint32_t* tomb,
                                  uint32_t tomb_bits, const uint32_t* allow, int nq, int kc, uint64_t* out,
-                                 uint64_t* kth, cudaStream_t st) {
+                                 float* tau, float* edges, uint32_t* edge_cnt, int* done, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     if (S > SSEL_E * 1024) return cudaErrorInvalidValue;
     int nt = ((S + SSEL_E - 1) / SSEL_E + 31) / 32 * 32;
     if (nt < 64) nt = 64;
-    sample_select_kernel<<<nq, nt, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, kth);
+    // ladder ranks: kc, kc/sqrt2, kc/2 ... 1 (at most LB_NEDGE of them, the largest kept), ascending;
+    // unused low slots repeat the smallest rank (their buckets stay empty)
+    EdgeRanks er;
+    {
+        int lad[64], n = 0, r = kc;
+        for (;;) {
+            lad[n++] = r;
+            if (r == 1 || n == LB_NEDGE) break;
+            int nr = (int)(r * 0.70710678f);
+            r = nr < 1 ? 1 : nr;
+        }
+        for (int i = 0; i < LB_NEDGE; i++) {
+            const int j = LB_NEDGE - 1 - i;  // position from the top
+            er.r[i] = lad[j < n ? j : n - 1];
+        }
+    }
+    sample_select_kernel<<<nq, nt, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, tau, edges,
+                                            edge_cnt, er, done);
     count_launch();
-    return cudaGetLastError();
-}
-
-__global__ void tau_from_kth_kernel(const uint64_t* __restrict__ kth, int nq, int stride, int off,
-                                    float* __restrict__ tau) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    const uint64_t p = kth[(size_t)q * stride + off];
-    tau[q] = (p == kInvalid) ? INFINITY : nextafterf(key_of(p), INFINITY);
-}
-
-cudaError_t launch_tau_from_kth(const uint64_t* kth, int nq, int stride, int off, float* tau, cudaStream_t st) {
-    if (nq <= 0) return cudaSuccess;
-    tau_from_kth_kernel<<<(nq + 127) / 128, 128, 0, st>>>(kth, nq, stride, off, tau);
+    sample_select_exact_kernel<<<nq, nt, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, tau, edges,
+                                                  edge_cnt, done);
     count_launch();
     return cudaGetLastError();
 }
@@ -617,6 +814,7 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     a.part_offset = s.part_offset;
     a.tau_init = s.tau_init;
     a.keys_out = s.keys_out; a.keys_ld = s.keys_ld;
+    a.edges = s.edges; a.edge_cnt = s.edge_cnt;
     dense_scan_tc_plan(s.nq, a.tile_end - a.tile_begin, sm_count, s.kc, &groups, &cand_bytes);
     if (s.keys_out == nullptr && 2 * groups != s.parts) return cudaErrorInvalidValue;  // partial[] sized for s.parts lists
     a.groups = groups;
@@ -624,7 +822,7 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     a.kc = s.kc; a.cap = next_pow2(s.kc + TC_N);
     if (a.cap < 512) a.cap = 512;
     a.cand = cand; a.partial = s.partial; a.debug = s.debug;
-    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 8 * 32 * 32 * 4 + 8 * (2 * TC_STAGES + 4) + 16;
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * 2 * (TC_N / 2) * 4 + 8 * (2 * TC_STAGES + 4) + 16;
     const dim3 grid(nqb * groups);
 #define LB_TC1(KIND_, METRIC_, CAP_)                                                                           \
     {                                                                                                          \

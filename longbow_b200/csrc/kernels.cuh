@@ -29,7 +29,14 @@ struct ScanArgs {
     const float* tau_init = nullptr;
     float* keys_out = nullptr;  // bootstrap sample mode: dump raw keys [nq][keys_ld]
     int keys_ld = 0;
+    // shared progressive threshold (tensor-core scan): per query a ladder of LB_NEDGE keys taken from the
+    // bootstrap sample and the number of live rows seen so far at or below each
+    const float* edges = nullptr;  // [nq][LB_NEDGE] ascending, already nextafter()'d
+    uint32_t* edge_cnt = nullptr;  // [nq][LB_NEDGE]
 };
+
+constexpr int LB_NEDGE = 16;
+struct EdgeRanks { int r[LB_NEDGE]; };  // ascending 1-based sample ranks of the ladder
 
 struct RescoreArgs {
     int dtype, metric;
@@ -75,8 +82,7 @@ bool dense_tc_eligible(int dtype, int dim, const void* db, const void* queries, 
 void dense_scan_tc_plan(int nq, int n_row_tiles, int sm_count, int kc, int* groups_out, size_t* cand_bytes);
 cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_rows, const uint32_t* tomb,
                                  uint32_t tomb_bits, const uint32_t* allow, int nq, int kc, uint64_t* out,
-                                 uint64_t* kth, cudaStream_t st);
-cudaError_t launch_tau_from_kth(const uint64_t* kth, int nq, int stride, int off, float* tau, cudaStream_t st);
+                                 float* tau, float* edges, uint32_t* edge_cnt, int* done, cudaStream_t st);
 cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand, cudaStream_t st);
 
 // ---- PQ (kernels_pq.cu)
