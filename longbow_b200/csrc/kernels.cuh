@@ -4,6 +4,7 @@
 
 namespace lb {
 
+extern bool g_rescore_legacy;
 void count_launch();  // api.cu: process-wide launch counter (bench evidence)
 
 struct ScanArgs {

@@ -13,6 +13,8 @@
 
 namespace lb {
 
+bool g_rescore_legacy = false;  // lb_set_option("rescore_legacy"): A/B the thread-per-candidate kernel
+
 // ---------------------------------------------------------------------------------------------
 // Row auxiliaries used by coarse keys: aux[r] = |x_r|^2 (L2) or 1/|x_r| (cosine; 0 for a
 // zero row, which makes the coarse key 0 == cosine distance 1.0, simd.go:446-448).
@@ -478,10 +480,178 @@ __global__ void rescore_kernel(const T* __restrict__ db, uint32_t n_rows, int di
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// S3, cooperative-gather form (rows 16-byte aligned, row bytes a multiple of 16).
+// The thread-per-candidate kernel above makes every warp-level load touch 32 different cache lines
+// (one 16-byte piece of 32 different rows).  Here a warp gathers its 32 candidate rows together:
+// 128-byte chunks of each row are copied global -> shared with cp.async (each warp instruction
+// covers 4 rows x 128 contiguous bytes = 4 full lines), triple buffered, and lane l then runs the
+// reference-order accumulation of candidate l out of shared memory (row pitch 144 B: conflict free).
+// Arithmetic and order are identical to exact_pair(), so results are bit-identical to the kernel above.
+// ---------------------------------------------------------------------------------------------
+constexpr int RC_WARPS = 4;
+constexpr int RC_CHUNK = 128;            // bytes of a row per stage
+constexpr int RC_PITCH = RC_CHUNK + 16;  // shared-memory row pitch
+constexpr int RC_NBUF = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(RC_WARPS * 32)
+rescore_coop_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T* __restrict__ queries, int nq,
+                    const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ids32, int c, int k, int n2,
+                    const uint32_t* __restrict__ tomb, uint32_t tomb_bits, const uint32_t* __restrict__ allow,
+                    int64_t id_base, float* __restrict__ out_d, int64_t* __restrict__ out_l, int negate_dot,
+                    const float* __restrict__ nrm) {
+    constexpr int V = Elem<T>::kVec;              // elements per 16-byte piece
+    constexpr int PIECES = RC_CHUNK / 16;         // pieces per row chunk
+    constexpr int ACC = (METRIC == METRIC_COSINE) ? METRIC_DOT : METRIC;  // cosine: stored |x|^2, dot chain only
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                      // [n2]
+    float* qf = reinterpret_cast<float*>(keys + n2);                              // [dim]
+    unsigned char* stage_all = reinterpret_cast<unsigned char*>(qf + ((dim + 3) & ~3));  // [warps][NBUF][32][PITCH]
+    __shared__ float s_qn[4];
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const T* qrow = queries + (size_t)q * dim;
+    for (int i = tid; i < dim; i += blockDim.x) qf[i] = Elem<T>::widen(qrow[i]);
+    for (int i = tid; i < n2; i += blockDim.x) keys[i] = kInvalid;
+    __syncthreads();
+    if (METRIC == METRIC_COSINE) {
+        // |q|^2 once per block in the reference lane order (simd.go:399-450)
+        if (tid < 4) {
+            float sacc = 0.f;
+            const int main_end = dim - (dim & 3);
+            for (int i = tid; i < main_end; i += 4) sacc = __fadd_rn(sacc, __fmul_rn(qf[i], qf[i]));
+            if (tid == 0) for (int i = main_end; i < dim; i++) sacc = __fadd_rn(sacc, __fmul_rn(qf[i], qf[i]));
+            s_qn[tid] = sacc;
+        }
+        __syncthreads();
+    }
+    const size_t row_bytes = (size_t)dim * sizeof(T);
+    const int n_chunks = (int)((row_bytes + RC_CHUNK - 1) / RC_CHUNK);
+    unsigned char* stage = stage_all + (size_t)warp * RC_NBUF * 32 * RC_PITCH;
+
+    for (int base = warp * 32; base < c; base += RC_WARPS * 32) {
+        // candidate of this lane
+        const int ci = base + lane;
+        uint32_t id = 0xffffffffu;
+        bool ok = false;
+        if (ci < c) {
+            if (packed != nullptr) {
+                const uint64_t p = packed[(size_t)q * c + ci];
+                if (p != kInvalid) { id = id_of(p); ok = id < n_rows; }
+            } else {
+                id = ids32[(size_t)q * c + ci];
+                ok = id < n_rows;
+                if (ok && allow != nullptr && !bit_set(allow, id)) ok = false;
+                if (ok && tomb != nullptr && id < tomb_bits && bit_set(tomb, id)) ok = false;
+            }
+        }
+        // rows this lane copies: copy instruction i moves piece (lane % 8) of row 4i + lane / 8
+        const unsigned char* src_row[8];
+        bool src_ok[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = 4 * i + (lane >> 3);
+            const uint32_t rid = __shfl_sync(0xffffffffu, id, r);
+            src_ok[i] = __shfl_sync(0xffffffffu, ok ? 1 : 0, r) != 0;
+            src_row[i] = reinterpret_cast<const unsigned char*>(db) + (size_t)rid * row_bytes + (lane & 7) * 16;
+        }
+        auto issue = [&](int ch) {
+            unsigned char* dstb = stage + (size_t)(ch % RC_NBUF) * 32 * RC_PITCH + (lane & 7) * 16;
+            const size_t off = (size_t)ch * RC_CHUNK;
+            const bool in_row = off + (size_t)(lane & 7) * 16 < row_bytes;  // tail chunk: pieces past the row end
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (src_ok[i] && in_row) cp_async16(dstb + (size_t)(4 * i + (lane >> 3)) * RC_PITCH, src_row[i] + off);
+            }
+            cp_async_commit();
+        };
+        ExactAcc<ACC> acc;
+        acc.init();
+        issue(0);
+        if (n_chunks > 1) issue(1); else cp_async_commit();
+        for (int ch = 0; ch < n_chunks; ch++) {
+            if (ch + 2 < n_chunks) issue(ch + 2); else cp_async_commit();
+            cp_async_wait<2>();
+            __syncwarp();
+            if (ok) {
+                const uint4* rowp = reinterpret_cast<const uint4*>(stage + (size_t)(ch % RC_NBUF) * 32 * RC_PITCH +
+                                                                   (size_t)lane * RC_PITCH);
+                const int e0 = ch * (RC_CHUNK / (int)sizeof(T));
+#pragma unroll
+                for (int p = 0; p < PIECES; p++) {
+                    const int i0 = e0 + p * V;
+                    if (i0 < dim) {  // dim % V == 0 on this path: a piece is inside the row entirely or not at all
+                        float x[V];
+                        unpack16<T>(rowp[p], x);
+#pragma unroll
+                        for (int e = 0; e < V; e++) acc.add(e & 3, qf[i0 + e], x[e]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (ok) {
+            float d;
+            if (METRIC == METRIC_COSINE) {
+                const float dot = acc.finish();
+                const float na = __fadd_rn(__fadd_rn(__fadd_rn(s_qn[0], s_qn[1]), s_qn[2]), s_qn[3]);
+                const float nb = __ldg(nrm + id);
+                if (na == 0.f || nb == 0.f) d = 1.0f;
+                else d = __fsub_rn(1.0f, __fdiv_rn(dot, (float)sqrt((double)na * (double)nb)));
+            } else {
+                d = acc.finish();
+            }
+            if (METRIC == METRIC_DOT && negate_dot) d = -d;
+            if (d < INFINITY) keys[ci] = pack_key(d, id);  // NaN / +Inf are never returned
+        }
+    }
+    __syncthreads();
+    block_bitonic_sort(keys, n2);
+    for (int j = tid; j < k; j += blockDim.x) {
+        const uint64_t p = (j < n2) ? keys[j] : kInvalid;
+        const bool valid = p != kInvalid;
+        out_d[(size_t)q * k + j] = valid ? key_of(p) : 3.402823466e+38f;
+        out_l[(size_t)q * k + j] = valid ? (int64_t)id_of(p) + id_base : -1;
+    }
+}
+
 template <typename T>
 static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
     int n2 = next_pow2(max(a.c, 32));
     if (n2 > 1024) return cudaErrorInvalidValue;
+    // cooperative-gather kernel whenever rows are 16-byte aligned multiples of 16 bytes
+    const size_t row_bytes = (size_t)a.dim * sizeof(T);
+    const bool coop = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.db) & 15) == 0) &&
+                      !(a.metric == METRIC_COSINE && a.nrm == nullptr) && !g_rescore_legacy;
+    if (coop) {
+        const size_t smem = (size_t)n2 * 8 + (size_t)((a.dim + 3) & ~3) * 4 + (size_t)RC_WARPS * RC_NBUF * 32 * RC_PITCH;
+#define LB_RC(M)                                                                                            \
+    {                                                                                                       \
+        auto kern = rescore_coop_kernel<T, M>;                                                              \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                     \
+        kern<<<a.nq, RC_WARPS * 32, smem, st>>>((const T*)a.db, a.n_rows, a.dim, (const T*)a.queries, a.nq, \
+                                                a.packed, a.ids32, a.c, a.k, n2, a.tomb, a.tomb_bits, a.allow, \
+                                                a.id_base, a.out_d, a.out_l, a.negate_dot, a.nrm);          \
+    }
+        switch (a.metric) {
+            case METRIC_L2: LB_RC(METRIC_L2) break;
+            case METRIC_COSINE: LB_RC(METRIC_COSINE) break;
+            default: LB_RC(METRIC_DOT) break;
+        }
+#undef LB_RC
+        count_launch();
+        return cudaGetLastError();
+    }
     size_t smem = (size_t)n2 * 8 + (size_t)a.dim * 4;
 #define LB_RS(M)                                                                                            \
     {                                                                                                       \
