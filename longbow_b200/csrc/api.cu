@@ -506,7 +506,7 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         if (parts > 1) {
             CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
             // the re-score stage sorts its kc exact distances, so an unordered top-kc is enough
-            if (merge_select_fits(parts, kc)) CK(launch_merge_select(partial, parts, cq, kc, merged, nullptr, st));
+            if (merge_select_fits(parts, kc)) CK(launch_merge_select(partial, parts, cq, kc, merged, nullptr, a.edges, a.edge_cnt, st));
             else CK(launch_merge_partials(partial, parts, cq, kc, merged, st));
         } else {
             merged = partial;

@@ -221,8 +221,8 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t* a, int n, int lane) 
     for (int size = 2; size <= n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int t = lane; t < (n >> 1); t += 32) {
-                int lo = ((t / stride) * (stride << 1)) + (t % stride);
-                int hi = lo + stride;
+                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));  // stride is a power of two
+                const int hi = lo + stride;
                 bool up = ((lo & size) == 0);
                 uint64_t x = a[lo], y = a[hi];
                 if ((x > y) == up) { a[lo] = y; a[hi] = x; }
@@ -237,8 +237,8 @@ __device__ __forceinline__ void block_bitonic_sort_t(K* a, int n) {
     for (int size = 2; size <= n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
-                int lo = ((t / stride) * (stride << 1)) + (t % stride);
-                int hi = lo + stride;
+                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));  // stride is a power of two
+                const int hi = lo + stride;
                 bool up = ((lo & size) == 0);
                 K x = a[lo], y = a[hi];
                 if ((x > y) == up) { a[lo] = y; a[hi] = x; }
@@ -252,8 +252,8 @@ __device__ __forceinline__ void block_bitonic_sort(uint64_t* a, int n) {
     for (int size = 2; size <= n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
-                int lo = ((t / stride) * (stride << 1)) + (t % stride);
-                int hi = lo + stride;
+                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));  // stride is a power of two
+                const int hi = lo + stride;
                 bool up = ((lo & size) == 0);
                 uint64_t x = a[lo], y = a[hi];
                 if ((x > y) == up) { a[lo] = y; a[hi] = x; }

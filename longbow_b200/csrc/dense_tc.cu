@@ -482,6 +482,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 // accumulator columns from TMEM with the loads in flight together, and let the lanes that
                 // own a survivor append it.  Columns ascend, so every list stays in increasing row order.
                 uint32_t cols = __reduce_or_sync(0xffffffffu, hits);
+                if (a.debug & 32) cols = 0;  // probe: filter only, survivors ignored
                 while (cols) {
                     int jj[4];
                     uint32_t dv[4];
@@ -600,7 +601,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 // Bootstrap selection: per query, the kc smallest (key,row) of a dense [nq][S] sample key matrix
 // (rows [0,S) of the index), honouring n_rows and the tombstone / allow bitmaps.  Block-wide
 // MSB-first radix select over the packed 64-bit value; entries live in registers.
-constexpr int SSEL_E = 32;
+constexpr int SSEL_EMAX = 32;  // entries per thread: 8 / 16 / 32 by sample size
 constexpr int SSEL_SUB = 1024;   // sub-sample whose order statistic supplies the pivot
 constexpr int SSEL_COLL = 2048;  // capacity of the collected (<= pivot) set
 
@@ -619,6 +620,7 @@ __device__ __forceinline__ uint32_t sample_key(const float* __restrict__ keys, i
 // r chosen so that about 4*kc of the S keys fall at or below it; everything <= pivot is collected into
 // shared memory and sorted.  If at least kc were collected, their kc smallest (key,row) are exactly the
 // kc smallest of the whole sample.  Otherwise done[q] stays 0 and the exact kernel below handles q.
+template <int SSEL_E>
 __global__ void __launch_bounds__(1024)
 sample_select_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_rows, const uint32_t* __restrict__ tomb,
                      uint32_t tomb_bits, const uint32_t* __restrict__ allow, int nq, int kc,
@@ -633,11 +635,12 @@ sample_select_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_r
     for (int e = 0; e < SSEL_E; e++)
         v[e] = sample_key(keys, ld, S, n_rows, tomb, tomb_bits, allow, q, (uint32_t)(e * nt + tid));
     if (tid == 0) { s_out = 0; done[q] = 0; }
-    for (int t = tid; t < SSEL_SUB; t += nt) s_sub[t] = 0xffffffffu;
+    const int nsub = next_pow2(nt);  // nt <= 1024 == SSEL_SUB
+    for (int t = tid; t < nsub; t += nt) s_sub[t] = 0xffffffffu;
     __syncthreads();
     s_sub[tid] = v[0];
     __syncthreads();
-    block_bitonic_sort_t<uint32_t>(s_sub, SSEL_SUB);
+    block_bitonic_sort_t<uint32_t>(s_sub, nsub);
     int r = (int)(((int64_t)4 * kc * nt + S - 1) / S);
     if (r < 12) r = 12;
     if (r > nt) return;
@@ -670,6 +673,7 @@ sample_select_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_r
 
 // Exact path for the queries the fast path left (fewer than kc sample rows at or below the pivot, too
 // many, or fewer than kc valid rows at all): block-wide MSB-first search over the packed 64-bit value.
+template <int SSEL_E>
 __global__ void __launch_bounds__(1024)
 sample_select_exact_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_rows,
                            const uint32_t* __restrict__ tomb, uint32_t tomb_bits, const uint32_t* __restrict__ allow,
@@ -712,8 +716,9 @@ cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_ro
                                  uint32_t tomb_bits, const uint32_t* allow, int nq, int kc, uint64_t* out,
                                  float* tau, float* edges, uint32_t* edge_cnt, int* done, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    if (S > SSEL_E * 1024) return cudaErrorInvalidValue;
-    int nt = ((S + SSEL_E - 1) / SSEL_E + 31) / 32 * 32;
+    if (S > SSEL_EMAX * 1024) return cudaErrorInvalidValue;
+    const int E = (S <= 8 * 256) ? 8 : (S <= 16 * 512) ? 16 : 32;
+    int nt = ((S + E - 1) / E + 31) / 32 * 32;
     if (nt < 64) nt = 64;
     // ladder ranks: kc, kc/sqrt2, kc/2 ... 1 (at most LB_NEDGE of them, the largest kept), ascending;
     // unused low slots repeat the smallest rank (their buckets stay empty)
@@ -731,12 +736,17 @@ cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_ro
             er.r[i] = lad[j < n ? j : n - 1];
         }
     }
-    sample_select_kernel<<<nq, nt, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, tau, edges,
-                                            edge_cnt, er, done);
-    count_launch();
-    sample_select_exact_kernel<<<nq, nt, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, tau, edges,
-                                                  edge_cnt, done);
-    count_launch();
+#define LB_SSEL(E_)                                                                                             \
+    {                                                                                                           \
+        sample_select_kernel<E_><<<nq, nt, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, tau, \
+                                                    edges, edge_cnt, er, done);                                 \
+        count_launch();                                                                                         \
+        sample_select_exact_kernel<E_><<<nq, nt, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, \
+                                                          tau, edges, edge_cnt, done);                          \
+        count_launch();                                                                                         \
+    }
+    if (E == 8) LB_SSEL(8) else if (E == 16) LB_SSEL(16) else LB_SSEL(32)
+#undef LB_SSEL
     return cudaGetLastError();
 }
 

@@ -7,6 +7,8 @@ namespace lb {
 extern bool g_rescore_legacy;
 void count_launch();  // api.cu: process-wide launch counter (bench evidence)
 
+constexpr int LB_NEDGE = 16;  // rungs of the shared threshold ladder (dense_tc.cu)
+
 struct ScanArgs {
     int dtype, metric;
     const void* db;          // [n_rows][dim] row-major, element type = dtype
@@ -36,7 +38,6 @@ struct ScanArgs {
     uint32_t* edge_cnt = nullptr;  // [nq][LB_NEDGE]
 };
 
-constexpr int LB_NEDGE = 16;
 struct EdgeRanks { int r[LB_NEDGE]; };  // ascending 1-based sample ranks of the ladder
 
 struct RescoreArgs {
@@ -67,7 +68,7 @@ cudaError_t launch_merge_partials(const uint64_t* partial, int parts, int nq, in
                                   cudaStream_t st);
 bool merge_select_fits(int parts, int kc);
 cudaError_t launch_merge_select(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged, uint64_t* kth,
-                                cudaStream_t st);
+                                const float* edges, const uint32_t* edge_cnt, cudaStream_t st);
 cudaError_t launch_row_norm_exact(int dtype, const void* db, int64_t n, int dim, float* nrm, int64_t row0,
                                   cudaStream_t st);
 cudaError_t launch_rescore(const RescoreArgs& a, cudaStream_t st);

@@ -353,20 +353,67 @@ merge_partials_kernel(const uint64_t* __restrict__ partial, int parts, int nq, i
 constexpr int MSEL_E = 20;
 constexpr int MSEL_T = 256;
 
+constexpr int MSEL_CAP = 2048;  // valid entries the sort path holds in shared memory
+
 __global__ void __launch_bounds__(MSEL_T)
 merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int kc, uint64_t* __restrict__ merged,
-                    uint64_t* __restrict__ kth) {
+                    uint64_t* __restrict__ kth, const float* __restrict__ edges, const uint32_t* __restrict__ edge_cnt) {
     __shared__ int s_red[64];
     __shared__ int s_out;
+    __shared__ uint32_t s_thr;
+    __shared__ uint64_t s_buf[MSEL_CAP];
     const int q = blockIdx.x, tid = threadIdx.x;
     const int total = parts * kc;
+    // Final shared threshold of the tensor-core scan (dense_tc.cu): the lowest ladder edge whose counters
+    // reach kc.  At least kc live rows lie below it, every one of the global kc best among them, and list
+    // compaction only ever dropped rows that are not among those -- so everything at or above the edge
+    // can be discarded before sorting.
+    if (tid == 0) {
+        uint32_t thr = 0xffffffffu;
+        if (edges != nullptr) {
+            uint32_t cum = 0;
+            for (int i = 0; i < LB_NEDGE; i++) {
+                cum += edge_cnt[(size_t)q * LB_NEDGE + i];
+                if (cum >= (uint32_t)kc) {
+                    const float e = edges[(size_t)q * LB_NEDGE + i];
+                    if (e < INFINITY) thr = float_to_ordered(e);
+                    break;
+                }
+            }
+        }
+        s_thr = thr;
+    }
+    // Usual case (tight scan thresholds): the lists are mostly empty.  Compact the valid entries into
+    // shared memory and sort them -- a few hundred to a couple of thousand values.
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    const uint32_t thr = s_thr;
+    for (int i = tid; i < total; i += MSEL_T) {
+        const uint64_t x = partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)];
+        if (x != kInvalid && (uint32_t)(x >> 32) < thr) {
+            const int pos = atomicAdd(&s_out, 1);
+            if (pos < MSEL_CAP) s_buf[pos] = x;
+        }
+    }
+    __syncthreads();
+    const int n = s_out;
+    if (n <= MSEL_CAP) {  // block-uniform
+        const int n2 = next_pow2(max(n, 2));
+        for (int t = n + tid; t < n2; t += MSEL_T) s_buf[t] = kInvalid;
+        __syncthreads();
+        block_bitonic_sort(s_buf, n2);
+        for (int t = tid; t < kc; t += MSEL_T) merged[(size_t)q * kc + t] = (t < n) ? s_buf[t] : kInvalid;
+        if (kth != nullptr && tid == 0) kth[q] = (n >= kc) ? s_buf[kc - 1] : kInvalid;
+        return;
+    }
+    __syncthreads();
+    if (tid == 0) s_out = 0;
     uint64_t v[MSEL_E];
 #pragma unroll
     for (int e = 0; e < MSEL_E; e++) {
         const int i = e * MSEL_T + tid;
         v[e] = (i < total) ? partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)] : kInvalid;
     }
-    if (tid == 0) s_out = 0;
     const uint64_t T = block_kth_smallest<MSEL_E>(v, kc, s_red, tid, MSEL_T / 32);  // kInvalid: keep all valid
     // unordered compaction of everything <= T (exactly kc entries when at least kc are valid)
 #pragma unroll
@@ -384,9 +431,9 @@ merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int
 bool merge_select_fits(int parts, int kc) { return (int64_t)parts * kc <= (int64_t)MSEL_E * MSEL_T; }
 
 cudaError_t launch_merge_select(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged, uint64_t* kth,
-                                cudaStream_t st) {
+                                const float* edges, const uint32_t* edge_cnt, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    merge_select_kernel<<<nq, MSEL_T, 0, st>>>(partial, parts, nq, kc, merged, kth);
+    merge_select_kernel<<<nq, MSEL_T, 0, st>>>(partial, parts, nq, kc, merged, kth, edges, edge_cnt);
     count_launch();
     return cudaGetLastError();
 }
