@@ -215,6 +215,10 @@ int lb_set_option(const char* name, int value) {
         g_opt_tc_boot_tiles.store(value < 0 ? 0 : value);
         return LB_OK;
     }
+    if (strcmp(name, "tc_pair") == 0) {
+        g_tc_pair = value != 0;
+        return LB_OK;
+    }
     if (strcmp(name, "rescore_legacy") == 0) {
         g_rescore_legacy = value != 0;
         return LB_OK;

@@ -23,6 +23,8 @@
 
 namespace lb {
 
+bool g_tc_pair = true;  // lb_set_option("tc_pair"): CTA-pair (cta_group::2) scan on / off
+
 enum { KIND_F16 = 0, KIND_I8 = 1, KIND_TF32 = 2 };
 static_assert(LB_NEDGE == 16, "the epilogue unpacks four uint4 of ladder counters");
 
@@ -43,6 +45,7 @@ template <> struct TcTraits<KIND_TF32> {
 constexpr int TC_M = 128;       // queries per CTA (TMEM lanes)
 constexpr int TC_N = 256;       // rows per tile (TMEM columns per accumulator stage)
 constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES_PAIR = 6;  // CTA-pair variant: 32 KiB stages
 constexpr int TC_A_BYTES = TC_M * 128;   // 16 KiB
 constexpr int TC_B_BYTES = TC_N * 128;   // 32 KiB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -92,6 +95,53 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are credited to `bar` (a shared::cluster
+// address, here always the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if constexpr (KIND == KIND_F16) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    } else if constexpr (KIND == KIND_I8) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    }
+}
+
 template <int KIND>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     if constexpr (KIND == KIND_F16) {
@@ -285,39 +335,59 @@ __device__ __forceinline__ float select_compact(const uint64_t* buf, uint64_t* d
     return (c >= kc) ? ordered_to_float(T) : INFINITY;
 }
 
-template <int KIND, int METRIC, int CAP>
+// CG = 1: one CTA per 128-query block (cta_group::1).  CG = 2: a cluster of two CTAs on one TPC works on
+// two adjacent query blocks with cta_group::2 MMAs (M = 256): each CTA stages its own 128 queries and only
+// HALF of every 256-row database tile, so the shared-memory fill per MMA drops from 48 KiB to 32 KiB and
+// the operand reads from 12 KiB to 8 KiB per instruction -- the CG = 1 kernel is bound by exactly that
+// shared-memory bandwidth.  The leader CTA (cluster rank 0) issues every MMA; accumulators
+// land in each CTA's own TMEM, so the epilogue is identical.
+template <int KIND, int METRIC, int CAP, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const TcArgs a) {
     using TR = TcTraits<KIND>;
+    constexpr int STAGES = (CG == 2) ? TC_STAGES_PAIR : TC_STAGES;
+    constexpr int B_ROWS = TC_N / CG;                 // database rows of a tile this CTA stages
+    constexpr int B_BYTES = B_ROWS * 128;
+    constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* base_ptr = smem_raw + (base - raw);
-    const uint32_t aux_off = TC_STAGES * TC_STAGE_BYTES;                // [2 groups][2 buffers][TC_N / 2] floats
+    const uint32_t aux_off = STAGES * STAGE_BYTES;                      // [2 groups][2 buffers][TC_N / 2] floats
     const uint32_t bar_off = aux_off + 2u * 2u * (TC_N / 2) * 4u;
     const uint32_t bar_base = base + bar_off;
-    // barriers: full[4], empty[4], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
+    // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (2 * TC_STAGES + 4));
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (2 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qb = blockIdx.x / a.groups, g = blockIdx.x % a.groups;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // CTA (pair) index
+    const int qb = (unit / a.groups) * CG + (int)rank, g = unit % a.groups;
+    const bool leader = rank == 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        // full: one arrive.expect_tx (the leader's producer); tmem_empty: 8 epilogue warps of every CTA of the pair
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // peers' barriers are initialised too
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -329,38 +399,50 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             for (int rt = a.tile_begin + g; rt < a.tile_end; rt += a.groups) {
                 for (int kb = 0; kb < a.k_blocks; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const bool first = ((rt - a.tile_begin - g) / a.groups) * a.k_blocks + kb < TC_STAGES;
-                    const bool ld_a = !(a.debug & 4) || first, ld_b = !(a.debug & 2) || first;
-                    mbar_arrive_expect_tx(full_bar(stage), (ld_a ? TC_A_BYTES : 0) + (ld_b ? TC_B_BYTES : 0));
-                    const uint32_t sa = base + stage * TC_STAGE_BYTES;
-                    if (ld_a) tma_load_2d(sa, &map_q, full_bar(stage), kb * TR::kBlockK, qb * TC_M);
-                    if (ld_b) tma_load_2d(sa + TC_A_BYTES, &map_db, full_bar(stage), kb * TR::kBlockK, rt * TC_N);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    const uint32_t sa = base + stage * STAGE_BYTES;
+                    if constexpr (CG == 2) {
+                        // both CTAs load; every byte is credited to the leader's full barrier
+                        const uint32_t fb = map_to_cta(full_bar(stage), 0);
+                        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                        tma_load_2d_pair(sa, &map_q, fb, kb * TR::kBlockK, qb * TC_M);
+                        tma_load_2d_pair(sa + TC_A_BYTES, &map_db, fb, kb * TR::kBlockK, rt * TC_N + (int)rank * B_ROWS);
+                    } else {
+                        const bool first = ((rt - a.tile_begin - g) / a.groups) * a.k_blocks + kb < STAGES;
+                        const bool ld_a = !(a.debug & 4) || first, ld_b = !(a.debug & 2) || first;
+                        mbar_arrive_expect_tx(full_bar(stage), (ld_a ? TC_A_BYTES : 0) + (ld_b ? B_BYTES : 0));
+                        if (ld_a) tma_load_2d(sa, &map_q, full_bar(stage), kb * TR::kBlockK, qb * TC_M);
+                        if (ld_b) tma_load_2d(sa + TC_A_BYTES, &map_db, full_bar(stage), kb * TR::kBlockK, rt * TC_N);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            const uint32_t idesc = TR::kIdescFmt | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+        if (lane == 0 && leader) {
+            const uint32_t idesc = TR::kIdescFmt | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)((TC_M * CG) >> 4) << 24);
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             for (int rt = a.tile_begin + g; rt < a.tile_end; rt += a.groups) {
-                mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
+                mbar_wait(tempty_bar(as), aphase ^ 1u);  // the epilogue(s) have drained this accumulator stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * TC_N;
                 for (int kb = 0; kb < a.k_blocks; kb++) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t sa = base + stage * TC_STAGE_BYTES;
+                    const uint32_t sa = base + stage * STAGE_BYTES;
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + TC_A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; k++)  // 4 x (UMMA_K * elem = 32 B) per 128-byte swizzle row
-                        tc_mma<KIND>(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-                    tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    for (int k = 0; k < 4; k++) {  // 4 x (UMMA_K * elem = 32 B) per 128-byte swizzle row
+                        if constexpr (CG == 2) tc_mma_pair<KIND>(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+                        else tc_mma<KIND>(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+                    }
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                    if constexpr (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(tfull_bar(as));  // accumulator complete -> epilogue
+                // accumulator complete -> epilogue(s)
+                if constexpr (CG == 2) tc_commit_pair(tfull_bar(as)); else tc_commit(tfull_bar(as));
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
@@ -540,7 +622,10 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             // release the accumulator stage (the survivor path re-reads TMEM, so only now)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(as), 0));  // the leader issues the MMAs
+                else mbar_arrive(tempty_bar(as));
+            }
             if (++as == 2) { as = 0; aphase ^= 1u; }
 
             // refresh the shared threshold from the counters fetched at the top of this tile
@@ -588,10 +673,13 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // no CTA leaves while its peer may still touch it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if constexpr (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -809,9 +897,12 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     const int kind = s.dtype == DT_F16 ? KIND_F16 : s.dtype == DT_I8 ? KIND_I8 : KIND_TF32;
     const int elem = kind == KIND_F16 ? 2 : kind == KIND_I8 ? 1 : 4;
     const int block_k = 128 / elem;
+    const int nqb_ = (s.nq + TC_M - 1) / TC_M;
+    // CTA pairs (cta_group::2) whenever the query blocks pair up; lb_set_option("tc_pair", 0) disables
+    const int cg = (g_tc_pair && (nqb_ % 2 == 0) && !(s.debug & 6)) ? 2 : 1;
     CUtensorMap mq, mdb;
     if (!make_map(&mq, kind, s.queries, (uint64_t)s.nq, s.dim, TC_M)) return cudaErrorInvalidValue;
-    if (!make_map(&mdb, kind, s.db, (uint64_t)s.n_rows, s.dim, TC_N)) return cudaErrorInvalidValue;
+    if (!make_map(&mdb, kind, s.db, (uint64_t)s.n_rows, s.dim, TC_N / cg)) return cudaErrorInvalidValue;
     TcArgs a;
     a.aux = s.aux; a.n_rows = s.n_rows; a.nq = s.nq;
     a.k_blocks = (s.dim + block_k - 1) / block_k;
@@ -832,14 +923,33 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     a.kc = s.kc; a.cap = next_pow2(s.kc + TC_N);
     if (a.cap < 512) a.cap = 512;
     a.cand = cand; a.partial = s.partial; a.debug = s.debug;
-    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * 2 * (TC_N / 2) * 4 + 8 * (2 * TC_STAGES + 4) + 16;
+    const size_t stage_bytes = cg == 2 ? (size_t)TC_STAGES_PAIR * (TC_A_BYTES + TC_B_BYTES / 2) : (size_t)TC_STAGES * TC_STAGE_BYTES;
+    const int n_stages = cg == 2 ? TC_STAGES_PAIR : TC_STAGES;
+    const size_t smem = 1024 + stage_bytes + 2 * 2 * (TC_N / 2) * 4 + 8 * (2 * n_stages + 4) + 16;
     const dim3 grid(nqb * groups);
-#define LB_TC1(KIND_, METRIC_, CAP_)                                                                           \
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define LB_TC2(KIND_, METRIC_, CAP_, CG_)                                                                      \
     {                                                                                                          \
-        auto kern = dense_scan_tc<KIND_, METRIC_, CAP_>;                                                       \
+        auto kern = dense_scan_tc<KIND_, METRIC_, CAP_, CG_>;                                                  \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
         if (e != cudaSuccess) return e;                                                                        \
-        kern<<<grid, TC_THREADS, smem, st>>>(mq, mdb, a);                                                      \
+        e = cudaLaunchKernelEx(&cfg, kern, mq, mdb, a);                                                        \
+        if (e != cudaSuccess) return e;                                                                        \
+    }
+#define LB_TC1(KIND_, METRIC_, CAP_)                                                                           \
+    {                                                                                                          \
+        if (cg == 2) LB_TC2(KIND_, METRIC_, CAP_, 2) else LB_TC2(KIND_, METRIC_, CAP_, 1)                      \
     }
 #define LB_TC(KIND_, METRIC_)                                                                                  \
     {                                                                                                          \
@@ -854,6 +964,7 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     }
 #undef LB_TC
 #undef LB_TC1
+#undef LB_TC2
     count_launch();
     return cudaGetLastError();
 }

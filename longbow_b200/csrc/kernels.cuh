@@ -5,6 +5,7 @@
 namespace lb {
 
 extern bool g_rescore_legacy;
+extern bool g_tc_pair;
 void count_launch();  // api.cu: process-wide launch counter (bench evidence)
 
 constexpr int LB_NEDGE = 16;  // rungs of the shared threshold ladder (dense_tc.cu)
