@@ -439,22 +439,20 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
             const int n_tiles = (int)((idx->size + 255) / 256);
             a.tq = 128; a.cap = 0; a.rows_per_part = 0;
             a.debug = g_opt_tc_debug.load(std::memory_order_relaxed);
-            // Bootstrap: the first 32 row tiles (8192 rows) are scanned in "dump keys" mode into a small
-            // [nq][8192] matrix; a radix select gives each query its kc best sample rows and their
-            // kc-th key, a valid upper bound of the global kc-th best.  The main scan starts every
-            // list at that threshold, so its epilogue almost never leaves the 3-instruction filter
-            // (DESIGN.md "bootstrap threshold").
-            // Sample size ~ the rows one candidate list will see in the main scan (so a list expects
-            // fewer than kc survivors), clamped to [8, 128] tiles; small indexes skip the bootstrap.
+            // Bootstrap: the first boot_tiles row tiles are scanned in "dump keys" mode into a small
+            // [nq][S] matrix; sample_select gives each query its kc best sample rows, their kc-th key (a
+            // valid upper bound of the global kc-th best: the scan's starting threshold) and the ladder of
+            // sample keys that seeds the shared progressive threshold.  Small indexes skip it.
             int boot_tiles = 0;
             size_t cand_bytes;
             int gm;
             dense_scan_tc_plan(cq, n_tiles, idx->sm_count, kc, &gm, &cand_bytes);
             if (g_opt_tc_boot.load(std::memory_order_relaxed)) {
                 int bt = g_opt_tc_boot_tiles.load(std::memory_order_relaxed);
-                if (bt <= 0) {
-                    bt = (n_tiles + 2 * gm - 1) / (2 * gm);
+                if (bt <= 0) {  // auto: ~1% of the index, 8..32 tiles (measured optimum at C2: 32 of 3907)
+                    bt = n_tiles / 128;
                     if (bt < 8) bt = 8;
+                    if (bt > 32) bt = 32;
                 }
                 if (bt > 128) bt = 128;
                 if (bt * 4 <= n_tiles) boot_tiles = bt;

@@ -24,8 +24,9 @@ def gather_layout(local_d, local_l, world: int, all_gather):
     import torch
     gd = torch.empty((world,) + tuple(local_d.shape), dtype=local_d.dtype, device=local_d.device)
     gl = torch.empty((world,) + tuple(local_l.shape), dtype=local_l.dtype, device=local_l.device)
-    all_gather(gd, local_d)
-    all_gather(gl, local_l)
+    # the concatenated [world * nq, k] view is the one layout every backend (NCCL, gloo) accepts
+    all_gather(gd.view((-1,) + tuple(local_d.shape[1:])), local_d)
+    all_gather(gl.view((-1,) + tuple(local_l.shape[1:])), local_l)
     return gd, gl
 
 
