@@ -203,7 +203,7 @@ const char* lb_last_error(void) { return t_err.c_str(); }
 int lb_set_option(const char* name, int value) {
     if (!name) return fail(LB_ERR_INVALID, "name is NULL");
     if (strcmp(name, "dense_scan") == 0) {
-        if (value < 0 || value > 2) return fail(LB_ERR_INVALID, "dense_scan: 0 auto, 1 simt, 2 tensor-core");
+        if (value < 0 || value > 3) return fail(LB_ERR_INVALID, "dense_scan: 0 auto, 1 simt, 2 tensor-core, 3 streaming");
         g_opt_dense_scan.store(value);
         return LB_OK;
     }
@@ -432,10 +432,60 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         const int mode = g_opt_dense_scan.load(std::memory_order_relaxed);
         const bool tc_ok = dense_tc_eligible(idx->dtype, idx->dim, idx->rows, a.queries, kc);
         if (mode == 2 && !tc_ok) return fail(LB_ERR_UNSUPPORTED, "tensor-core scan not eligible for this index");
-        const bool use_tc = tc_ok && mode != 1;
+        const bool stream_ok = dense_stream_eligible(idx->dtype, idx->dim, idx->rows, cq, kc);
+        if (mode == 3 && !stream_ok) return fail(LB_ERR_UNSUPPORTED, "streaming scan not eligible for this search");
+        const bool use_stream = stream_ok && (mode == 3 || (mode == 0 && cq == 1));  // single query: HBM-bound streaming kernel
+        // (measured: from 2 queries up the tensor-core scan with one padded query block is already faster)
+        const bool use_tc = !use_stream && tc_ok && mode != 1 && mode != 3;
         uint64_t *partial, *merged;
         int parts;
-        if (use_tc) {
+        bool merged_done = false;
+        if (use_stream) {
+            a.debug = 0;
+            // bootstrap sample ~1% of the rows (2048..8192), skipped for small indexes
+            int64_t S = (idx->size / 128 + 255) / 256 * 256;
+            if (S < 2048) S = 2048;
+            if (S > 8192) S = 8192;
+            if (!g_opt_tc_boot.load(std::memory_order_relaxed) || S * 4 > idx->size) S = 0;
+            int grid = dense_stream_grid(idx->sm_count);
+            const int64_t max_grid = (idx->size - S + 255) / 256;
+            if (grid > max_grid) grid = (int)max_grid;
+            if (grid < 1) grid = 1;
+            parts = 2;  // (unused by the compact merge below)
+            // per query: the sample's kc best (head) + one compact list every CTA appends its survivors to
+            const size_t stride = (size_t)grid * kc;
+            uint64_t *head = nullptr, *compact;
+            uint32_t* out_cnt;
+            CK(scr.get((void**)&compact, (size_t)cq * stride * 8));
+            CK(scr.get((void**)&out_cnt, (size_t)cq * 4));
+            CK(cudaMemsetAsync(out_cnt, 0, (size_t)cq * 4, st));
+            if (S) {
+                float *keys, *tau, *edges;
+                uint32_t* edge_cnt;
+                int* sel_done;
+                CK(scr.get((void**)&head, (size_t)cq * kc * 8));
+                CK(scr.get((void**)&sel_done, (size_t)cq * 4));
+                CK(scr.get((void**)&keys, (size_t)cq * S * 4));
+                CK(scr.get((void**)&tau, (size_t)cq * 4));
+                CK(scr.get((void**)&edges, (size_t)cq * LB_NEDGE * 4));
+                CK(scr.get((void**)&edge_cnt, (size_t)cq * LB_NEDGE * 4));
+                ScanArgs b = a;
+                b.keys_out = keys; b.keys_ld = (int)S; b.partial = nullptr;
+                int gb = (int)((S + 255) / 256);
+                CK(launch_dense_scan_stream(b, gb, 0, (uint32_t)S, nullptr, 0, st));
+                CK(launch_sample_select(keys, (int)S, (int)S, a.n_rows, a.tomb, a.tomb_bits, a.allow, cq, kc, head, tau,
+                                        edges, edge_cnt, sel_done, st));
+                a.edges = edges; a.edge_cnt = edge_cnt; a.tau_init = tau;
+            }
+            a.partial = compact;
+            {
+                ProfScope prof(st, (double)cq * (double)(idx->size - S));
+                CK(launch_dense_scan_stream(a, grid, (uint32_t)S, 0, out_cnt, stride, st));
+            }
+            CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
+            CK(launch_merge_select_compact(head, compact, out_cnt, stride, cq, kc, merged, a.edges, a.edge_cnt, st));
+            merged_done = true;
+        } else if (use_tc) {
             const int n_tiles = (int)((idx->size + 255) / 256);
             a.tq = 128; a.cap = 0; a.rows_per_part = 0;
             a.debug = g_opt_tc_debug.load(std::memory_order_relaxed);
@@ -505,11 +555,11 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
             ProfScope prof(st, (double)cq * (double)idx->size);
             CK(launch_dense_scan_simt(a, st));
         }
-        if (parts > 1) {
+        if (merged_done) {
+        } else if (parts > 1) {
             CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
             // the re-score stage sorts its kc exact distances, so an unordered top-kc is enough
-            if (merge_select_fits(parts, kc)) CK(launch_merge_select(partial, parts, cq, kc, merged, nullptr, a.edges, a.edge_cnt, st));
-            else CK(launch_merge_partials(partial, parts, cq, kc, merged, st));
+            CK(launch_merge_select(partial, parts, cq, kc, merged, nullptr, a.edges, a.edge_cnt, st));
         } else {
             merged = partial;
         }

@@ -534,17 +534,30 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     }
                 }
                 uint32_t hits = 0;
+                if constexpr (KIND == KIND_I8 && METRIC == METRIC_DOT) {
+                    // integer dot, key = -dot: filter in the integer domain (key < tau <=> dot > floor(-tau)),
+                    // no int->float conversion per key (the conversion pipe is a quarter-rate unit)
+                    const int ti = __float2int_rd(-tau);  // saturates: tau = +inf admits every row, -inf none
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    float dot;
-                    if constexpr (KIND == KIND_I8) dot = (float)(int32_t)v[j];
-                    else dot = __uint_as_float(v[j]);
-                    float key;
-                    if constexpr (METRIC == METRIC_L2) key = fmaf(-2.f, dot, ax[j]);
-                    else if constexpr (METRIC == METRIC_COSINE) key = -dot * ax[j];
-                    else key = -dot;
-                    v[j] = __float_as_uint(key);
-                    if (key < tau) hits |= 1u << j;
+                    for (int j = 0; j < 32; j++)
+                        if ((int32_t)v[j] > ti) hits |= 1u << j;
+                    if (dump) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = __float_as_uint(-(float)(int32_t)v[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        float dot;
+                        if constexpr (KIND == KIND_I8) dot = (float)(int32_t)v[j];
+                        else dot = __uint_as_float(v[j]);
+                        float key;
+                        if constexpr (METRIC == METRIC_L2) key = fmaf(-2.f, dot, ax[j]);
+                        else if constexpr (METRIC == METRIC_COSINE) key = -dot * ax[j];
+                        else key = -dot;
+                        v[j] = __float_as_uint(key);
+                        if (key < tau) hits |= 1u << j;
+                    }
                 }
                 if (dump) {
                     // bootstrap sample: write the keys of this chunk (row-major per query)
@@ -899,7 +912,9 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     const int block_k = 128 / elem;
     const int nqb_ = (s.nq + TC_M - 1) / TC_M;
     // CTA pairs (cta_group::2) whenever the query blocks pair up; lb_set_option("tc_pair", 0) disables
-    const int cg = (g_tc_pair && (nqb_ % 2 == 0) && !(s.debug & 6)) ? 2 : 1;
+    const int kb_ = (s.dim + block_k - 1) / block_k;
+    // (short rows are epilogue-bound: a pair only adds cross-CTA hand-shakes there -- measured slower at 128-byte rows)
+    const int cg = (g_tc_pair && (nqb_ % 2 == 0) && kb_ >= 4 && !(s.debug & 6)) ? 2 : 1;
     CUtensorMap mq, mdb;
     if (!make_map(&mq, kind, s.queries, (uint64_t)s.nq, s.dim, TC_M)) return cudaErrorInvalidValue;
     if (!make_map(&mdb, kind, s.db, (uint64_t)s.n_rows, s.dim, TC_N / cg)) return cudaErrorInvalidValue;

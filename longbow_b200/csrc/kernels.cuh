@@ -67,9 +67,13 @@ cudaError_t launch_row_aux(int dtype, const void* db, int64_t n, int dim, int me
                            cudaStream_t st);
 cudaError_t launch_merge_partials(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged,
                                   cudaStream_t st);
-bool merge_select_fits(int parts, int kc);
 cudaError_t launch_merge_select(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged, uint64_t* kth,
                                 const float* edges, const uint32_t* edge_cnt, cudaStream_t st);
+// compact form: per query, `head` kc entries at head[q*kc] (may be null) plus counts[q] entries at
+// compact[q*stride]
+cudaError_t launch_merge_select_compact(const uint64_t* head, const uint64_t* compact, const uint32_t* counts,
+                                        size_t stride, int nq, int kc, uint64_t* merged, const float* edges,
+                                        const uint32_t* edge_cnt, cudaStream_t st);
 cudaError_t launch_row_norm_exact(int dtype, const void* db, int64_t n, int dim, float* nrm, int64_t row0,
                                   cudaStream_t st);
 cudaError_t launch_rescore(const RescoreArgs& a, cudaStream_t st);
@@ -87,6 +91,12 @@ cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_ro
                                  uint32_t tomb_bits, const uint32_t* allow, int nq, int kc, uint64_t* out,
                                  float* tau, float* edges, uint32_t* edge_cnt, int* done, cudaStream_t st);
 cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand, cudaStream_t st);
+
+// ---- streaming scan for small query batches (dense_stream.cu)
+bool dense_stream_eligible(int dtype, int dim, const void* db, int nq, int kc);
+int dense_stream_grid(int sm_count);
+cudaError_t launch_dense_scan_stream(const ScanArgs& s, int grid, uint32_t row_begin, uint32_t dump_rows,
+                                     uint32_t* out_cnt, size_t out_stride, cudaStream_t st);
 
 // ---- PQ (kernels_pq.cu)
 struct PqScanArgs {

@@ -344,30 +344,32 @@ merge_partials_kernel(const uint64_t* __restrict__ partial, int parts, int nq, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// S2 (selection form): per query, keep the kc smallest of parts*kc packed entries WITHOUT sorting:
-// block-wide MSB-first radix select (8 passes x 8 bits over the packed 64-bit (key,row) value, so
-// ties in the key are resolved by row id), then an unordered compaction.  Entries live in
-// registers (<= 20 per thread).  ~10x fewer instructions than the bitonic merge; the re-score
-// stage sorts its kc exact distances anyway.  Optionally reports the kc-th value (bootstrap).
+// S2 (selection form): per query, the kc smallest (key,row) of parts*kc packed entries.
+// Entries are first filtered by the final shared threshold of the scan (when there is one) and compacted
+// into a 4096-entry shared buffer; the buffer is sorted whenever it fills (keeping the best kc) and once
+// at the end.  With tight scan thresholds the lists are nearly empty and a single short sort remains; in
+// the worst case (no threshold, every slot valid) this degrades to the streaming merge above.
+// Output is sorted ascending.
 // ---------------------------------------------------------------------------------------------
-constexpr int MSEL_E = 20;
 constexpr int MSEL_T = 256;
-
-constexpr int MSEL_CAP = 2048;  // valid entries the sort path holds in shared memory
+constexpr int MSEL_CAP = 4096;
 
 __global__ void __launch_bounds__(MSEL_T)
 merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int kc, uint64_t* __restrict__ merged,
-                    uint64_t* __restrict__ kth, const float* __restrict__ edges, const uint32_t* __restrict__ edge_cnt) {
-    __shared__ int s_red[64];
-    __shared__ int s_out;
+                    uint64_t* __restrict__ kth, const float* __restrict__ edges, const uint32_t* __restrict__ edge_cnt,
+                    const uint64_t* __restrict__ compact, const uint32_t* __restrict__ counts, size_t stride) {
+    __shared__ int s_n;
     __shared__ uint32_t s_thr;
     __shared__ uint64_t s_buf[MSEL_CAP];
     const int q = blockIdx.x, tid = threadIdx.x;
-    const int total = parts * kc;
-    // Final shared threshold of the tensor-core scan (dense_tc.cu): the lowest ladder edge whose counters
-    // reach kc.  At least kc live rows lie below it, every one of the global kc best among them, and list
-    // compaction only ever dropped rows that are not among those -- so everything at or above the edge
-    // can be discarded before sorting.
+    // list form: partial[part][q][kc].  compact form: `parts` (0 or 1) head lists of kc entries at
+    // partial[q*kc], then counts[q] entries at compact[q*stride].
+    const int head = parts * kc;
+    const int total = (compact != nullptr) ? head + (int)min((size_t)counts[q], stride) : head;
+    // Final shared threshold of the scan (dense_tc.cu / dense_stream.cu): the lowest ladder edge whose
+    // counters reach kc.  At least kc live rows lie below it, every one of the global kc best among them,
+    // and list compaction only ever dropped rows that are not among those -- so everything at or above the
+    // edge can be discarded before sorting.
     if (tid == 0) {
         uint32_t thr = 0xffffffffu;
         if (edges != nullptr) {
@@ -382,58 +384,60 @@ merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int
             }
         }
         s_thr = thr;
+        s_n = 0;
     }
-    // Usual case (tight scan thresholds): the lists are mostly empty.  Compact the valid entries into
-    // shared memory and sort them -- a few hundred to a couple of thousand values.
-    if (tid == 0) s_out = 0;
     __syncthreads();
     const uint32_t thr = s_thr;
-    for (int i = tid; i < total; i += MSEL_T) {
-        const uint64_t x = partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)];
-        if (x != kInvalid && (uint32_t)(x >> 32) < thr) {
-            const int pos = atomicAdd(&s_out, 1);
-            if (pos < MSEL_CAP) s_buf[pos] = x;
+    int have = 0;  // s_buf[0, have) = best so far (sorted) after a flush
+    for (int base = 0; base < total; base += MSEL_T) {
+        const int i = base + tid;
+        uint64_t x = kInvalid;
+        if (i < total) {
+            if (compact == nullptr) x = partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)];
+            else x = (i < head) ? partial[(size_t)q * kc + i] : compact[(size_t)q * stride + (i - head)];
         }
-    }
-    __syncthreads();
-    const int n = s_out;
-    if (n <= MSEL_CAP) {  // block-uniform
-        const int n2 = next_pow2(max(n, 2));
-        for (int t = n + tid; t < n2; t += MSEL_T) s_buf[t] = kInvalid;
+        const bool keep = (x != kInvalid) && ((uint32_t)(x >> 32) < thr);
+        if (keep) {
+            const int pos = have + atomicAdd(&s_n, 1);  // < MSEL_CAP: flushed before MSEL_T more could overflow
+            s_buf[pos] = x;
+        }
         __syncthreads();
-        block_bitonic_sort(s_buf, n2);
-        for (int t = tid; t < kc; t += MSEL_T) merged[(size_t)q * kc + t] = (t < n) ? s_buf[t] : kInvalid;
-        if (kth != nullptr && tid == 0) kth[q] = (n >= kc) ? s_buf[kc - 1] : kInvalid;
-        return;
-    }
-    __syncthreads();
-    if (tid == 0) s_out = 0;
-    uint64_t v[MSEL_E];
-#pragma unroll
-    for (int e = 0; e < MSEL_E; e++) {
-        const int i = e * MSEL_T + tid;
-        v[e] = (i < total) ? partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)] : kInvalid;
-    }
-    const uint64_t T = block_kth_smallest<MSEL_E>(v, kc, s_red, tid, MSEL_T / 32);  // kInvalid: keep all valid
-    // unordered compaction of everything <= T (exactly kc entries when at least kc are valid)
-#pragma unroll
-    for (int e = 0; e < MSEL_E; e++) {
-        if (v[e] != kInvalid && v[e] <= T) {
-            const int pos = atomicAdd(&s_out, 1);
-            if (pos < kc) merged[(size_t)q * kc + pos] = v[e];
+        if (have + s_n > MSEL_CAP - MSEL_T) {  // block-uniform: sort, keep the best kc, continue
+            const int n = have + s_n;
+            const int n2 = next_pow2(n);
+            for (int t = n + tid; t < n2; t += MSEL_T) s_buf[t] = kInvalid;
+            __syncthreads();
+            block_bitonic_sort(s_buf, n2);
+            have = min(n, kc);
+            if (tid == 0) s_n = 0;
+            __syncthreads();
         }
     }
+    const int n = have + s_n;
+    const int n2 = next_pow2(max(n, 2));
+    for (int t = n + tid; t < n2; t += MSEL_T) s_buf[t] = kInvalid;
     __syncthreads();
-    for (int t = s_out + tid; t < kc; t += MSEL_T) merged[(size_t)q * kc + t] = kInvalid;
-    if (kth != nullptr && tid == 0) kth[q] = T;  // kInvalid when fewer than kc valid entries exist
+    block_bitonic_sort(s_buf, n2);
+    for (int t = tid; t < kc; t += MSEL_T) merged[(size_t)q * kc + t] = (t < n) ? s_buf[t] : kInvalid;
+    if (kth != nullptr && tid == 0) kth[q] = (n >= kc) ? s_buf[kc - 1] : kInvalid;
 }
-
-bool merge_select_fits(int parts, int kc) { return (int64_t)parts * kc <= (int64_t)MSEL_E * MSEL_T; }
 
 cudaError_t launch_merge_select(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged, uint64_t* kth,
                                 const float* edges, const uint32_t* edge_cnt, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    merge_select_kernel<<<nq, MSEL_T, 0, st>>>(partial, parts, nq, kc, merged, kth, edges, edge_cnt);
+    if (kc > MSEL_CAP - 2 * MSEL_T) return cudaErrorInvalidValue;
+    merge_select_kernel<<<nq, MSEL_T, 0, st>>>(partial, parts, nq, kc, merged, kth, edges, edge_cnt, nullptr, nullptr, 0);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_select_compact(const uint64_t* head, const uint64_t* compact, const uint32_t* counts,
+                                        size_t stride, int nq, int kc, uint64_t* merged, const float* edges,
+                                        const uint32_t* edge_cnt, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    if (kc > MSEL_CAP - 2 * MSEL_T) return cudaErrorInvalidValue;
+    merge_select_kernel<<<nq, MSEL_T, 0, st>>>(head, head ? 1 : 0, nq, kc, merged, nullptr, edges, edge_cnt, compact,
+                                               counts, stride);
     count_launch();
     return cudaGetLastError();
 }

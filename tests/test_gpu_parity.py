@@ -396,3 +396,58 @@ def test_tensor_core_bootstrap_ties_and_toggle(lbgpu, oracle, scan_mode):
     finally:
         _lib.set_option("tc_boot", 1)
     idx.close()
+
+
+# ------------------------------------------------------------------ streaming scan (small query batches)
+@pytest.mark.parametrize("dtype,metric", [(np.float16, COS), (np.float16, L2), (np.float32, L2), (np.float32, DOT),
+                                          (np.float32, COS), (np.int8, DOT), (np.int8, L2)])
+@pytest.mark.parametrize("n,dim,k", [(70001, 768, 100), (40000, 128, 10), (300, 128, 5), (9000, 256, 32), (131072, 64, 10)])
+@pytest.mark.parametrize("nq", [1, 3, 8])
+def test_streaming_scan_parity(lbgpu, oracle, scan_mode, dtype, metric, n, dim, k, nq):
+    if (dim * np.dtype(dtype).itemsize) % 128 != 0:
+        pytest.skip("row bytes not a multiple of 128: not eligible for the streaming scan")
+    rng = np.random.default_rng(3000 + n + metric + nq)
+    db, q = make_db(rng, n, dim, dtype), make_db(rng, nq, dim, dtype)
+    if metric == COS:
+        db[[3, n // 2, n - 1]] = 0
+    if n > 1000:
+        db[n // 3] = db[5]  # exact duplicate rows across the bootstrap sample boundary: ties by id
+        q[0] = db[5]
+    idx = lbgpu.DenseIndex(dim, dtype, metric)
+    idx.add(db)
+    wd, wl = oracle.search(metric, db, q, k)
+    scan_mode(3)
+    gd, gl = idx.search(q, k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, f"stream {dtype.__name__} metric={metric} nq={nq}")
+    scan_mode(0)  # auto must pick an exact path too
+    gd, gl = idx.search(q, k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "auto")
+    tomb, allow = random_bitmap(rng, n, 0.05), random_bitmap(rng, n, 0.30)
+    idx.set_tombstones(tomb)
+    scan_mode(3)
+    gd, gl = idx.search(q, k, allow=allow)
+    wd, wl = oracle.search(metric, db, q, k, tomb=lbgpu.pack_bitmap(tomb), allow=lbgpu.pack_bitmap(allow))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "stream + bitmaps")
+    idx.close()
+
+
+def test_streaming_scan_adversarial_order(lbgpu, oracle, scan_mode):
+    """Rows sorted from worst to best: every row beats the running threshold, so the lists overflow and the
+    compaction path runs on every trip."""
+    rng = np.random.default_rng(77)
+    n, dim = 60000, 128
+    q = rng.random((2, dim), dtype=np.float32)
+    db = rng.random((n, dim), dtype=np.float32)
+    order = np.argsort(-np.linalg.norm(db - q[0], axis=1))
+    db = np.ascontiguousarray(db[order])
+    idx = lbgpu.DenseIndex(dim, np.float32, L2)
+    idx.add(db)
+    scan_mode(3)
+    from longbow_b200 import _lib
+    for boot in (1, 0):
+        _lib.set_option("tc_boot", boot)
+        gd, gl = idx.search(q, 50)
+        wd, wl = oracle.search(L2, db, q, 50)
+        assert_topk_equal(gd, gl, wd, wl, 0.0, f"adversarial boot={boot}")
+    _lib.set_option("tc_boot", 1)
+    idx.close()

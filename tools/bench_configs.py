@@ -25,6 +25,9 @@ HBM = PEAKS.get("hbm_gbs", 6650.0)
 TF = PEAKS.get("bf16_tflops", 1590.0)
 dev = torch.device("cuda", 0)
 STEPS = int(os.environ.get("STEPS", "10"))
+for _opt in ("tc_pair", "dense_scan", "tc_boot_tiles"):
+    if os.environ.get(_opt.upper()):
+        _lib.set_option(_opt, int(os.environ[_opt.upper()]))
 
 
 def timed(fn, steps=STEPS, warm=3):
@@ -88,6 +91,13 @@ def c2():
     ol = torch.empty((Q, K), dtype=torch.int64, device=dev)
     ms, sm = timed(lambda: idx.search_device(qs, K, od, ol))
     report("C2 brute-force cosine k=100, 1M x 768 fp16, 1024 queries", ms, sm, Q, N * D * 2, 2.0 * Q * N * D)
+    for nq in (1, 2, 4, 8, 32):
+        qn = qs[:nq].contiguous()
+        odn = torch.empty((nq, K), dtype=torch.float32, device=dev)
+        oln = torch.empty((nq, K), dtype=torch.int64, device=dev)
+        ms, sm = timed(lambda: idx.search_device(qn, K, odn, oln))
+        report(f"C2 database, {nq} quer{'y' if nq == 1 else 'ies'} per call (HBM-bound streaming scan)", ms, sm, nq,
+               N * D * 2, None)
     idx.close()
 
 
@@ -144,6 +154,12 @@ def c4():
     ol1 = torch.empty((1, K), dtype=torch.int64, device=dev)
     ms, sm = timed(lambda: idx.search_device(q1, K, od1, ol1))
     report("C4 single query (HBM-bound pass over the shard)", ms, sm, 1, N * D, None)
+    for nq in (2, 4, 8, 32):
+        qn = qs[:nq].contiguous()
+        odn = torch.empty((nq, K), dtype=torch.float32, device=dev)
+        oln = torch.empty((nq, K), dtype=torch.int64, device=dev)
+        ms, sm = timed(lambda: idx.search_device(qn, K, odn, oln))
+        report(f"C4 shard, {nq} queries per call (streaming scan)", ms, sm, nq, N * D, None)
     idx.close()
 
 
