@@ -262,6 +262,34 @@ def main():
         e2e = {"value": NQ * steps / dt, "unit": "queries/s", "h2d_bytes_per_step": NQ * DIM * 2 * world,
                "d2h_bytes_per_step": NQ * K * 12, "ms_per_step": dt / steps * 1e3}
 
+    # ---- the HBM-bound end of the same path: one query per call (gpu.Index.Search as the reference calls it),
+    # device-resident, streaming scan; reported as scan GB/s against the measured copy bandwidth
+    hbm_scan = None
+    if world == 1:
+        q1 = d_qs[0, :1].contiguous()
+        o1d = torch.empty((1, K), dtype=torch.float32, device=dev)
+        o1l = torch.empty((1, K), dtype=torch.int64, device=dev)
+        for _ in range(5):
+            sidx.search_device(q1, K, o1d, o1l)
+        torch.cuda.synchronize()
+        _lib.prof_read(reset=True)
+        _lib.prof_enable(True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        n1 = 20
+        for i in range(n1):
+            sidx.search_device(d_qs[(i % (warm + steps)), :1], K, o1d, o1l)
+        s1.record()
+        torch.cuda.synchronize()
+        _lib.prof_enable(False)
+        k_ms, k_n, k_units = _lib.prof_read(reset=True)
+        l1 = _lib.launch_count()
+        if k_n:
+            rows_scanned = k_units / k_n
+            hbm_scan = {"queries_per_call": 1, "ms_per_call": s0.elapsed_time(s1) / n1,
+                        "scan_kernel_ms": k_ms / k_n, "bytes_per_launch": rows_scanned * DIM * 2,
+                        "achieved_gbs": rows_scanned * DIM * 2 / (k_ms / k_n * 1e-3) / 1e9}
+
     if rank == 0:
         peaks = {}
         try:
@@ -276,8 +304,24 @@ def main():
         avg_scan_ms = scan_ms / max(scan_n, 1)
         achieved = flops_per_launch / (avg_scan_ms * 1e-3) / 1e12 if scan_n else None
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))
+            for kname, rec in tj.items():
+                if kname.startswith("dense_scan_tc") and world == 1 and n_rows == N_ROWS:
+                    traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+        except Exception:
+            pass
+        sustained = peaks.get("bf16_tflops_sustained")
+        if hbm_scan is not None:
+            hbm_scan["peak_gbs"] = hbm_peak = peaks.get("hbm_gbs", 6650.0)
+            hbm_scan["frac"] = hbm_scan["achieved_gbs"] / hbm_peak
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "frac_of_sustained_peak": (achieved / sustained) if (achieved and sustained) else None,
+                "algorithmic_bytes_per_launch": scan_units / max(scan_n, 1) / NQ * DIM * 2,
+                "algorithmic_flops_per_launch": flops_per_launch,
+                "hbm_bound_single_query_scan": hbm_scan,
                 "kernel": "coarse distance scan + fused top-k (dense_scan)", "avg_launch_ms": avg_scan_ms,
                 "launches_timed": scan_n, "share_of_step": scan_ms / ms if ms else None,
                 "rows_per_launch": scan_units / max(scan_n, 1) / NQ,

@@ -96,6 +96,8 @@ dense_scan_stream(const StreamArgs a) {
     constexpr int V = SQ::kV;
     constexpr int RPW = 32 / LPR;                       // rows per warp instruction
     constexpr int ROWS_PER_ITER = ST_WARPS * U * RPW;   // rows one CTA consumes per loop trip
+    constexpr int CHK = (512 / ROWS_PER_ITER) > 0 ? (512 / ROWS_PER_ITER) : 1;
+    static_assert(CHK * ROWS_PER_ITER <= 512, "candidate lists are sized for 512 rows between overflow checks");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     QT* qs = reinterpret_cast<QT*>(smem_raw);                                   // [NQ][dim]
     const size_t q_bytes = ((size_t)NQ * a.dim * sizeof(QT) + 15) & ~(size_t)15;
@@ -133,7 +135,9 @@ dense_scan_stream(const StreamArgs a) {
     for (uint32_t base = a.row_begin + blockIdx.x * ROWS_PER_ITER; base < n_rows;
          base += gridDim.x * ROWS_PER_ITER, iter++) {
         // shared-threshold counters: fetched now (L2), folded into s_tau after this trip's rows are done
-        const bool refresh = shared_tau && !dump && (iter & 3) == 0 && tid < a.nq;
+        // list-overflow check and threshold refresh need block barriers: only every CHK trips (<= 512 rows)
+        const bool chk = ((iter + 1) % CHK) == 0;  // block-uniform
+        const bool refresh = shared_tau && !dump && chk && tid < a.nq;
         uint4 gc[LB_NEDGE / 4];
         if (refresh) {
 #pragma unroll
@@ -203,12 +207,12 @@ dense_scan_stream(const StreamArgs a) {
                 }
             }
         }
-        if (dump) continue;
+        if (dump || !chk) continue;
         __syncthreads();
-        // compaction of any list that could overflow on the next trip; shared-threshold refresh
+        // compaction of any list that could overflow before the next check; shared-threshold refresh
         for (int q = 0; q < a.nq; q++) {
             const int c = min(s_cnt[q], a.cap);
-            if (c > a.cap - ROWS_PER_ITER) {  // block-uniform
+            if (c > a.cap - CHK * ROWS_PER_ITER) {  // block-uniform
                 uint64_t* buf = lists + (size_t)q * a.cap;
                 const int n2 = next_pow2(c);
                 for (int t = c + tid; t < n2; t += ST_THREADS) buf[t] = kInvalid;
@@ -286,7 +290,7 @@ static cudaError_t launch_stream_nq(const StreamArgs& a, int grid, cudaStream_t 
         }                                                                                                    \
         kern<<<grid, ST_THREADS, smem, st>>>(a);                                                             \
     }
-    if (row_bytes >= 384) LB_ST(32, (NQ == 1 ? 8 : NQ == 2 ? 4 : 2)) else LB_ST(8, (NQ == 1 ? 16 : NQ == 2 ? 8 : 4))
+    if (row_bytes >= 384) LB_ST(32, (NQ == 1 ? 8 : NQ == 2 ? 4 : 2)) else LB_ST(8, (NQ <= 2 ? 8 : 4))
 #undef LB_ST
     count_launch();
     return cudaGetLastError();
