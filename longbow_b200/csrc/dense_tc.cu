@@ -495,6 +495,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         uint32_t aphase = 0;
         int abuf = 0;
         int rt = a.tile_begin + g;
+        uint32_t tile_no = 0;
         // Row auxiliaries (|x|^2 or 1/|x|) of a tile are staged in shared memory one tile ahead: the
         // global load for the NEXT tile is issued before this tile's accumulator is awaited, so its
         // L2 latency never sits between a TMEM load and the filter.
@@ -512,9 +513,12 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 if (rt + a.groups < a.tile_end)
                     axn = __ldg(a.aux + (size_t)(rt + a.groups) * TC_N + grp * HALF + tq);
             }
-            // counters of the shared threshold: loaded (L2, never L1) before the wait, used after the tile
+            // counters of the shared threshold: loaded (L2, never L1) before the wait, used after the tile.
+            // Short rows make tiles cheap (one k-block = 4 MMAs): refresh only every 8th tile there.
+            const bool do_refresh = shared_tau && (a.k_blocks >= 4 || (tile_no & 7) == 0);
+            tile_no++;
             uint4 gc[LB_NEDGE / 4];
-            if (shared_tau) {
+            if (do_refresh) {
 #pragma unroll
                 for (int i = 0; i < LB_NEDGE / 4; i++) gc[i] = __ldcg(reinterpret_cast<const uint4*>(gcnt) + i);
             }
@@ -538,9 +542,25 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     // integer dot, key = -dot: filter in the integer domain (key < tau <=> dot > floor(-tau)),
                     // no int->float conversion per key (the conversion pipe is a quarter-rate unit)
                     const int ti = __float2int_rd(-tau);  // saturates: tau = +inf admits every row, -inf none
+                    // First the chunk maximum (3-input integer max, four independent chains: ~0.5 instruction
+                    // per key); the per-key mask is built only when some lane of the warp has a survivor.
+                    // (v[0..3] seed the chains; trips j = 4, 12, 20 add eight values each, j = 28 the last four)
+                    int m0 = (int32_t)v[0], m1 = (int32_t)v[1], m2 = (int32_t)v[2], m3 = (int32_t)v[3];
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if ((int32_t)v[j] > ti) hits |= 1u << j;
+                    for (int j = 4; j < 32; j += 8) {
+                        m0 = __vimax3_s32(m0, (int32_t)v[j], (int32_t)v[j + 1]);
+                        m1 = __vimax3_s32(m1, (int32_t)v[j + 2], (int32_t)v[j + 3]);
+                        if (j + 4 < 32) {
+                            m2 = __vimax3_s32(m2, (int32_t)v[j + 4], (int32_t)v[j + 5]);
+                            m3 = __vimax3_s32(m3, (int32_t)v[j + 6], (int32_t)v[j + 7]);
+                        }
+                    }
+                    const int mx = max(__vimax3_s32(m0, m1, m2), m3);
+                    if (__any_sync(0xffffffffu, mx > ti) || dump) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if ((int32_t)v[j] > ti) hits |= 1u << j;
+                    }
                     if (dump) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) v[j] = __float_as_uint(-(float)(int32_t)v[j]);
@@ -642,7 +662,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             if (++as == 2) { as = 0; aphase ^= 1u; }
 
             // refresh the shared threshold from the counters fetched at the top of this tile
-            if (shared_tau) {
+            if (do_refresh) {
                 const uint32_t cv[LB_NEDGE] = {gc[0].x, gc[0].y, gc[0].z, gc[0].w, gc[1].x, gc[1].y, gc[1].z, gc[1].w,
                                                gc[2].x, gc[2].y, gc[2].z, gc[2].w, gc[3].x, gc[3].y, gc[3].z, gc[3].w};
                 uint32_t cum = 0;
