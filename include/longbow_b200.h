@@ -119,10 +119,12 @@ int lb_index_rerank_device(lb_index *idx, const void *d_queries, int64_t nq, con
  * (simd.EuclideanDistanceBatchFlat with the flat buffer already in HBM). */
 int lb_index_distances(lb_index *idx, const void *query, float *out);
 
-/* Diagnostics of the last search on this handle by the calling thread: number of queries whose
- * result was NOT certified exact by the coarse-margin test (see DESIGN.md "certification").
- * 0 means every returned top-k provably equals the exhaustive exact top-k. */
+/* Reserved (always 0 in this version). */
 int64_t lb_index_last_uncertified(const lb_index *idx);
+/* Diagnostics: the COARSE ranking keys the tensor-core scan computes for rows [0, n_rows) of nq queries
+ * (out: [nq][n_rows]): |x|^2 - 2 q.x (L2), -q.x/|x| (cosine), -q.x (dot).  They only rank candidates -- every
+ * returned distance comes from the exact re-score -- and exist so tests can bound the coarse error. */
+int lb_index_coarse_keys(lb_index *idx, const void *queries, int64_t nq, int64_t n_rows, float *out);
 
 /* ------------------------------------------------------------------------------------------
  * 3. Stateless simd surface (host buffers in, host buffers out; data uploaded per call).
@@ -194,6 +196,8 @@ int64_t lb_kernel_launch_count(void);
 /* Test / diagnostic knobs.  "dense_scan": 0 = auto (tensor-core scan when the index is eligible:
  * fp16 or int8, 16-byte row pitch), 1 = force the SIMT scan, 2 = force the tensor-core scan
  * (LB_ERR_UNSUPPORTED if not eligible).  Both scans feed the same exact re-score stage.
+ * "dense_scan" 3 = force the streaming scan (1..8 queries).  "tc_pair": CTA-pair MMAs on/off.
+ * "f32_tc": 3xTF32 tensor-core scan for fp32 indexes on/off.  "tc_boot_tiles": bootstrap sample size.
  * "tc_boot": 1 (default) = bootstrap-threshold pre-scan for the tensor-core path, 0 = off.
  * "tc_debug": timing probes of the tensor-core scan; results are INVALID when non-zero. */
 int lb_set_option(const char *name, int value);

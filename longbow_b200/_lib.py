@@ -47,6 +47,7 @@ SIGNATURES = {
     "lb_index_rerank_device": (i32, [vp, vp, i64, vp, i32, i32, vp, vp, vp, vp]),
     "lb_index_distances": (i32, [vp, vp, vp]),
     "lb_index_last_uncertified": (i64, [vp]),
+    "lb_index_coarse_keys": (i32, [vp, vp, i64, i64, vp]),
     "lb_simd_distance_batch_flat": (i32, [i32, i32, i32, vp, vp, i64, i32, vp]),
     "lb_simd_adc_distance_batch": (i32, [i32, vp, vp, i32, i64, vp]),
     "lb_select_k": (i32, [i32, vp, i64, i32, vp, vp]),

@@ -91,6 +91,7 @@ struct Scratch {
 static std::atomic<int> g_opt_dense_scan{0};
 static std::atomic<int> g_opt_tc_debug{0};
 static std::atomic<int> g_opt_tc_boot_tiles{0};  // 0 = auto
+static std::atomic<int> g_opt_f32_tc{1};         // fp32 indexes: 3xTF32 tensor-core scan (0: SIMT scan)
 static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off (A/B timing)    // timing probes of the tensor-core scan (results invalid when != 0)  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
 
 // ---- dominant-kernel timing (lb_prof_*)
@@ -128,6 +129,9 @@ struct lb_index {
     void* rows = nullptr;  // [capacity][dim]
     float* aux = nullptr;  // [capacity + 256] coarse-key auxiliaries
     float* nrm = nullptr;  // [capacity] cosine only: exact |x|^2 in reference lane order
+    float* lo = nullptr;   // fp32 only, built on first tensor-core search: x - tf32(x) for the 3xTF32 scan
+    int64_t lo_rows = 0, lo_cap = 0;
+    std::mutex lo_mu;
     int64_t size = 0, capacity = 0;
     uint32_t* tomb = nullptr;
     int64_t tomb_bits = 0, tomb_cap_words = 0;
@@ -215,6 +219,10 @@ int lb_set_option(const char* name, int value) {
         g_opt_tc_boot_tiles.store(value < 0 ? 0 : value);
         return LB_OK;
     }
+    if (strcmp(name, "f32_tc") == 0) {
+        g_opt_f32_tc.store(value ? 1 : 0);
+        return LB_OK;
+    }
     if (strcmp(name, "tc_pair") == 0) {
         g_tc_pair = value != 0;
         return LB_OK;
@@ -292,6 +300,7 @@ void lb_index_free(lb_index* idx) {
         if (idx->rows) cudaFree(idx->rows);
         if (idx->aux) cudaFree(idx->aux);
         if (idx->nrm) cudaFree(idx->nrm);
+        if (idx->lo) cudaFree(idx->lo);
         if (idx->tomb) cudaFree(idx->tomb);
     }
     cudaGetLastError();
@@ -405,6 +414,29 @@ static int coarse_k(int k) {
     return ((kc + 31) / 32) * 32;
 }
 
+// fp32 indexes: the low parts of the rows for the 3xTF32 tensor-core scan, built (or extended after an add) by
+// the first search that needs them.  Searches may run concurrently (read lock on the Go side), so the build is
+// serialised here; rows only ever grow, and add() needs exclusive access anyway.
+static int ensure_lo(lb_index* idx, cudaStream_t st) {
+    std::lock_guard<std::mutex> g(idx->lo_mu);
+    if (idx->lo_rows == idx->size && idx->lo != nullptr) return LB_OK;
+    if (idx->lo_cap < idx->capacity || idx->lo == nullptr) {
+        float* nl = nullptr;
+        CK(cudaMalloc((void**)&nl, (size_t)idx->capacity * idx->dim * 4));
+        CK(cudaDeviceSynchronize());
+        if (idx->lo && idx->lo_rows > 0)
+            CK(cudaMemcpy(nl, idx->lo, (size_t)idx->lo_rows * idx->dim * 4, cudaMemcpyDeviceToDevice));
+        if (idx->lo) cudaFree(idx->lo);
+        idx->lo = nl;
+        idx->lo_cap = idx->capacity;
+    }
+    const size_t off = (size_t)idx->lo_rows * idx->dim;
+    CK(launch_split_lo((const float*)idx->rows + off, idx->lo + off, (size_t)(idx->size - idx->lo_rows) * idx->dim, st));
+    CK(cudaStreamSynchronize(st));  // other threads' streams may use it as soon as the lock drops
+    idx->lo_rows = idx->size;
+    return LB_OK;
+}
+
 static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const uint64_t* d_allow, float* d_dist,
                        int64_t* d_lab, cudaStream_t st) {
     if (nq == 0) return LB_OK;
@@ -430,7 +462,8 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         a.allow = (const uint32_t*)d_allow;
         a.kc = kc;
         const int mode = g_opt_dense_scan.load(std::memory_order_relaxed);
-        const bool tc_ok = dense_tc_eligible(idx->dtype, idx->dim, idx->rows, a.queries, kc);
+        const bool tc_ok = dense_tc_eligible(idx->dtype, idx->dim, idx->rows, a.queries, kc) &&
+                           (idx->dtype != DT_F32 || g_opt_f32_tc.load(std::memory_order_relaxed));
         if (mode == 2 && !tc_ok) return fail(LB_ERR_UNSUPPORTED, "tensor-core scan not eligible for this index");
         const bool stream_ok = dense_stream_eligible(idx->dtype, idx->dim, idx->rows, cq, kc);
         if (mode == 3 && !stream_ok) return fail(LB_ERR_UNSUPPORTED, "streaming scan not eligible for this search");
@@ -486,6 +519,14 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
             CK(launch_merge_select_compact(head, compact, out_cnt, stride, cq, kc, merged, a.edges, a.edge_cnt, st));
             merged_done = true;
         } else if (use_tc) {
+            if (idx->dtype == DT_F32) {
+                int rc = ensure_lo(idx, st);
+                if (rc) return rc;
+                float* qlo;
+                CK(scr.get((void**)&qlo, (size_t)cq * idx->dim * 4));
+                CK(launch_split_lo((const float*)a.queries, qlo, (size_t)cq * idx->dim, st));
+                a.db_lo = idx->lo; a.queries_lo = qlo;
+            }
             const int n_tiles = (int)((idx->size + 255) / 256);
             a.tq = 128; a.cap = 0; a.rows_per_part = 0;
             a.debug = g_opt_tc_debug.load(std::memory_order_relaxed);
@@ -683,6 +724,52 @@ int lb_index_distances(lb_index* idx, const void* query, float* out) {
     CK(cudaMemcpyAsync(d_q, query, qb, cudaMemcpyHostToDevice, st));
     CK(launch_batch_flat(idx->metric, idx->dtype, idx->rows, idx->size, idx->dim, d_q, d_o, 1, st));
     CK(cudaMemcpyAsync(out, d_o, (size_t)idx->size * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
+// Diagnostics: the COARSE ranking keys the tensor-core scan computes for rows [0, n_rows) -- |x|^2 - 2 q.x (L2),
+// -q.x / |x| (cosine), -q.x (dot) -- so tests can bound the coarse error against float64 (these keys only
+// rank candidates; every returned distance comes from the exact re-score).
+int lb_index_coarse_keys(lb_index* idx, const void* queries, int64_t nq, int64_t n_rows, float* out) {
+    if (!idx || !queries || !out) return fail(LB_ERR_INVALID, "NULL argument");
+    if (nq <= 0 || n_rows <= 0 || n_rows > idx->size) return fail(LB_ERR_INVALID, "bad size");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    const size_t qb = (size_t)nq * idx->dim * dtype_size(idx->dtype);
+    void* d_q;
+    CK(scr.get(&d_q, qb));
+    CK(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, st));
+    if (!dense_tc_eligible(idx->dtype, idx->dim, idx->rows, d_q, 32))
+        return fail(LB_ERR_UNSUPPORTED, "tensor-core scan not eligible for this index");
+    const int tiles = (int)((n_rows + 255) / 256);
+    const int S = tiles * 256;
+    ScanArgs a;
+    a.dtype = idx->dtype; a.metric = idx->metric; a.db = idx->rows; a.aux = idx->aux;
+    a.n_rows = (uint32_t)idx->size; a.dim = idx->dim; a.queries = d_q; a.nq = (int)nq;
+    a.tomb = nullptr; a.tomb_bits = 0; a.allow = nullptr; a.kc = 32; a.cap = 0; a.tq = 128; a.rows_per_part = 0;
+    if (idx->dtype == DT_F32) {
+        rc = ensure_lo(idx, st);
+        if (rc) return rc;
+        float* qlo;
+        CK(scr.get((void**)&qlo, (size_t)nq * idx->dim * 4));
+        CK(launch_split_lo((const float*)d_q, qlo, (size_t)nq * idx->dim, st));
+        a.db_lo = idx->lo; a.queries_lo = qlo;
+    }
+    float* keys;
+    uint64_t* cand;
+    size_t cand_bytes;
+    int gm;
+    dense_scan_tc_plan((int)nq, tiles, idx->sm_count, a.kc, &gm, &cand_bytes);
+    CK(scr.get((void**)&cand, cand_bytes));
+    CK(scr.get((void**)&keys, (size_t)nq * S * 4));
+    a.parts = 0; a.partial = nullptr; a.tile_begin = 0; a.tile_end = tiles; a.part_offset = 0;
+    a.keys_out = keys; a.keys_ld = S;
+    CK(launch_dense_scan_tc(a, idx->sm_count, cand, st));
+    CK(cudaMemcpy2DAsync(out, (size_t)n_rows * 4, keys, (size_t)S * 4, (size_t)n_rows * 4, (size_t)nq,
+                         cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return LB_OK;
 }

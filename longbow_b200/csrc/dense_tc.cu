@@ -343,12 +343,20 @@ __device__ __forceinline__ float select_compact(const uint64_t* buf, uint64_t* d
 // land in each CTA's own TMEM, so the epilogue is identical.
 template <int KIND, int METRIC, int CAP, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const TcArgs a) {
+dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
+              const __grid_constant__ CUtensorMap map_qlo, const __grid_constant__ CUtensorMap map_dblo, const TcArgs a) {
     using TR = TcTraits<KIND>;
-    constexpr int STAGES = (CG == 2) ? TC_STAGES_PAIR : TC_STAGES;
+    // fp32 rows: "3xTF32".  kind::tf32 reads fp32 words and uses their top 19 bits; every operand is therefore
+    // staged twice -- hi = x with the low 13 mantissa bits cleared, lo = x - hi (exact) -- and each k-step issues
+    // hi*hi + hi*lo + lo*hi, which leaves an error of ~2^-21 relative: the same class as the fp16 path, so the
+    // same candidate margin applies.
+    constexpr bool X3 = (KIND == KIND_TF32);
+    constexpr int PARTS = X3 ? 2 : 1;
     constexpr int B_ROWS = TC_N / CG;                 // database rows of a tile this CTA stages
     constexpr int B_BYTES = B_ROWS * 128;
-    constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    constexpr int STAGE_BYTES = PARTS * (TC_A_BYTES + B_BYTES);
+    constexpr int STAGES = (TC_STAGES * TC_STAGE_BYTES) / STAGE_BYTES;   // 4 / 6 (pair); fp32: 2 / 3
+    constexpr int B_OFF = PARTS * TC_A_BYTES;         // stage layout: A_hi [A_lo] B_hi [B_lo]
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -405,13 +413,22 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                         const uint32_t fb = map_to_cta(full_bar(stage), 0);
                         if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
                         tma_load_2d_pair(sa, &map_q, fb, kb * TR::kBlockK, qb * TC_M);
-                        tma_load_2d_pair(sa + TC_A_BYTES, &map_db, fb, kb * TR::kBlockK, rt * TC_N + (int)rank * B_ROWS);
+                        tma_load_2d_pair(sa + B_OFF, &map_db, fb, kb * TR::kBlockK, rt * TC_N + (int)rank * B_ROWS);
+                        if constexpr (X3) {
+                            tma_load_2d_pair(sa + TC_A_BYTES, &map_qlo, fb, kb * TR::kBlockK, qb * TC_M);
+                            tma_load_2d_pair(sa + B_OFF + B_BYTES, &map_dblo, fb, kb * TR::kBlockK,
+                                             rt * TC_N + (int)rank * B_ROWS);
+                        }
                     } else {
                         const bool first = ((rt - a.tile_begin - g) / a.groups) * a.k_blocks + kb < STAGES;
                         const bool ld_a = !(a.debug & 4) || first, ld_b = !(a.debug & 2) || first;
-                        mbar_arrive_expect_tx(full_bar(stage), (ld_a ? TC_A_BYTES : 0) + (ld_b ? B_BYTES : 0));
+                        mbar_arrive_expect_tx(full_bar(stage), PARTS * ((ld_a ? TC_A_BYTES : 0) + (ld_b ? B_BYTES : 0)));
                         if (ld_a) tma_load_2d(sa, &map_q, full_bar(stage), kb * TR::kBlockK, qb * TC_M);
-                        if (ld_b) tma_load_2d(sa + TC_A_BYTES, &map_db, full_bar(stage), kb * TR::kBlockK, rt * TC_N);
+                        if (ld_b) tma_load_2d(sa + B_OFF, &map_db, full_bar(stage), kb * TR::kBlockK, rt * TC_N);
+                        if constexpr (X3) {
+                            if (ld_a) tma_load_2d(sa + TC_A_BYTES, &map_qlo, full_bar(stage), kb * TR::kBlockK, qb * TC_M);
+                            if (ld_b) tma_load_2d(sa + B_OFF + B_BYTES, &map_dblo, full_bar(stage), kb * TR::kBlockK, rt * TC_N);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -431,11 +448,21 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * STAGE_BYTES;
-                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + TC_A_BYTES);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + B_OFF);
+                    auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
+                        if constexpr (CG == 2) tc_mma_pair<KIND>(d_tmem, ad, bd, idesc, acc);
+                        else tc_mma<KIND>(d_tmem, ad, bd, idesc, acc);
+                    };
 #pragma unroll
                     for (int k = 0; k < 4; k++) {  // 4 x (UMMA_K * elem = 32 B) per 128-byte swizzle row
-                        if constexpr (CG == 2) tc_mma_pair<KIND>(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-                        else tc_mma<KIND>(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+                        if constexpr (X3) {
+                            const uint64_t dal = make_smem_desc(sa + TC_A_BYTES), dbl = make_smem_desc(sa + B_OFF + B_BYTES);
+                            mma(da + 2u * k, dbl + 2u * k, (kb | k) != 0);   // hi * lo   (small terms first)
+                            mma(dal + 2u * k, db + 2u * k, 1u);              // lo * hi
+                            mma(da + 2u * k, db + 2u * k, 1u);               // hi * hi
+                        } else {
+                            mma(da + 2u * k, db + 2u * k, (kb | k) != 0);
+                        }
                     }
                     // frees the smem slot (in both CTAs of a pair) when these MMAs retire
                     if constexpr (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
@@ -871,6 +898,28 @@ cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_ro
     return cudaGetLastError();
 }
 
+// fp32 operand split for the 3xTF32 scan: hi = x with the 13 low mantissa bits cleared (what kind::tf32 reads),
+// lo = x - hi (exact in fp32).  In place for hi is not wanted (rows stay the reference's bytes): only lo is stored,
+// the tensor core sees hi by ignoring the low bits of the original words.
+__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const float v = x[i];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        lo[i] = v - hi;
+    }
+}
+
+cudaError_t launch_split_lo(const float* x, float* lo, size_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_lo_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, lo, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -907,7 +956,6 @@ static bool make_map(CUtensorMap* m, int kind, const void* ptr, uint64_t rows, i
 bool dense_tc_eligible(int dtype, int dim, const void* db, const void* queries, int kc) {
     const int elem = dtype == DT_F16 ? 2 : dtype == DT_I8 ? 1 : dtype == DT_F32 ? 4 : 0;
     if (elem == 0) return false;
-    if (dtype == DT_F32) return false;  // fp32 stays on the SIMT scan this round (TF32 needs wider margins)
     if (((size_t)dim * elem) % 16 != 0) return false;                    // TMA row pitch
     if ((reinterpret_cast<uintptr_t>(db) | reinterpret_cast<uintptr_t>(queries)) & 15) return false;
     if (kc + TC_N > 1024) return false;
@@ -935,9 +983,15 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     const int kb_ = (s.dim + block_k - 1) / block_k;
     // (short rows are epilogue-bound: a pair only adds cross-CTA hand-shakes there -- measured slower at 128-byte rows)
     const int cg = (g_tc_pair && (nqb_ % 2 == 0) && kb_ >= 4 && !(s.debug & 6)) ? 2 : 1;
-    CUtensorMap mq, mdb;
+    CUtensorMap mq, mdb, mqlo, mdblo;
     if (!make_map(&mq, kind, s.queries, (uint64_t)s.nq, s.dim, TC_M)) return cudaErrorInvalidValue;
     if (!make_map(&mdb, kind, s.db, (uint64_t)s.n_rows, s.dim, TC_N / cg)) return cudaErrorInvalidValue;
+    mqlo = mq; mdblo = mdb;
+    if (kind == KIND_TF32) {  // 3xTF32: the low parts of both operands
+        if (s.db_lo == nullptr || s.queries_lo == nullptr) return cudaErrorInvalidValue;
+        if (!make_map(&mqlo, kind, s.queries_lo, (uint64_t)s.nq, s.dim, TC_M)) return cudaErrorInvalidValue;
+        if (!make_map(&mdblo, kind, s.db_lo, (uint64_t)s.n_rows, s.dim, TC_N / cg)) return cudaErrorInvalidValue;
+    }
     TcArgs a;
     a.aux = s.aux; a.n_rows = s.n_rows; a.nq = s.nq;
     a.k_blocks = (s.dim + block_k - 1) / block_k;
@@ -958,9 +1012,9 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     a.kc = s.kc; a.cap = next_pow2(s.kc + TC_N);
     if (a.cap < 512) a.cap = 512;
     a.cand = cand; a.partial = s.partial; a.debug = s.debug;
-    const size_t stage_bytes = cg == 2 ? (size_t)TC_STAGES_PAIR * (TC_A_BYTES + TC_B_BYTES / 2) : (size_t)TC_STAGES * TC_STAGE_BYTES;
-    const int n_stages = cg == 2 ? TC_STAGES_PAIR : TC_STAGES;
-    const size_t smem = 1024 + stage_bytes + 2 * 2 * (TC_N / 2) * 4 + 8 * (2 * n_stages + 4) + 16;
+    // the ring always occupies TC_STAGES * TC_STAGE_BYTES (192 KiB) whatever the stage size; its barrier block is
+    // sized for the deepest ring (6 stages)
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 2 * 2 * (TC_N / 2) * 4 + 8 * (2 * TC_STAGES_PAIR + 4) + 16;
     const dim3 grid(nqb * groups);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -979,7 +1033,7 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
         auto kern = dense_scan_tc<KIND_, METRIC_, CAP_, CG_>;                                                  \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
         if (e != cudaSuccess) return e;                                                                        \
-        e = cudaLaunchKernelEx(&cfg, kern, mq, mdb, a);                                                        \
+        e = cudaLaunchKernelEx(&cfg, kern, mq, mdb, mqlo, mdblo, a);                                                        \
         if (e != cudaSuccess) return e;                                                                        \
     }
 #define LB_TC1(KIND_, METRIC_, CAP_)                                                                           \
@@ -995,7 +1049,7 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     } else if (kind == KIND_I8) {
         if (s.metric == METRIC_L2) LB_TC(KIND_I8, METRIC_L2) else LB_TC(KIND_I8, METRIC_DOT)
     } else {
-        return cudaErrorInvalidValue;
+        if (s.metric == METRIC_L2) LB_TC(KIND_TF32, METRIC_L2) else if (s.metric == METRIC_COSINE) LB_TC(KIND_TF32, METRIC_COSINE) else LB_TC(KIND_TF32, METRIC_DOT)
     }
 #undef LB_TC
 #undef LB_TC1

@@ -35,6 +35,8 @@ struct ScanArgs {
     int keys_ld = 0;
     // shared progressive threshold (tensor-core scan): per query a ladder of LB_NEDGE keys taken from the
     // bootstrap sample and the number of live rows seen so far at or below each
+    const void* db_lo = nullptr;       // fp32 tensor-core scan (3xTF32): x - tf32(x) of the rows / queries
+    const void* queries_lo = nullptr;
     const float* edges = nullptr;  // [nq][LB_NEDGE] ascending, already nextafter()'d
     uint32_t* edge_cnt = nullptr;  // [nq][LB_NEDGE]
 };
@@ -91,6 +93,7 @@ cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_ro
                                  uint32_t tomb_bits, const uint32_t* allow, int nq, int kc, uint64_t* out,
                                  float* tau, float* edges, uint32_t* edge_cnt, int* done, cudaStream_t st);
 cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand, cudaStream_t st);
+cudaError_t launch_split_lo(const float* x, float* lo, size_t n, cudaStream_t st);
 
 // ---- streaming scan for small query batches (dense_stream.cu)
 bool dense_stream_eligible(int dtype, int dim, const void* db, int nq, int kc);

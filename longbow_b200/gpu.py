@@ -247,6 +247,13 @@ class DenseIndex:
                                                None if allow is None else allow.data_ptr(), out_d.data_ptr(),
                                                out_l.data_ptr(), _stream_ptr(stream)))
 
+    def coarse_keys(self, queries: np.ndarray, n_rows: int) -> np.ndarray:
+        """Diagnostics: the tensor-core scan's coarse ranking keys for rows [0, n_rows) (tests only)."""
+        q = np.ascontiguousarray(queries, dtype=self.np_dtype).reshape(-1, self.dim)
+        out = np.empty((q.shape[0], n_rows), np.float32)
+        check(self._lib.lb_index_coarse_keys(self._h, _ptr(q), q.shape[0], int(n_rows), _ptr(out)))
+        return out
+
     def last_uncertified(self) -> int:
         return int(self._lib.lb_index_last_uncertified(self._h))
 

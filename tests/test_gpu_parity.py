@@ -339,7 +339,8 @@ def scan_mode():
     _lib.set_option("dense_scan", 0)
 
 
-@pytest.mark.parametrize("dtype,metric", [(np.float16, COS), (np.float16, L2), (np.float16, DOT), (np.int8, DOT), (np.int8, L2)])
+@pytest.mark.parametrize("dtype,metric", [(np.float16, COS), (np.float16, L2), (np.float16, DOT), (np.int8, DOT), (np.int8, L2),
+                                          (np.float32, L2), (np.float32, COS), (np.float32, DOT)])
 @pytest.mark.parametrize("n,dim,nq,k", [(70001, 768, 300, 100), (40000, 64, 129, 10), (9000, 208, 40, 32), (300, 128, 5, 10), (20000, 128, 40, 300)])
 def test_tensor_core_scan_parity(lbgpu, oracle, scan_mode, dtype, metric, n, dim, nq, k):
     rng = np.random.default_rng(2000 + n + metric)
@@ -450,4 +451,39 @@ def test_streaming_scan_adversarial_order(lbgpu, oracle, scan_mode):
         wd, wl = oracle.search(L2, db, q, 50)
         assert_topk_equal(gd, gl, wd, wl, 0.0, f"adversarial boot={boot}")
     _lib.set_option("tc_boot", 1)
+    idx.close()
+
+
+# ------------------------------------------------------------------ coarse-key accuracy of the tensor-core scan
+@pytest.mark.parametrize("dtype,metric,bound", [
+    # 3xTF32: operand error ~2^-21; what remains (~4e-6 on the all-positive test data) is the tensor core's
+    # truncating fp32 accumulation over 3 * dim/8 steps.  Plain TF32 would sit at 1e-4 .. 1e-3.
+    (np.float32, L2, 1.2e-5), (np.float32, COS, 1.2e-5), (np.float32, DOT, 1.2e-5),
+    (np.float16, COS, 4e-6), (np.float16, L2, 4e-6), (np.int8, DOT, 1e-12), (np.int8, L2, 1e-12)])  # int8: exact
+def test_coarse_keys_accuracy(lbgpu, dtype, metric, bound):
+    """The coarse keys only rank candidates, but the candidate margin (kc - k) assumes they are accurate to a
+    few fp32 ulps of |q||x|.  For fp32 rows this pins the 3xTF32 split: a plain TF32 product (or a hardware
+    conversion that rounds instead of truncating the hi part) would miss the bound by two orders of magnitude."""
+    rng = np.random.default_rng(5)
+    n, dim, nq = 2048, 256, 16
+    db, q = make_db(rng, n, dim, dtype), make_db(rng, nq, dim, dtype)
+    idx = lbgpu.DenseIndex(dim, dtype, metric)
+    idx.add(db)
+    keys = idx.coarse_keys(q, n).astype(np.float64)
+    d64, q64 = db.astype(np.float64), q.astype(np.float64)
+    dots = q64 @ d64.T
+    xn = np.linalg.norm(d64, axis=1)
+    if metric == L2:
+        want = (xn ** 2)[None, :] - 2.0 * dots
+    elif metric == COS:
+        want = -dots / np.maximum(xn, 1e-300)[None, :]
+    else:
+        want = -dots
+    scale = np.linalg.norm(q64, axis=1)[:, None] * np.maximum(xn, 1e-30)[None, :]
+    if metric == COS:
+        scale = np.linalg.norm(q64, axis=1)[:, None] * np.ones_like(xn)[None, :]
+    if metric == L2:
+        scale = scale + (xn ** 2)[None, :]
+    err = np.abs(keys - want) / scale
+    assert err.max() <= bound, f"coarse key error {err.max():.3e} of |q||x| (bound {bound})"
     idx.close()
