@@ -96,7 +96,7 @@ def c2():
         odn = torch.empty((nq, K), dtype=torch.float32, device=dev)
         oln = torch.empty((nq, K), dtype=torch.int64, device=dev)
         ms, sm = timed(lambda: idx.search_device(qn, K, odn, oln))
-        report(f"C2 database, {nq} quer{'y' if nq == 1 else 'ies'} per call (HBM-bound streaming scan)", ms, sm, nq,
+        report(f"C2 database, {nq} quer{'y' if nq == 1 else 'ies'} per call (HBM-bound: streaming scan at 1 query, one padded tensor-core query block above)", ms, sm, nq,
                N * D * 2, None)
     idx.close()
 
@@ -159,7 +159,7 @@ def c4():
         odn = torch.empty((nq, K), dtype=torch.float32, device=dev)
         oln = torch.empty((nq, K), dtype=torch.int64, device=dev)
         ms, sm = timed(lambda: idx.search_device(qn, K, odn, oln))
-        report(f"C4 shard, {nq} queries per call (streaming scan)", ms, sm, nq, N * D, None)
+        report(f"C4 shard, {nq} queries per call (one padded tensor-core query block)", ms, sm, nq, N * D, None)
     idx.close()
 
 
