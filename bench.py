@@ -13,6 +13,10 @@ Prints ONE JSON line (rank 0).
 import argparse
 import json
 import os
+
+# NCCL prints its version banner (and anything NCCL_DEBUG asks for) on stdout: send it to stderr instead, rank 0
+# prints ONE JSON line on stdout
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import statistics
 import sys
 import threading
@@ -186,7 +190,8 @@ def main():
     # ---- device-resident arm ("value")
     log("index resident")
     for s in range(warm):
-        sidx.search_device(d_qs[s], K, out_d, out_l)
+        sidx.search_device(d_qs[s], K, out_d, out_l, overlap=True)
+    sidx.wait()
     barrier()
     log("warm-up done")
     sampler = ClockSampler(local)
@@ -197,7 +202,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(steps):
-        sidx.search_device(d_qs[warm + s], K, out_d, out_l)
+        # N > 1: the NCCL exchange of batch s overlaps the scan of batch s + 1 (side stream)
+        sidx.search_device(d_qs[warm + s], K, out_d, out_l, overlap=True)
+    sidx.wait()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -208,7 +215,8 @@ def main():
     if sampler.summary()["samples"] < 5:  # timed region too short for NVML: keep sampling the same load
         t_end = time.time() + 1.0
         while time.time() < t_end:
-            sidx.search_device(d_qs[warm + steps - 1], K, out_d, out_l)
+            sidx.search_device(d_qs[warm + steps - 1], K, out_d, out_l, overlap=True)
+            sidx.wait()
             torch.cuda.synchronize()
     sampler.stop_flag = True
     sampler.join(timeout=5)
@@ -272,7 +280,7 @@ def main():
 
         def step(s):
             dq.copy_(hq[s], non_blocking=True)
-            sidx.search_device(dq, K, out_d, out_l)
+            sidx.search_device(dq, K, out_d, out_l)  # ordered: this step's result is read back below
             if rank == 0:
                 hd.copy_(out_d, non_blocking=True)
                 hl.copy_(out_l, non_blocking=True)

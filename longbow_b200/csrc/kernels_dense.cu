@@ -389,22 +389,29 @@ merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int
     __syncthreads();
     const uint32_t thr = s_thr;
     int have = 0;  // s_buf[0, have) = best so far (sorted) after a flush
-    for (int base = 0; base < total; base += MSEL_T) {
-        const int i = base + tid;
-        uint64_t x = kInvalid;
-        if (i < total) {
-            if (compact == nullptr) x = partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)];
-            else x = (i < head) ? partial[(size_t)q * kc + i] : compact[(size_t)q * stride + (i - head)];
-        }
-        const bool keep = (x != kInvalid) && ((uint32_t)(x >> 32) < thr);
-        if (keep) {
-            const int pos = have + atomicAdd(&s_n, 1);  // < MSEL_CAP: flushed before MSEL_T more could overflow
-            s_buf[pos] = x;
-        }
-        __syncthreads();
-        if (have + s_n > MSEL_CAP - MSEL_T) {  // block-uniform: sort, keep the best kc, continue
-            const int n = have + s_n;
-            const int n2 = next_pow2(n);
+    auto fetch = [&](int i) -> uint64_t {
+        if (i >= total) return kInvalid;
+        uint64_t x;
+        if (compact == nullptr) x = partial[((size_t)(i / kc) * nq + q) * kc + (i % kc)];
+        else x = (i < head) ? partial[(size_t)q * kc + i] : compact[(size_t)q * stride + (i - head)];
+        return ((x != kInvalid) && ((uint32_t)(x >> 32) < thr)) ? x : kInvalid;
+    };
+    // Slots are fetched 8 per thread with all loads in flight (one memory round trip per 2048 slots, not
+    // per 256); the buffer is flushed (sorted, best kc kept) before a batch that could overflow it.
+    constexpr int BATCH = 8;
+    for (int base = 0; base < total; base += MSEL_T * BATCH) {
+        uint64_t x[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) x[b] = fetch(base + b * MSEL_T + tid);
+        int mine = 0;
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) mine += (x[b] != kInvalid);
+        // worst case every slot of the batch survives: flush first if that could overflow
+        const int filled = have + s_n;
+        __syncthreads();  // everyone has read s_n before anyone appends to it again
+        if (filled > MSEL_CAP - MSEL_T * BATCH) {  // block-uniform
+            const int n = filled;
+            const int n2 = next_pow2(max(n, 2));
             for (int t = n + tid; t < n2; t += MSEL_T) s_buf[t] = kInvalid;
             __syncthreads();
             block_bitonic_sort(s_buf, n2);
@@ -412,6 +419,13 @@ merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int
             if (tid == 0) s_n = 0;
             __syncthreads();
         }
+        if (mine) {
+            int pos = have + atomicAdd(&s_n, mine);
+#pragma unroll
+            for (int b = 0; b < BATCH; b++)
+                if (x[b] != kInvalid) s_buf[pos++] = x[b];
+        }
+        __syncthreads();
     }
     const int n = have + s_n;
     const int n2 = next_pow2(max(n, 2));
@@ -425,7 +439,7 @@ merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int
 cudaError_t launch_merge_select(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged, uint64_t* kth,
                                 const float* edges, const uint32_t* edge_cnt, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    if (kc > MSEL_CAP - 2 * MSEL_T) return cudaErrorInvalidValue;
+    if (kc > MSEL_CAP - 8 * MSEL_T) return cudaErrorInvalidValue;
     merge_select_kernel<<<nq, MSEL_T, 0, st>>>(partial, parts, nq, kc, merged, kth, edges, edge_cnt, nullptr, nullptr, 0);
     count_launch();
     return cudaGetLastError();
@@ -435,7 +449,7 @@ cudaError_t launch_merge_select_compact(const uint64_t* head, const uint64_t* co
                                         size_t stride, int nq, int kc, uint64_t* merged, const float* edges,
                                         const uint32_t* edge_cnt, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    if (kc > MSEL_CAP - 2 * MSEL_T) return cudaErrorInvalidValue;
+    if (kc > MSEL_CAP - 8 * MSEL_T) return cudaErrorInvalidValue;
     merge_select_kernel<<<nq, MSEL_T, 0, st>>>(head, head ? 1 : 0, nq, kc, merged, nullptr, edges, edge_cnt, compact,
                                                counts, stride);
     count_launch();
