@@ -603,20 +603,46 @@ rescore_coop_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T*
     const int n_chunks = (int)((row_bytes + RC_CHUNK - 1) / RC_CHUNK);
     unsigned char* stage = stage_all + (size_t)warp * RC_NBUF * 32 * RC_PITCH;
 
-    for (int base = warp * 32; base < c; base += RC_WARPS * 32) {
-        // candidate of this lane
-        const int ci = base + lane;
-        uint32_t id = 0xffffffffu;
-        bool ok = false;
-        if (ci < c) {
-            if (packed != nullptr) {
-                const uint64_t p = packed[(size_t)q * c + ci];
-                if (p != kInvalid) { id = id_of(p); ok = id < n_rows; }
-            } else {
+    // Re-rank mode: drop out-of-range / tombstoned / filtered ids FIRST and compact the survivors, so every
+    // warp gathers 32 live rows per trip (with a 30% predicate and 5% tombstones three lanes in four would
+    // otherwise idle through the whole gather).  Order does not matter: the result is sorted by (distance, id).
+    uint32_t* live = reinterpret_cast<uint32_t*>(stage_all + (size_t)RC_WARPS * RC_NBUF * 32 * RC_PITCH);  // [n2]
+    __shared__ int s_live;
+    int n_cand = c;
+    if (packed == nullptr) {
+        if (tid == 0) s_live = 0;
+        __syncthreads();
+        for (int ci = tid; ci < ((c + 31) & ~31); ci += blockDim.x) {
+            uint32_t id = 0xffffffffu;
+            bool ok = false;
+            if (ci < c) {
                 id = ids32[(size_t)q * c + ci];
                 ok = id < n_rows;
                 if (ok && allow != nullptr && !bit_set(allow, id)) ok = false;
                 if (ok && tomb != nullptr && id < tomb_bits && bit_set(tomb, id)) ok = false;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            int b = 0;
+            if (lane == 0 && m) b = atomicAdd(&s_live, __popc(m));
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (ok) live[b + __popc(m & ((1u << lane) - 1u))] = id;
+        }
+        __syncthreads();
+        n_cand = s_live;
+    }
+
+    for (int base = warp * 32; base < n_cand; base += RC_WARPS * 32) {
+        // candidate of this lane
+        const int ci = base + lane;
+        uint32_t id = 0xffffffffu;
+        bool ok = false;
+        if (ci < n_cand) {
+            if (packed != nullptr) {
+                const uint64_t p = packed[(size_t)q * c + ci];
+                if (p != kInvalid) { id = id_of(p); ok = id < n_rows; }
+            } else {
+                id = live[ci];
+                ok = true;
             }
         }
         // rows this lane copies: copy instruction i moves piece (lane % 8) of row 4i + lane / 8
@@ -698,7 +724,8 @@ static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
     const bool coop = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.db) & 15) == 0) &&
                       !(a.metric == METRIC_COSINE && a.nrm == nullptr) && !g_rescore_legacy;
     if (coop) {
-        const size_t smem = (size_t)n2 * 8 + (size_t)((a.dim + 3) & ~3) * 4 + (size_t)RC_WARPS * RC_NBUF * 32 * RC_PITCH;
+        const size_t smem = (size_t)n2 * 8 + (size_t)((a.dim + 3) & ~3) * 4 + (size_t)RC_WARPS * RC_NBUF * 32 * RC_PITCH +
+                            (size_t)n2 * 4;
 #define LB_RC(M)                                                                                            \
     {                                                                                                       \
         auto kern = rescore_coop_kernel<T, M>;                                                              \
