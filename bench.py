@@ -14,9 +14,17 @@ import argparse
 import json
 import os
 
-# NCCL prints its version banner (and anything NCCL_DEBUG asks for) on stdout: send it to stderr instead, rank 0
-# prints ONE JSON line on stdout
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# Libraries (NCCL's version banner, torch warnings) write to stdout; the contract is ONE JSON line there.  File
+# descriptor 1 is pointed at stderr for the whole run and restored just before the result is printed.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+    os.dup2(2, 1)
 import statistics
 import sys
 import threading
@@ -123,7 +131,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     qps = nq * args.steps / dt
     sample = f"{nq} queries/step x full {N_ROWS} x {DIM} fp16 DB, k={K}, {oracle.fast_isa()} + OpenMP"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -131,7 +139,7 @@ def run_reference(args):
                    "note": "CPU restatement of the reference's SIMD path (Go toolchain absent); each step is a bounded sample"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -191,19 +199,19 @@ def main():
     # tail kernels of batch s (selection, merge, exact re-score, NCCL exchange) overlap the scan of batch s + 1;
     # every batch is still one complete search (scan + top-k + re-score [+ all-gather + merge]).
     log("index resident")
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    # (N > 1 keeps ONE stream with the NCCL exchange in order on it: the configuration verified on 8 GPUs.)
+    n_streams = 2 if world == 1 else 1
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
     outs = [(out_d, out_l), (torch.empty_like(out_d), torch.empty_like(out_l))]
 
     def run_steps(first, count):
         for s in range(first, first + count):
-            with torch.cuda.stream(streams[s % 2]):
-                sidx.search_device(d_qs[s], K, outs[s % 2][0], outs[s % 2][1], overlap=True)
+            with torch.cuda.stream(streams[s % n_streams]):
+                sidx.search_device(d_qs[s], K, outs[s % 2][0], outs[s % 2][1])
 
     def join_streams():
         cur = torch.cuda.current_stream()
         for st_ in streams:
-            with torch.cuda.stream(st_):
-                sidx.wait()
             cur.wait_stream(st_)
 
     run_steps(0, warm)
@@ -388,12 +396,13 @@ def main():
                        "rows": n_rows, "dim": DIM, "queries_per_step": NQ, "k": K,
                        "sharding": f"rows/{world} per GPU + NCCL all-gather top-k merge" if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2 (1.5 GB DB streamed per step; fresh query batch each step)",
-                       "streams": "batches alternate between 2 CUDA streams (tail kernels overlap the next scan)"},
+                       "streams": ("batches alternate between 2 CUDA streams (tail kernels overlap the next scan)"
+                                   if world == 1 else "one stream per rank, NCCL exchange in order")},
             "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof,
         }
         if not args.no_cpu and world == 1:
             out["cpu_baseline"] = cpu_baseline(db.numpy(), qs[0].numpy(), K)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
