@@ -119,7 +119,11 @@ int lb_index_rerank_device(lb_index *idx, const void *d_queries, int64_t nq, con
  * (simd.EuclideanDistanceBatchFlat with the flat buffer already in HBM). */
 int lb_index_distances(lb_index *idx, const void *query, float *out);
 
-/* Reserved (always 0 in this version). */
+/* Number of queries of the last lb_index_search (host) call on this handle whose coarse-stage result could not
+ * be CERTIFIED -- the margin between the kc-th coarse key and the k-th exact distance did not cover the coarse
+ * error bound, so a row outside the candidate set might have belonged to the top-k -- and which were therefore
+ * recomputed by an exhaustive exact scan before returning (DESIGN.md 4.1 "certification").  The *_device entry
+ * points do not certify. */
 int64_t lb_index_last_uncertified(const lb_index *idx);
 /* Diagnostics: the COARSE ranking keys the tensor-core scan computes for rows [0, n_rows) of nq queries
  * (out: [nq][n_rows]): |x|^2 - 2 q.x (L2), -q.x/|x| (cosine), -q.x (dot).  They only rank candidates -- every

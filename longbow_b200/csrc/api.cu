@@ -92,6 +92,7 @@ static std::atomic<int> g_opt_dense_scan{0};
 static std::atomic<int> g_opt_tc_debug{0};
 static std::atomic<int> g_opt_tc_boot_tiles{0};  // 0 = auto
 static std::atomic<int> g_opt_f32_tc{1};         // fp32 indexes: 3xTF32 tensor-core scan (0: SIMT scan)
+static std::atomic<int> g_opt_certify{1};        // host searches: certify the coarse stage, redo flagged queries exactly
 static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off (A/B timing)    // timing probes of the tensor-core scan (results invalid when != 0)  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
 
 // ---- dominant-kernel timing (lb_prof_*)
@@ -129,6 +130,7 @@ struct lb_index {
     void* rows = nullptr;  // [capacity][dim]
     float* aux = nullptr;  // [capacity + 256] coarse-key auxiliaries
     float* nrm = nullptr;  // [capacity] cosine only: exact |x|^2 in reference lane order
+    float* max_norm2 = nullptr;  // device scalar: max |x|^2 over the rows (certification bound), float dtypes only
     float* lo = nullptr;   // fp32 only, built on first tensor-core search: x - tf32(x) for the 3xTF32 scan
     int64_t lo_rows = 0, lo_cap = 0;
     std::mutex lo_mu;
@@ -219,6 +221,10 @@ int lb_set_option(const char* name, int value) {
         g_opt_tc_boot_tiles.store(value < 0 ? 0 : value);
         return LB_OK;
     }
+    if (strcmp(name, "certify") == 0) {
+        g_opt_certify.store(value ? 1 : 0);
+        return LB_OK;
+    }
     if (strcmp(name, "f32_tc") == 0) {
         g_opt_f32_tc.store(value ? 1 : 0);
         return LB_OK;
@@ -289,6 +295,11 @@ int lb_index_create(int device, int dim, int dtype, int metric, lb_index** out) 
     if (!idx) return fail(LB_ERR_OOM, "host allocation failed");
     idx->device = device; idx->dim = dim; idx->dtype = dtype; idx->metric = metric;
     idx->sm_count = g_dev[device].sm_count;
+    if (dtype != DT_I8) {
+        cudaError_t e = cudaMalloc((void**)&idx->max_norm2, 4);
+        if (e == cudaSuccess) e = cudaMemset(idx->max_norm2, 0, 4);
+        if (e != cudaSuccess) { if (idx->max_norm2) cudaFree(idx->max_norm2); delete idx; return fail_cuda(e, "cudaMalloc(stats)"); }
+    }
     *out = idx;
     return LB_OK;
 }
@@ -301,6 +312,7 @@ void lb_index_free(lb_index* idx) {
         if (idx->aux) cudaFree(idx->aux);
         if (idx->nrm) cudaFree(idx->nrm);
         if (idx->lo) cudaFree(idx->lo);
+        if (idx->max_norm2) cudaFree(idx->max_norm2);
         if (idx->tomb) cudaFree(idx->tomb);
     }
     cudaGetLastError();
@@ -358,6 +370,7 @@ static int index_add_common(lb_index* idx, const void* src, int64_t n, bool src_
         CK(launch_row_aux(idx->dtype, idx->rows, idx->size, idx->dim, idx->metric, idx->aux, row0, st));
     if (idx->metric == METRIC_COSINE)
         CK(launch_row_norm_exact(idx->dtype, idx->rows, idx->size, idx->dim, idx->nrm, row0, st));
+    if (idx->max_norm2) CK(launch_row_maxnorm(idx->dtype, idx->rows, idx->size, idx->dim, row0, idx->max_norm2, st));
     if (!src_on_device) CK(cudaStreamSynchronize(st));  // cgo: the Go slice may move after return
     return LB_OK;
 }
@@ -437,8 +450,10 @@ static int ensure_lo(lb_index* idx, cudaStream_t st) {
     return LB_OK;
 }
 
+// d_cert_flags [nq] / d_cert_count [1] (optional, device): certification of the coarse stage, see RescoreArgs
 static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const uint64_t* d_allow, float* d_dist,
-                       int64_t* d_lab, cudaStream_t st) {
+                       int64_t* d_lab, cudaStream_t st, uint32_t* d_cert_flags = nullptr,
+                       uint32_t* d_cert_count = nullptr) {
     if (nq == 0) return LB_OK;
     const int kc = coarse_k(k);
     if (kc > 896) return fail(LB_ERR_UNSUPPORTED, "k too large for the fused selector (k <= 704)");
@@ -610,8 +625,47 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         r.dim = idx->dim; r.queries = a.queries; r.nq = cq; r.packed = merged; r.ids32 = nullptr;
         r.c = kc; r.k = k; r.tomb = nullptr; r.tomb_bits = 0; r.allow = nullptr; r.id_base = idx->id_base;
         r.out_d = d_dist + (size_t)qo * k; r.out_l = d_lab + (size_t)qo * k; r.negate_dot = 1;
+        if (d_cert_flags != nullptr && idx->max_norm2 != nullptr) {
+            r.cert_flags = d_cert_flags + qo; r.cert_count = d_cert_count; r.max_norm2 = idx->max_norm2;
+            // coarse-key error bound relative to |q||x|: truncating fp32 accumulation over dim terms (measured
+            // ~4e-6 at dim 256, test_coarse_keys_accuracy), plus the 3xTF32 operand residue for fp32 rows
+            float beta = (float)idx->dim * 1.2e-7f;
+            if (beta < 8e-6f) beta = 8e-6f;
+            if (idx->dtype == DT_F32) beta += 1e-6f;
+            r.beta = beta;
+        }
         CK(launch_rescore(r, st));
     }
+    return LB_OK;
+}
+
+// Exhaustive exact search of ONE query (device pointer): the reference's arithmetic for every row, bitmaps
+// applied, k smallest by (distance, row).  Slow (one thread per row over the whole index); used only for the
+// queries the certification flags.
+static int exact_search_one(lb_index* idx, const void* d_q1, int k, const uint64_t* d_allow, float* h_dist, int64_t* h_lab,
+                            cudaStream_t st) {
+    Scratch scr(st);
+    const int64_t n = idx->size;
+    if (k > 4096) return fail(LB_ERR_UNSUPPORTED, "k > 4096");
+    int chunks = (int)((n + 4095) / 4096);
+    if (chunks < 1) chunks = 1;
+    float *d_o, *d_od;
+    int64_t* d_oi;
+    uint64_t *p, *m;
+    CK(scr.get((void**)&d_o, (size_t)n * 4));
+    CK(scr.get((void**)&d_od, (size_t)k * 4));
+    CK(scr.get((void**)&d_oi, (size_t)k * 8));
+    CK(scr.get((void**)&p, (size_t)chunks * k * 8));
+    CK(scr.get((void**)&m, (size_t)k * 8));
+    CK(launch_batch_flat(idx->metric, idx->dtype, idx->rows, n, idx->dim, d_q1, d_o, 1, st));
+    CK(launch_mask_rows(d_o, n, idx->tomb, (uint32_t)(idx->tomb_bits > 0xffffffffll ? 0xffffffffll : idx->tomb_bits),
+                        (const uint32_t*)d_allow, st));
+    CK(launch_select_k(d_o, n, k, p, m, d_oi, d_od, st));
+    CK(cudaMemcpyAsync(h_dist, d_od, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_lab, d_oi, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int j = 0; j < k; j++)
+        if (h_lab[j] >= 0) h_lab[j] += idx->id_base;
     return LB_OK;
 }
 
@@ -646,11 +700,40 @@ int lb_index_search(lb_index* idx, const void* queries, int64_t nq, int k, const
         CK(scr.get((void**)&d_allow, words * 8));
         CK(cudaMemcpyAsync(d_allow, allow, words * 8, cudaMemcpyHostToDevice, st));
     }
-    rc = search_core(idx, d_q, nq, k, d_allow, d_d, d_l, st);
+    // certification: queries whose candidate margin does not cover the coarse error bound are re-done exactly
+    uint32_t *d_flags = nullptr, *d_count = nullptr;
+    if (idx->max_norm2 != nullptr && g_opt_certify.load(std::memory_order_relaxed)) {
+        CK(scr.get((void**)&d_flags, (size_t)nq * 4));
+        CK(scr.get((void**)&d_count, 4));
+        CK(cudaMemsetAsync(d_count, 0, 4, st));
+        CK(cudaMemsetAsync(d_flags, 0, (size_t)nq * 4, st));
+    }
+    rc = search_core(idx, d_q, nq, k, d_allow, d_d, d_l, st, d_flags, d_count);
     if (rc) { cudaStreamSynchronize(st); return rc; }
+    // the 4-byte count lands in a per-thread pinned word (a copy into pageable memory would stall every stream)
+    static thread_local uint32_t* t_pinned = nullptr;
+    if (d_count && t_pinned == nullptr && cudaHostAlloc((void**)&t_pinned, 64, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        t_pinned = nullptr;
+        d_count = nullptr;  // cannot report: skip the fallback rather than slow every call down
+    }
     CK(cudaMemcpyAsync(distances, d_d, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(labels, d_l, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    if (d_count) CK(cudaMemcpyAsync(t_pinned, d_count, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    const uint32_t n_uncert = d_count ? *t_pinned : 0u;
+    idx->last_uncertified.store((int64_t)n_uncert);
+    if (n_uncert > 0) {
+        std::vector<uint32_t> flags((size_t)nq);
+        CK(cudaMemcpy(flags.data(), d_flags, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+        const size_t qstride = (size_t)idx->dim * dtype_size(idx->dtype);
+        for (int64_t q = 0; q < nq; q++) {
+            if (!flags[(size_t)q]) continue;
+            rc = exact_search_one(idx, (const char*)d_q + (size_t)q * qstride, k, d_allow, distances + (size_t)q * k,
+                                  labels + (size_t)q * k, st);
+            if (rc) return rc;
+        }
+    }
     return LB_OK;
 }
 

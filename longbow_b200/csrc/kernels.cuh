@@ -61,7 +61,26 @@ struct RescoreArgs {
     int64_t* out_l;          // [nq][k]
     int negate_dot;          // 1: dot returned as a distance (negated)
     const float* nrm = nullptr;  // cosine only: exact per-row |x|^2 (reference lane order), or null
+    // certification of the coarse stage (packed mode only; null = off).  cert_flags[q] = 1 when the margin
+    // between the kc-th coarse key and the k-th exact result does not cover the coarse error bound, i.e. a row
+    // outside the candidate set could belong to the true top-k; cert_count accumulates such queries.
+    uint32_t* cert_flags = nullptr;
+    uint32_t* cert_count = nullptr;
+    const float* max_norm2 = nullptr;  // device scalar: max |x|^2 over the index (float bits, non-negative)
+    float beta = 0.f;                  // relative coarse-key error bound (of |q||x|)
 };
+
+struct CertArgs {
+    uint32_t* flags;
+    uint32_t* count;
+    const float* max_norm2;
+    float beta;
+};
+
+cudaError_t launch_row_maxnorm(int dtype, const void* db, int64_t n, int dim, int64_t row0, float* max_norm2,
+                               cudaStream_t st);
+cudaError_t launch_mask_rows(float* dist, int64_t n, const uint32_t* tomb, uint32_t tomb_bits, const uint32_t* allow,
+                             cudaStream_t st);
 
 size_t dense_scan_simt_smem(int tq, int cap);
 cudaError_t launch_dense_scan_simt(const ScanArgs& a, cudaStream_t st);

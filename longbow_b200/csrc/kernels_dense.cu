@@ -465,6 +465,46 @@ cudaError_t launch_merge_partials(const uint64_t* partial, int parts, int nq, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Certification of the coarse stage (thread 0 of a re-score block, after the exact sort).
+// Every row outside the candidate set has a coarse key >= the kc-th coarse key c_last; its exact key is at
+// least c_last - eps.  If that still exceeds the exact key of the k-th result (+ eps for the mapping), no
+// outside row can belong to the true top-k.  Exact keys are mapped into coarse-key space:
+//   L2  key = |x|^2 - 2 q.x = d^2 - |q|^2      cosine  key = -q.x/|x| = (d - 1) |q|      dot  key = -q.x = d
+// ---------------------------------------------------------------------------------------------
+template <int METRIC>
+__device__ __forceinline__ void certify(const CertArgs& ca, int q, const uint64_t* packed_q, int c, const uint64_t* keys,
+                                        int k, float qn2) {
+    bool cert = true;
+    const uint64_t last = packed_q[c - 1];
+    const uint64_t kth = (k - 1 < c) ? keys[k - 1] : kInvalid;
+    if (last != kInvalid && kth != kInvalid) {  // fewer candidates than kc: every live row was a candidate
+        const float c_last = key_of(last), dk = key_of(kth);
+        const float qn = sqrtf(qn2), xn2 = *ca.max_norm2, xn = sqrtf(xn2);
+        float ek, eps;
+        if (METRIC == METRIC_L2) { ek = dk * dk - qn2; eps = 2.f * ca.beta * qn * xn + 4e-6f * (xn2 + qn2); }
+        else if (METRIC == METRIC_COSINE) { ek = (dk - 1.f) * qn; eps = ca.beta * qn + 2e-6f * qn; }
+        else { ek = dk; eps = ca.beta * qn * xn; }
+        cert = (c_last - ek) > 2.f * eps;
+    }
+    ca.flags[q] = cert ? 0u : 1u;
+    if (!cert) atomicAdd(ca.count, 1u);
+}
+
+// |q|^2 of the block's query (fp32, any order: only used for the certification bound)
+__device__ __forceinline__ float block_qnorm2(const float* qf, int dim, float* s_red8) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) s = fmaf(qf[i], qf[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) s_red8[threadIdx.x >> 5] = s;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) t += s_red8[w];
+    __syncthreads();
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
 // S3: exact re-score of candidate ids + final (distance,id) sort -> top-k.
 //   grid = nq; block = next_pow2(c) threads (>= 32, <= 1024); one thread per candidate.
 // Candidate sources:
@@ -479,8 +519,10 @@ __global__ void rescore_kernel(const T* __restrict__ db, uint32_t n_rows, int di
                                int nq, const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ids32,
                                int c, int k, const uint32_t* __restrict__ tomb, uint32_t tomb_bits,
                                const uint32_t* __restrict__ allow, int64_t id_base, float* __restrict__ out_d,
-                               int64_t* __restrict__ out_l, int negate_dot, const float* __restrict__ nrm) {
+                               int64_t* __restrict__ out_l, int negate_dot, const float* __restrict__ nrm,
+                               const CertArgs ca) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float s_red32[32];
     const int n2 = blockDim.x;
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [n2]
     float* qf = reinterpret_cast<float*>(keys + n2);          // [dim]
@@ -537,6 +579,10 @@ __global__ void rescore_kernel(const T* __restrict__ db, uint32_t n_rows, int di
     keys[threadIdx.x] = mine;
     __syncthreads();
     block_bitonic_sort(keys, n2);
+    if (ca.flags != nullptr && packed != nullptr) {  // block-uniform
+        const float qn2 = block_qnorm2(qf, dim, s_red32);
+        if (threadIdx.x == 0) certify<METRIC>(ca, q, packed + (size_t)q * c, c, keys, k, qn2);
+    }
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
         uint64_t p = (j < n2) ? keys[j] : kInvalid;
         bool valid = p != kInvalid;
@@ -574,7 +620,8 @@ rescore_coop_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T*
                     const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ids32, int c, int k, int n2,
                     const uint32_t* __restrict__ tomb, uint32_t tomb_bits, const uint32_t* __restrict__ allow,
                     int64_t id_base, float* __restrict__ out_d, int64_t* __restrict__ out_l, int negate_dot,
-                    const float* __restrict__ nrm) {
+                    const float* __restrict__ nrm, const CertArgs ca) {
+    __shared__ float s_red32[32];
     constexpr int V = Elem<T>::kVec;              // elements per 16-byte piece
     constexpr int PIECES = RC_CHUNK / 16;         // pieces per row chunk
     constexpr int ACC = (METRIC == METRIC_COSINE) ? METRIC_DOT : METRIC;  // cosine: stored |x|^2, dot chain only
@@ -707,6 +754,10 @@ rescore_coop_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T*
     }
     __syncthreads();
     block_bitonic_sort(keys, n2);
+    if (ca.flags != nullptr && packed != nullptr) {  // block-uniform
+        const float qn2 = block_qnorm2(qf, dim, s_red32);
+        if (tid == 0) certify<METRIC>(ca, q, packed + (size_t)q * c, c, keys, k, qn2);
+    }
     for (int j = tid; j < k; j += blockDim.x) {
         const uint64_t p = (j < n2) ? keys[j] : kInvalid;
         const bool valid = p != kInvalid;
@@ -719,6 +770,7 @@ template <typename T>
 static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
     int n2 = next_pow2(max(a.c, 32));
     if (n2 > 1024) return cudaErrorInvalidValue;
+    const CertArgs ca{a.cert_flags, a.cert_count, a.max_norm2, a.beta};
     // cooperative-gather kernel whenever rows are 16-byte aligned multiples of 16 bytes
     const size_t row_bytes = (size_t)a.dim * sizeof(T);
     const bool coop = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.db) & 15) == 0) &&
@@ -733,7 +785,7 @@ static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
         if (e != cudaSuccess) return e;                                                                     \
         kern<<<a.nq, RC_WARPS * 32, smem, st>>>((const T*)a.db, a.n_rows, a.dim, (const T*)a.queries, a.nq, \
                                                 a.packed, a.ids32, a.c, a.k, n2, a.tomb, a.tomb_bits, a.allow, \
-                                                a.id_base, a.out_d, a.out_l, a.negate_dot, a.nrm);          \
+                                                a.id_base, a.out_d, a.out_l, a.negate_dot, a.nrm, ca);      \
     }
         switch (a.metric) {
             case METRIC_L2: LB_RC(METRIC_L2) break;
@@ -754,7 +806,7 @@ static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
         }                                                                                                   \
         kern<<<a.nq, n2, smem, st>>>((const T*)a.db, a.n_rows, a.dim, (const T*)a.queries, a.nq, a.packed,  \
                                      a.ids32, a.c, a.k, a.tomb, a.tomb_bits, a.allow, a.id_base, a.out_d,   \
-                                     a.out_l, a.negate_dot, a.nrm);                                         \
+                                     a.out_l, a.negate_dot, a.nrm, ca);                                     \
     }
     switch (a.metric) {
         case METRIC_L2: LB_RS(METRIC_L2) break;
@@ -762,6 +814,56 @@ static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
         default: LB_RS(METRIC_DOT) break;
     }
 #undef LB_RS
+    count_launch();
+    return cudaGetLastError();
+}
+
+// max |x|^2 over rows [row0, n): one warp per row, atomicMax on the float bits (non-negative floats order as uints)
+template <typename T>
+__global__ void row_maxnorm_kernel(const T* __restrict__ db, int64_t n, int dim, int64_t row0, float* __restrict__ out) {
+    const int64_t r = row0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const T* row = db + r * dim;
+    float s = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const float v = Elem<T>::widen(row[i]);
+        s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && s == s) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(fabsf(s)));
+}
+
+cudaError_t launch_row_maxnorm(int dtype, const void* db, int64_t n, int dim, int64_t row0, float* max_norm2,
+                               cudaStream_t st) {
+    if (n <= row0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n - row0 + 7) / 8);
+    switch (dtype) {
+        case DT_F32: row_maxnorm_kernel<float><<<blocks, 256, 0, st>>>((const float*)db, n, dim, row0, max_norm2); break;
+        case DT_F16: row_maxnorm_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)db, n, dim, row0, max_norm2); break;
+        case DT_I8: row_maxnorm_kernel<int8_t><<<blocks, 256, 0, st>>>((const int8_t*)db, n, dim, row0, max_norm2); break;
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// exact fallback: rows excluded by the bitmaps get NaN (select_k ignores NaN)
+__global__ void mask_rows_kernel(float* __restrict__ dist, int64_t n, const uint32_t* __restrict__ tomb, uint32_t tomb_bits,
+                                 const uint32_t* __restrict__ allow) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool ok = true;
+    if (tomb != nullptr && (uint32_t)i < tomb_bits && bit_set(tomb, (uint32_t)i)) ok = false;
+    if (ok && allow != nullptr && !bit_set(allow, (uint32_t)i)) ok = false;
+    if (!ok) dist[i] = __int_as_float(0x7fc00000);
+}
+
+cudaError_t launch_mask_rows(float* dist, int64_t n, const uint32_t* tomb, uint32_t tomb_bits, const uint32_t* allow,
+                             cudaStream_t st) {
+    if (n <= 0 || (tomb == nullptr && allow == nullptr)) return cudaSuccess;
+    mask_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dist, n, tomb, tomb_bits, allow);
     count_launch();
     return cudaGetLastError();
 }

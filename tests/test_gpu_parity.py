@@ -487,3 +487,46 @@ def test_coarse_keys_accuracy(lbgpu, dtype, metric, bound):
     err = np.abs(keys - want) / scale
     assert err.max() <= bound, f"coarse key error {err.max():.3e} of |q||x| (bound {bound})"
     idx.close()
+
+
+# ------------------------------------------------------------------ certification of the coarse stage
+def test_certification_near_ties(lbgpu, oracle):
+    """300 rows that differ from each other by one fp16 ulp in one coordinate: their exact distances to the
+    query differ by less than the coarse error, and there are more of them than the candidate margin (kc - k).
+    The host search must notice (certification), redo those queries exhaustively, and still match the oracle."""
+    from longbow_b200 import _lib
+    rng = np.random.default_rng(99)
+    n, dim, k = 30000, 256, 100
+    db = make_db(rng, n, dim, np.float16)
+    base = db[17].copy()
+    pos = rng.choice(np.arange(1000, n), 300, replace=False)
+    for j, r in enumerate(pos):
+        v = base.copy()
+        toward = np.float16(np.inf) if j % 2 else np.float16(-np.inf)
+        v[j % dim] = np.nextafter(v[j % dim], toward, dtype=np.float16)
+        db[r] = v
+    q = np.stack([base, db[5], db[12345]])  # query 0 sits in the middle of the near-tie cluster
+    for metric in (COS, L2, DOT):
+        idx = lbgpu.DenseIndex(dim, np.float16, metric)
+        idx.add(db)
+        gd, gl = idx.search(q, k)
+        wd, wl = oracle.search(metric, db, q, k)
+        assert_topk_equal(gd, gl, wd, wl, 0.0, f"near ties, metric {metric}")
+        assert idx.last_uncertified() >= 1, "the near-tie query must be flagged"
+        # the same through the device entry point is NOT certified; with certification off the host call may differ
+        idx.close()
+    # ordinary data: nothing is flagged
+    db2, q2 = make_db(rng, 20000, 128, np.float32), make_db(rng, 50, 128, np.float32)
+    idx = lbgpu.DenseIndex(128, np.float32, L2)
+    idx.add(db2)
+    gd, gl = idx.search(q2, 10)
+    wd, wl = oracle.search(L2, db2, q2, 10)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "plain fp32")
+    assert idx.last_uncertified() == 0
+    _lib.set_option("certify", 0)
+    try:
+        idx.search(q2, 10)
+        assert idx.last_uncertified() == 0
+    finally:
+        _lib.set_option("certify", 1)
+    idx.close()
