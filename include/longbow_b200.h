@@ -178,6 +178,14 @@ int lb_pq_set_tombstones(lb_pq *pq, const uint64_t *bitmap, int64_t nbits);
 int lb_pq_build_adc_table(lb_pq *pq, const float *query, float *table);
 /* PQEncoder.Encode for n vectors (internal/pq/encoder.go:76-136). */
 int lb_pq_encode(lb_pq *pq, const float *vectors, int64_t n, uint8_t *codes);
+/* PQEncoder.Train (internal/pq/encoder.go:39-73) = TrainKMeans per subspace (internal/pq/kmeans.go:64-151), on the
+ * GPU: vectors [n*dims] fp32 (host), init_idx [m*k] = the data rows the centroids of each subspace start from (the
+ * reference draws them with rand.Perm; supplying them makes the run reproducible and, given equal indices,
+ * bit-identical to the reference's arithmetic), max_iter <= 0 -> 20.  Output codebooks [m][k][dims/m] in the layout
+ * lb_pq_create's blob expects; iters_run [m] (optional) = iterations each subspace ran before the reference's
+ * early-stop rule fired.  Empty clusters are re-seeded from row (c*7919 + iter*104729) mod n. */
+int lb_pq_train(int device, const float *vectors, int64_t n, int dims, int m, int k, int max_iter,
+                const int32_t *init_idx, float *codebooks, int32_t *iters_run);
 /* ADC scan of all resident codes for nq fp32 queries, fused top-kprime, then (if a raw index
  * is attached) exact fp32 Euclidean re-rank of those candidates -> top-k. */
 int lb_pq_search(lb_pq *pq, const float *queries, int64_t nq, int k, int kprime, const uint64_t *allow,

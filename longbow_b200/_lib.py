@@ -63,6 +63,7 @@ SIGNATURES = {
     "lb_pq_set_tombstones": (i32, [vp, vp, i64]),
     "lb_pq_build_adc_table": (i32, [vp, vp, vp]),
     "lb_pq_encode": (i32, [vp, vp, i64, vp]),
+    "lb_pq_train": (i32, [i32, vp, i64, i32, i32, i32, i32, vp, vp, vp]),
     "lb_pq_search": (i32, [vp, vp, i64, i32, i32, vp, vp, vp]),
     "lb_pq_search_device": (i32, [vp, vp, i64, i32, i32, vp, vp, vp, vp]),
     "lb_filter_i64": (i32, [i32, vp, i64, i32, i64, i32, vp]),

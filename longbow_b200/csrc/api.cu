@@ -1107,6 +1107,57 @@ int lb_pq_encode(lb_pq* pq, const float* vectors, int64_t n, uint8_t* codes) {
     return LB_OK;
 }
 
+}  // extern "C"
+
+// memset-style fill of int32 words on the device
+static __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+extern "C" {
+
+int lb_pq_train(int device, const float* vectors, int64_t n, int dims, int m, int k, int max_iter,
+                const int32_t* init_idx, float* codebooks, int32_t* iters_run) {
+    if (!vectors || !init_idx || !codebooks) return fail(LB_ERR_INVALID, "NULL buffer");
+    if (n <= 0) return fail(LB_ERR_INVALID, "empty training data");                         // encoder.go:41-43
+    if (m <= 0 || dims <= 0 || dims % m != 0) return fail(LB_ERR_INVALID, "dimension must be divisible by M");
+    if (k <= 0 || n < k) return fail(LB_ERR_INVALID, "insufficient data for k-means: n < k");  // kmeans.go:65-67
+    if (k > 256) return fail(LB_ERR_UNSUPPORTED, "K > 256 (codes are bytes)");
+    if (dims / m > 128) return fail(LB_ERR_UNSUPPORTED, "sub-vector dimension > 128");
+    if (max_iter <= 0) max_iter = 20;                                                       // encoder.go:62
+    for (int64_t i = 0; i < (int64_t)m * k; i++)
+        if (init_idx[i] < 0 || init_idx[i] >= n) return fail(LB_ERR_INVALID, "init_idx out of range");
+    int rc = use_device(device);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch scr(st);
+    const int sub = dims / m;
+    float *d_data, *d_cent;
+    int32_t *d_init, *d_assign, *d_active, *d_iters;
+    uint32_t* d_changed;
+    CK(scr.get((void**)&d_data, (size_t)n * dims * 4));
+    CK(scr.get((void**)&d_cent, (size_t)m * k * sub * 4));
+    CK(scr.get((void**)&d_init, (size_t)m * k * 4));
+    CK(scr.get((void**)&d_assign, (size_t)m * n * 4));
+    CK(scr.get((void**)&d_active, (size_t)m * 4));
+    CK(scr.get((void**)&d_iters, (size_t)m * 4));
+    CK(scr.get((void**)&d_changed, (size_t)m * 4));
+    CK(cudaMemcpyAsync(d_data, vectors, (size_t)n * dims * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_init, init_idx, (size_t)m * k * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_changed, 0, (size_t)m * 4, st));
+    CK(cudaMemsetAsync(d_iters, 0, (size_t)m * 4, st));
+    const int64_t na = (int64_t)m * n;
+    fill_i32_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(d_assign, na, -1);
+    fill_i32_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_active, m, 1);
+    count_launch(); count_launch();
+    CK(launch_pq_train(d_data, n, dims, m, k, max_iter, d_init, d_cent, d_assign, d_changed, d_active, d_iters, st));
+    CK(cudaMemcpyAsync(codebooks, d_cent, (size_t)m * k * sub * 4, cudaMemcpyDeviceToHost, st));
+    if (iters_run) CK(cudaMemcpyAsync(iters_run, d_iters, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return LB_OK;
+}
+
 static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kprime, const uint64_t* d_allow,
                           float* d_dist, int64_t* d_lab, cudaStream_t st) {
     if (nq == 0) return LB_OK;

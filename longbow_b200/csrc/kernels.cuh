@@ -141,6 +141,9 @@ cudaError_t launch_adc_scan(const PqScanArgs& a, cudaStream_t st);
 cudaError_t launch_adc_batch(const float* table, const uint8_t* codes, int M, int64_t n, float* out, cudaStream_t st);
 cudaError_t launch_pq_encode(const float* codebooks, int M, int K, int sub, const float* vecs, int64_t n,
                              uint8_t* codes, cudaStream_t st);
+cudaError_t launch_pq_train(const float* d_data, int64_t n, int dims, int M, int K, int max_iter,
+                            const int32_t* d_init_idx, float* d_cent, int32_t* d_assign, uint32_t* d_changed,
+                            int32_t* d_active, int32_t* d_iters, cudaStream_t st);
 cudaError_t launch_unpack_topk(const uint64_t* merged, int nq, int kc, int k, int64_t id_base, float* out_d,
                                int64_t* out_l, cudaStream_t st);
 

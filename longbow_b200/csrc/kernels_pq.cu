@@ -223,6 +223,127 @@ cudaError_t launch_pq_encode(const float* codebooks, int M, int K, int sub, cons
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// PQ training: Lloyd's k-means per subspace, TrainKMeans (internal/pq/kmeans.go:64-151) as
+// PQEncoder.Train drives it (internal/pq/encoder.go:39-73).  Bit-exact with the reference's arithmetic
+// given the same initial rows: the E-step uses L2SquaredFloat32's 4-lane order and a strict '<' argmin,
+// and the M-step adds the member vectors of a centroid IN ROW ORDER with plain fp32 adds (one warp per
+// (subspace, centroid) walks the assignment array, ballots its members and adds them one at a time,
+// lanes = dimensions) before the fp32 division.  All M subspaces advance together; a subspace that meets
+// the reference's early-stop rule is frozen by its active[] flag (no host round trips).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+kmeans_assign_kernel(const float* __restrict__ data, int64_t n, int dims, int sub, int K, const float* __restrict__ cent,
+                     int32_t* __restrict__ assign, uint32_t* __restrict__ changed, const int32_t* __restrict__ active) {
+    extern __shared__ float cb[];  // [K][sub]
+    const int m = blockIdx.y;
+    if (!active[m]) return;
+    for (int i = threadIdx.x; i < K * sub; i += blockDim.x) cb[i] = cent[(size_t)m * K * sub + i];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* x = data + (size_t)i * dims + (size_t)m * sub;
+    int best = -1;
+    float bd = 3.402823466e+38f;
+    for (int c = 0; c < K; c++) {
+        ExactAcc<METRIC_L2> acc;
+        acc.init();
+        const float* cc = cb + c * sub;
+        int j = 0;
+        for (; j <= sub - 4; j += 4) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc.add(e, __ldg(x + j + e), cc[j + e]);
+        }
+        for (; j < sub; j++) acc.add(0, __ldg(x + j), cc[j]);
+        const float d = acc.sum();
+        if (d < bd) { bd = d; best = c; }
+    }
+    if (best < 0) best = 0;
+    int32_t* a = assign + (size_t)m * n + i;
+    if (*a != best) { atomicAdd(changed + m, 1u); *a = best; }
+}
+
+constexpr int KM_MAXJ = 4;  // sub <= 128
+__global__ void __launch_bounds__(32)
+kmeans_update_kernel(const float* __restrict__ data, int64_t n, int dims, int sub, int K, float* __restrict__ cent,
+                     const int32_t* __restrict__ assign, const int32_t* __restrict__ active, int iter) {
+    const int c = blockIdx.x, m = blockIdx.y, lane = threadIdx.x;
+    if (!active[m]) return;
+    const int32_t* a = assign + (size_t)m * n;
+    float sum[KM_MAXJ] = {0.f, 0.f, 0.f, 0.f};
+    int count = 0;
+    for (int64_t base = 0; base < n; base += 32) {
+        const int64_t i = base + lane;
+        unsigned mask = __ballot_sync(0xffffffffu, i < n && a[i] == c);
+        count += __popc(mask);
+        while (mask) {  // members in increasing row order
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float* v = data + (size_t)(base + b) * dims + (size_t)m * sub;
+#pragma unroll
+            for (int t = 0; t < KM_MAXJ; t++) {
+                const int j = lane + 32 * t;
+                if (j < sub) sum[t] = __fadd_rn(sum[t], __ldg(v + j));
+            }
+        }
+    }
+    float* cc = cent + ((size_t)m * K + c) * sub;
+#pragma unroll
+    for (int t = 0; t < KM_MAXJ; t++) {
+        const int j = lane + 32 * t;
+        if (j >= sub) continue;
+        if (count > 0) {
+            cc[j] = __fdiv_rn(sum[t], (float)count);
+        } else {  // empty cluster: re-seed (stand-in for the reference's rand.Intn, see oracle/lb_oracle.c)
+            const int64_t idx = ((int64_t)c * 7919 + (int64_t)iter * 104729) % n;
+            cc[j] = data[(size_t)idx * dims + (size_t)m * sub + j];
+        }
+    }
+}
+
+__global__ void kmeans_finish_iter_kernel(int M, int64_t n, int iter, uint32_t* __restrict__ changed,
+                                          int32_t* __restrict__ active, int32_t* __restrict__ iters) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M || !active[m]) return;
+    iters[m] = iter + 1;
+    if (iter > 0 && (int64_t)changed[m] < n / 1000 + 1) active[m] = 0;  // kmeans.go:146-148
+    changed[m] = 0;
+}
+
+__global__ void kmeans_init_kernel(const float* __restrict__ data, int dims, int sub, int K, int M,
+                                   const int32_t* __restrict__ init_idx, float* __restrict__ cent) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)M * K * sub) return;
+    const int j = (int)(t % sub);
+    const int c = (int)((t / sub) % K);
+    const int m = (int)(t / ((int64_t)sub * K));
+    cent[t] = data[(size_t)init_idx[(size_t)m * K + c] * dims + (size_t)m * sub + j];
+}
+
+cudaError_t launch_pq_train(const float* d_data, int64_t n, int dims, int M, int K, int max_iter,
+                            const int32_t* d_init_idx, float* d_cent, int32_t* d_assign, uint32_t* d_changed,
+                            int32_t* d_active, int32_t* d_iters, cudaStream_t st) {
+    const int sub = dims / M;
+    if (sub > 32 * KM_MAXJ) return cudaErrorInvalidValue;
+    const int64_t total = (int64_t)M * K * sub;
+    kmeans_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_data, dims, sub, K, M, d_init_idx, d_cent);
+    count_launch();
+    const size_t smem = (size_t)K * sub * 4;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    for (int it = 0; it < max_iter; it++) {
+        dim3 ga((unsigned)((n + 127) / 128), M);
+        kmeans_assign_kernel<<<ga, 128, smem, st>>>(d_data, n, dims, sub, K, d_cent, d_assign, d_changed, d_active);
+        dim3 gu(K, M);
+        kmeans_update_kernel<<<gu, 32, 0, st>>>(d_data, n, dims, sub, K, d_cent, d_assign, d_active, it);
+        kmeans_finish_iter_kernel<<<(M + 127) / 128, 128, 0, st>>>(M, n, it, d_changed, d_active, d_iters);
+        count_launch(); count_launch(); count_launch();
+    }
+    return cudaGetLastError();
+}
+
 __global__ void unpack_topk_kernel2(const uint64_t* __restrict__ merged, int nq, int kc, int k, int64_t id_base,
                                     float* __restrict__ out_d, int64_t* __restrict__ out_l) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

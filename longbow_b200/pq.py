@@ -59,6 +59,17 @@ class PQEncoder:
         cb = np.frombuffer(data, "<f4", offset=12).reshape(m, k, sub)
         return PQEncoder(dims, m, k, cb, device)
 
+    # encoder.go:39-73 + kmeans.go:64-151
+    @staticmethod
+    def Train(dims: int, m: int, k: int, vectors, init_idx=None, seed: int = 0, max_iter: int = 20,
+              device: int = 0) -> "PQEncoder":
+        """NewPQEncoder(dims, m, k) followed by Train(vectors): k-means per subspace on the GPU.
+
+        ``init_idx`` [m, k]: the data rows each subspace's centroids start from (the reference draws them with
+        ``rand.Perm``); by default a seeded NumPy permutation per subspace."""
+        cb, _ = train_codebooks(dims, m, k, vectors, init_idx, seed, max_iter, device)
+        return PQEncoder(dims, m, k, cb, device)
+
     def CodeSize(self) -> int:  # encoder.go:163-165
         return self.M
 
@@ -142,3 +153,24 @@ class PQEncoder:
         check(self._lib.lb_pq_search_device(self._h, q.data_ptr(), q.shape[0], int(k), int(kprime),
                                             None if allow is None else allow.data_ptr(), out_d.data_ptr(),
                                             out_l.data_ptr(), _stream_ptr(stream)))
+
+
+def train_codebooks(dims: int, m: int, k: int, vectors, init_idx=None, seed: int = 0, max_iter: int = 20,
+                    device: int = 0):
+    """TrainKMeans for every subspace (internal/pq/kmeans.go:64-151); returns (codebooks [m,k,sub], iters [m])."""
+    if dims % m != 0:
+        raise ValueError("dimension must be divisible by M")
+    v = np.ascontiguousarray(vectors, np.float32).reshape(-1, dims)
+    n = v.shape[0]
+    if n == 0:
+        raise ValueError("empty training data")
+    if n < k:
+        raise ValueError("insufficient data for k-means: n < k")
+    if init_idx is None:
+        rng = np.random.RandomState(seed)
+        init_idx = np.stack([rng.permutation(n)[:k] for _ in range(m)])
+    init_idx = np.ascontiguousarray(init_idx, np.int32).reshape(m, k)
+    cb = np.empty((m, k, dims // m), np.float32)
+    iters = np.zeros(m, np.int32)
+    check(_lib.load().lb_pq_train(device, _ptr(v), n, dims, m, k, max_iter, _ptr(init_idx), _ptr(cb), _ptr(iters)))
+    return cb, iters

@@ -573,3 +573,65 @@ LBO_API void lbo_mask_to_bitmap(const uint8_t *mask, int64_t n, uint64_t *bm) {
     memset(bm, 0, (size_t)((n + 63) / 64) * 8);
     for (int64_t i = 0; i < n; i++) if (mask[i]) bm[i >> 6] |= (uint64_t)1 << (i & 63);
 }
+
+/* ---------------------------------------------------------------------------
+ * PQ training: TrainKMeans (internal/pq/kmeans.go:64-151) per subspace, as PQEncoder.Train
+ * drives it (internal/pq/encoder.go:39-73: 20 iterations).
+ *   init      : centroid c = data row init_idx[c]   (reference: rand.Perm(n)[:k] -- Go's math/rand
+ *               stream is not reproducible here, so the caller supplies the indices; UNPINNED)
+ *   E-step    : argmin_c L2Squared(vec, cent_c), strict '<' (first lowest index), kmeans.go:101-118
+ *   sums      : centSum[j] += vec[j] in row order, fp32 (kmeans.go:126-130)
+ *   M-step    : cent[j] = sum[j] / float32(count) (kmeans.go:134-141); an empty cluster is re-seeded
+ *               from row (c*7919 + iter*104729) mod n  (reference: rand.Intn(n); UNPINNED stand-in)
+ *   early stop: iter > 0 && changed < n/1000 + 1 (kmeans.go:146-148)
+ * data: [n][dims] row-major, subspace m uses columns [m*sub, (m+1)*sub).  out: [M][K][sub].
+ * ------------------------------------------------------------------------- */
+LBO_API int lbo_pq_train(const float *data, int64_t n, int dims, int M, int K, int max_iter,
+                         const int32_t *init_idx /* [M][K] */, float *out, int32_t *iters_run /* [M] or NULL */) {
+    if (n < K || dims % M != 0) return 1;
+    const int sub = dims / M;
+    int32_t *assign = (int32_t *)malloc((size_t)n * sizeof(int32_t));
+    int32_t *counts = (int32_t *)malloc((size_t)K * sizeof(int32_t));
+    float *sums = (float *)malloc((size_t)K * sub * sizeof(float));
+    for (int m = 0; m < M; m++) {
+        float *cent = out + (size_t)m * K * sub;
+        for (int c = 0; c < K; c++)
+            memcpy(cent + (size_t)c * sub, data + (size_t)init_idx[(size_t)m * K + c] * dims + (size_t)m * sub,
+                   (size_t)sub * sizeof(float));
+        for (int64_t i = 0; i < n; i++) assign[i] = -1;
+        int it = 0;
+        for (; it < max_iter; it++) {
+            memset(sums, 0, (size_t)K * sub * sizeof(float));
+            memset(counts, 0, (size_t)K * sizeof(int32_t));
+            int64_t changed = 0;
+            for (int64_t i = 0; i < n; i++) {
+                const float *vec = data + (size_t)i * dims + (size_t)m * sub;
+                float best = FLT_MAX;
+                int bc = -1;
+                for (int c = 0; c < K; c++) {
+                    float d = lbo_l2sq_f32(vec, cent + (size_t)c * sub, sub);
+                    if (d < best) { best = d; bc = c; }
+                }
+                if (bc < 0) bc = 0; /* all distances NaN/Inf: Go would index -1 and panic; keep defined */
+                if (assign[i] != bc) { changed++; assign[i] = bc; }
+                counts[bc]++;
+                float *cs = sums + (size_t)bc * sub;
+                for (int j = 0; j < sub; j++) cs[j] += vec[j];
+            }
+            for (int c = 0; c < K; c++) {
+                float *cc = cent + (size_t)c * sub;
+                if (counts[c] > 0) {
+                    float cnt = (float)counts[c];
+                    for (int j = 0; j < sub; j++) cc[j] = sums[(size_t)c * sub + j] / cnt;
+                } else {
+                    int64_t idx = ((int64_t)c * 7919 + (int64_t)it * 104729) % n;
+                    memcpy(cc, data + (size_t)idx * dims + (size_t)m * sub, (size_t)sub * sizeof(float));
+                }
+            }
+            if (it > 0 && changed < n / 1000 + 1) { it++; break; }
+        }
+        if (iters_run) iters_run[m] = it;
+    }
+    free(assign); free(counts); free(sums);
+    return 0;
+}

@@ -184,6 +184,19 @@ def pq_encode(vecs: np.ndarray, codebooks: np.ndarray) -> np.ndarray:
     return codes
 
 
+def pq_train(data: np.ndarray, M: int, K: int, init_idx: np.ndarray, max_iter: int = 20):
+    """TrainKMeans per subspace (internal/pq/kmeans.go:64-151) from explicit initial rows; returns
+    (codebooks [M, K, sub], iterations run per subspace)."""
+    data = _c(data, np.float32)
+    n, dims = data.shape
+    init_idx = _c(init_idx, np.int32).reshape(M, K)
+    out = np.empty((M, K, dims // M), np.float32)
+    iters = np.zeros(M, np.int32)
+    rc = exact().lbo_pq_train(_p(data), C.c_int64(n), dims, M, K, max_iter, _p(init_idx), _p(out), _p(iters))
+    assert rc == 0
+    return out, iters
+
+
 def pq_decode(codes: np.ndarray, codebooks: np.ndarray) -> np.ndarray:
     codes, codebooks = _c(codes, np.uint8), _c(codebooks, np.float32)
     M, K, sub = codebooks.shape

@@ -530,3 +530,33 @@ def test_certification_near_ties(lbgpu, oracle):
     finally:
         _lib.set_option("certify", 1)
     idx.close()
+
+
+# ------------------------------------------------------------------ PQ training (k-means) on the GPU
+@pytest.mark.parametrize("n,dims,M,K", [(4000, 32, 4, 16), (6000, 64, 8, 256), (700, 12, 4, 32), (3000, 40, 2, 64)])
+def test_pq_train_bit_exact(oracle, n, dims, M, K):
+    """lb_pq_train == TrainKMeans (internal/pq/kmeans.go:64-151) restated in the oracle, bit for bit, from the
+    same initial rows -- including the number of iterations each subspace runs before the early stop."""
+    from longbow_b200 import pq
+    rng = np.random.default_rng(n + K)
+    centers = rng.standard_normal((K // 2, dims)).astype(np.float32) * 3
+    data = (centers[rng.integers(0, K // 2, n)] + rng.standard_normal((n, dims)).astype(np.float32)).astype(np.float32)
+    data[10] = data[11]  # duplicate rows: equal distances, the first centroid index must win
+    init = np.stack([rng.permutation(n)[:K] for _ in range(M)]).astype(np.int32)
+    cb, iters = pq.train_codebooks(dims, M, K, data, init_idx=init)
+    wcb, witers = oracle.pq_train(data, M, K, init)
+    assert np.array_equal(iters, witers), (iters, witers)
+    assert np.array_equal(cb, wcb)
+    if K == 256:  # resident handles need K = 256 (simd.ADCDistanceBatch hard-codes the table stride)
+        enc = pq.PQEncoder.Train(dims, M, K, data, init_idx=init)
+        codes = enc.EncodeBatch(data[:50])
+        assert np.array_equal(codes, oracle.pq_encode(data[:50], wcb))
+        enc.close()
+
+
+def test_pq_train_validation():
+    from longbow_b200 import pq
+    with pytest.raises(ValueError):
+        pq.train_codebooks(10, 3, 4, np.zeros((8, 10), np.float32))       # dims % M
+    with pytest.raises(ValueError):
+        pq.train_codebooks(8, 2, 16, np.zeros((4, 8), np.float32))        # n < k (kmeans.go:65-67)
