@@ -202,6 +202,13 @@ int lb_filter_i64(int device, const int64_t *column, int64_t n, int op, int64_t 
                   uint64_t *bitmap);
 int lb_filter_f32(int device, const float *column, int64_t n, int op, float value, int and_into,
                   uint64_t *bitmap);
+/* Same with the column and the bitmap (ceil(n/64) words, zero-initialised unless and_into) resident on the device:
+ * a multi-predicate filter is a chain of these on one stream, and the result feeds lb_index_search_device's
+ * d_allow without ever visiting the host. */
+int lb_filter_i64_device(int device, const int64_t *d_column, int64_t n, int op, int64_t value, int and_into,
+                         uint64_t *d_bitmap, void *stream);
+int lb_filter_f32_device(int device, const float *d_column, int64_t n, int op, float value, int and_into,
+                         uint64_t *d_bitmap, void *stream);
 
 /* Count of kernel launches issued by this library in this process (bench evidence). */
 int64_t lb_kernel_launch_count(void);

@@ -68,6 +68,8 @@ SIGNATURES = {
     "lb_pq_search_device": (i32, [vp, vp, i64, i32, i32, vp, vp, vp, vp]),
     "lb_filter_i64": (i32, [i32, vp, i64, i32, i64, i32, vp]),
     "lb_filter_f32": (i32, [i32, vp, i64, i32, fp, i32, vp]),
+    "lb_filter_i64_device": (i32, [i32, vp, i64, i32, i64, i32, vp, vp]),
+    "lb_filter_f32_device": (i32, [i32, vp, i64, i32, fp, i32, vp, vp]),
     "lb_kernel_launch_count": (i64, []),
     "lb_set_option": (i32, [C.c_char_p, i32]),
     "lb_prof_enable": (i32, [i32]),

@@ -1290,6 +1290,26 @@ int lb_filter_i64(int device, const int64_t* column, int64_t n, int op, int64_t 
                                       return launch_filter_i64(c, n, op, value, and_into, b, st);
                                   });
 }
+int lb_filter_i64_device(int device, const int64_t* d_column, int64_t n, int op, int64_t value, int and_into,
+                         uint64_t* d_bitmap, void* stream) {
+    if (n < 0 || op < 0 || op > 5) return fail(LB_ERR_INVALID, "bad argument");
+    if (n == 0) return LB_OK;
+    if (!d_column || !d_bitmap) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(device);
+    if (rc) return rc;
+    CK(launch_filter_i64(d_column, n, op, value, and_into, (uint32_t*)d_bitmap, (cudaStream_t)stream));
+    return LB_OK;
+}
+int lb_filter_f32_device(int device, const float* d_column, int64_t n, int op, float value, int and_into,
+                         uint64_t* d_bitmap, void* stream) {
+    if (n < 0 || op < 0 || op > 5) return fail(LB_ERR_INVALID, "bad argument");
+    if (n == 0) return LB_OK;
+    if (!d_column || !d_bitmap) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(device);
+    if (rc) return rc;
+    CK(launch_filter_f32(d_column, n, op, value, and_into, (uint32_t*)d_bitmap, (cudaStream_t)stream));
+    return LB_OK;
+}
 int lb_filter_f32(int device, const float* column, int64_t n, int op, float value, int and_into, uint64_t* bitmap) {
     return filter_common<float>(device, column, n, op, and_into, bitmap,
                                 [&](const float* c, uint32_t* b, cudaStream_t st) {

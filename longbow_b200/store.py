@@ -70,6 +70,52 @@ def RerankBatch(index: DenseIndex, query, candidateIDs, k: int):
     return [RankedResult(ID=int(i), Distance=float(x)) for x, i in zip(d[0], l[0]) if i >= 0]
 
 
+def SearchHybrid(gpuIndex, query, k: int, n_vectors: int, locations=None):
+    """ArrowHNSW.SearchHybrid (internal/store/hnsw_gpu.go:73-125): the GPU index generates k*10 candidates
+    (capped at the index length), labels are VectorIDs, ids whose location lookup fails or whose location is
+    tombstoned (BatchIdx == -1) are skipped, the first k survivors are returned with Score = GPU distance.
+
+    ``gpuIndex``: a ``gpu.Index`` (``Search(vector, k) -> (ids, distances)``).  ``locations``: optional
+    sequence / array of BatchIdx per VectorID (missing id or -1 = dropped), as ChunkedLocationStore answers."""
+    candidateCount = min(k * 10, n_vectors)
+    if candidateCount <= 0:
+        return []
+    ids, dists = gpuIndex.Search(np.asarray(query, np.float32), candidateCount)
+    out = []
+    for i, d in zip(ids, dists):
+        if len(out) >= k:
+            break
+        i = int(i)
+        if i < 0:
+            continue  # padding label -1 -> VectorID(0xFFFFFFFF) -> location miss (hnsw_gpu.go:108-111)
+        if locations is not None and (i >= len(locations) or int(locations[i]) == -1):
+            continue
+        out.append(SearchResult(ID=i, Score=float(d)))
+    return out
+
+
+def GenerateFilterBitsetDevice(d_column, op: int, value, d_bitmap=None, device: int = 0, stream=None):
+    """Device-resident form of GenerateFilterBitset: ``d_column`` is a CUDA tensor (int64 or float32), the bitmap
+    a CUDA int64 tensor of ceil(n/64) words (created zeroed when not given; AND-combined when given).  The result
+    can be passed straight to ``DenseIndex.search_device(..., allow=...)``."""
+    import torch
+    from .gpu import _stream_ptr
+    n = d_column.numel()
+    and_into = d_bitmap is not None
+    if d_bitmap is None:
+        d_bitmap = torch.zeros((n + 63) // 64, dtype=torch.int64, device=d_column.device)
+    lib = _lib.load()
+    if d_column.dtype == torch.int64:
+        check(lib.lb_filter_i64_device(device, d_column.data_ptr(), n, op, int(value), int(and_into),
+                                       d_bitmap.data_ptr(), _stream_ptr(stream)))
+    elif d_column.dtype == torch.float32:
+        check(lib.lb_filter_f32_device(device, d_column.data_ptr(), n, op, float(value), int(and_into),
+                                       d_bitmap.data_ptr(), _stream_ptr(stream)))
+    else:
+        raise TypeError("filter columns: int64 or float32")
+    return d_bitmap
+
+
 def MergeShardResults(distances, labels, k: int, device: int = 0):
     """Tail of ShardedHNSW.SearchVectors (internal/store/sharded_hnsw.go:432-503) /
     MergeSortedStreams (internal/store/result_merger.go:34-100), keyed on (distance, id).

@@ -560,3 +560,40 @@ def test_pq_train_validation():
         pq.train_codebooks(10, 3, 4, np.zeros((8, 10), np.float32))       # dims % M
     with pytest.raises(ValueError):
         pq.train_codebooks(8, 2, 16, np.zeros((4, 8), np.float32))        # n < k (kmeans.go:65-67)
+
+
+# ------------------------------------------------------------------ SearchHybrid mirror, device-resident predicates
+def test_search_hybrid_and_device_filters(lbgpu, oracle):
+    import torch
+    from longbow_b200 import store
+    rng = np.random.default_rng(8)
+    n, dim, k = 3000, 128, 10
+    db = rng.random((n, dim), dtype=np.float32)
+    q = rng.random(dim, dtype=np.float32)
+    g = lbgpu.NewIndexWithConfig(lbgpu.GPUConfig(DeviceID=0, Dimension=dim))
+    g.Add(list(range(n)), db)
+    wd, wl = oracle.search(L2, db, q[None, :], k * 10)
+    loc = np.zeros(n, np.int64)
+    loc[wl[0][:3]] = -1  # the three nearest are tombstoned at the location store
+    res = store.SearchHybrid(g, q, k, n, locations=loc)
+    want = [int(i) for i in wl[0] if loc[i] != -1][:k]
+    assert [r.ID for r in res] == want
+    assert np.array_equal(np.array([r.Score for r in res], np.float32), wd[0][3:3 + k])
+    g.Close()
+    # predicates evaluated on the device feed search_device without visiting the host
+    dev = torch.device("cuda", 0)
+    price = torch.from_numpy(rng.random(n).astype(np.float32)).to(dev)
+    cat = torch.from_numpy(rng.integers(0, 5, n)).to(dev)
+    bm = store.GenerateFilterBitsetDevice(price, 4, 0.5)            # price < 0.5
+    bm = store.GenerateFilterBitsetDevice(cat, 0, 2, d_bitmap=bm)   # AND category == 2
+    mask = (price.cpu().numpy() < 0.5) & (cat.cpu().numpy() == 2)
+    assert np.array_equal(bm.cpu().numpy().view(np.uint64), lbgpu.pack_bitmap(mask))
+    idx = lbgpu.DenseIndex(dim, np.float32, L2)
+    idx.add(db)
+    od = torch.empty((1, k), dtype=torch.float32, device=dev)
+    ol = torch.empty((1, k), dtype=torch.int64, device=dev)
+    idx.search_device(torch.from_numpy(q[None, :]).to(dev), k, od, ol, allow=bm)
+    torch.cuda.synchronize()
+    wd, wl = oracle.search(L2, db, q[None, :], k, allow=lbgpu.pack_bitmap(mask))
+    assert np.array_equal(ol.cpu().numpy(), wl) and np.array_equal(od.cpu().numpy(), wd)
+    idx.close()
