@@ -450,13 +450,33 @@ static int ensure_lo(lb_index* idx, cudaStream_t st) {
     return LB_OK;
 }
 
+static int exact_search_one(lb_index* idx, const void* d_q1, int k, const uint64_t* d_allow, float* d_out_d,
+                            int64_t* d_out_l, cudaStream_t st);
+
 // d_cert_flags [nq] / d_cert_count [1] (optional, device): certification of the coarse stage, see RescoreArgs
 static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const uint64_t* d_allow, float* d_dist,
                        int64_t* d_lab, cudaStream_t st, uint32_t* d_cert_flags = nullptr,
                        uint32_t* d_cert_count = nullptr) {
     if (nq == 0) return LB_OK;
     const int kc = coarse_k(k);
-    if (kc > 896) return fail(LB_ERR_UNSUPPORTED, "k too large for the fused selector (k <= 704)");
+    if (kc > 896) {
+        // k beyond the fused selector (k > 704): exhaustive exact kernel, one query at a time
+        if (k > 2048) return fail(LB_ERR_UNSUPPORTED, "k > 2048");
+        if (idx->size == 0) {
+            Scratch scr0(st);
+            uint64_t* merged0;
+            CK(scr0.get((void**)&merged0, 8));
+            CK(launch_unpack_topk(merged0, (int)nq, 0, k, 0, d_dist, d_lab, st));
+            return LB_OK;
+        }
+        const size_t qstride = (size_t)idx->dim * dtype_size(idx->dtype);
+        for (int64_t q = 0; q < nq; q++) {
+            int rc = exact_search_one(idx, (const char*)d_q + (size_t)q * qstride, k, d_allow, d_dist + (size_t)q * k,
+                                      d_lab + (size_t)q * k, st);
+            if (rc) return rc;
+        }
+        return LB_OK;
+    }
     Scratch scr(st);
     if (idx->size == 0) {
         uint64_t* merged;
@@ -639,33 +659,26 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
     return LB_OK;
 }
 
-// Exhaustive exact search of ONE query (device pointer): the reference's arithmetic for every row, bitmaps
-// applied, k smallest by (distance, row).  Slow (one thread per row over the whole index); used only for the
-// queries the certification flags.
-static int exact_search_one(lb_index* idx, const void* d_q1, int k, const uint64_t* d_allow, float* h_dist, int64_t* h_lab,
-                            cudaStream_t st) {
+// Exhaustive exact search of ONE query (device pointers in and out): the reference's arithmetic for every row,
+// bitmaps applied, k smallest by (distance, row).  Slow (one thread per row over the whole index); used for the
+// queries the certification flags and for k beyond the fused selector (e.g. SearchHybrid's k * 10 candidates,
+// internal/store/hnsw_gpu.go:85).
+static int exact_search_one(lb_index* idx, const void* d_q1, int k, const uint64_t* d_allow, float* d_out_d,
+                            int64_t* d_out_l, cudaStream_t st) {
     Scratch scr(st);
     const int64_t n = idx->size;
-    if (k > 4096) return fail(LB_ERR_UNSUPPORTED, "k > 4096");
+    if (k > 2048) return fail(LB_ERR_UNSUPPORTED, "k > 2048");
     int chunks = (int)((n + 4095) / 4096);
     if (chunks < 1) chunks = 1;
-    float *d_o, *d_od;
-    int64_t* d_oi;
+    float* d_o;
     uint64_t *p, *m;
     CK(scr.get((void**)&d_o, (size_t)n * 4));
-    CK(scr.get((void**)&d_od, (size_t)k * 4));
-    CK(scr.get((void**)&d_oi, (size_t)k * 8));
     CK(scr.get((void**)&p, (size_t)chunks * k * 8));
     CK(scr.get((void**)&m, (size_t)k * 8));
     CK(launch_batch_flat(idx->metric, idx->dtype, idx->rows, n, idx->dim, d_q1, d_o, 1, st));
     CK(launch_mask_rows(d_o, n, idx->tomb, (uint32_t)(idx->tomb_bits > 0xffffffffll ? 0xffffffffll : idx->tomb_bits),
                         (const uint32_t*)d_allow, st));
-    CK(launch_select_k(d_o, n, k, p, m, d_oi, d_od, st));
-    CK(cudaMemcpyAsync(h_dist, d_od, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_lab, d_oi, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (int j = 0; j < k; j++)
-        if (h_lab[j] >= 0) h_lab[j] += idx->id_base;
+    CK(launch_select_k(d_o, n, k, p, m, d_out_l, d_out_d, idx->id_base, st));
     return LB_OK;
 }
 
@@ -729,9 +742,12 @@ int lb_index_search(lb_index* idx, const void* queries, int64_t nq, int k, const
         const size_t qstride = (size_t)idx->dim * dtype_size(idx->dtype);
         for (int64_t q = 0; q < nq; q++) {
             if (!flags[(size_t)q]) continue;
-            rc = exact_search_one(idx, (const char*)d_q + (size_t)q * qstride, k, d_allow, distances + (size_t)q * k,
-                                  labels + (size_t)q * k, st);
+            rc = exact_search_one(idx, (const char*)d_q + (size_t)q * qstride, k, d_allow, d_d + (size_t)q * k,
+                                  d_l + (size_t)q * k, st);
             if (rc) return rc;
+            CK(cudaMemcpyAsync(distances + (size_t)q * k, d_d + (size_t)q * k, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(labels + (size_t)q * k, d_l + (size_t)q * k, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
         }
     }
     return LB_OK;
@@ -927,7 +943,7 @@ int lb_simd_adc_distance_batch(int device, const float* table, const uint8_t* fl
 int lb_select_k(int device, const float* distances, int64_t n, int k, int64_t* out_indices, float* out_distances) {
     if (k <= 0 || n < 0 || !out_indices) return fail(LB_ERR_INVALID, "bad argument");
     if (n > 0 && !distances) return fail(LB_ERR_INVALID, "NULL buffer");
-    if (k > 4096) return fail(LB_ERR_UNSUPPORTED, "k > 4096");
+    if (k > 2048) return fail(LB_ERR_UNSUPPORTED, "k > 2048");
     if (n > 0xfff00000ll) return fail(LB_ERR_UNSUPPORTED, "n too large");
     int rc = use_device(device);
     if (rc) return rc;
@@ -942,7 +958,7 @@ int lb_select_k(int device, const float* distances, int64_t n, int k, int64_t* o
     CK(scr.get((void**)&p, (size_t)chunks * k * 8));
     CK(scr.get((void**)&m, (size_t)k * 8));
     if (n > 0) CK(cudaMemcpyAsync(d_d, distances, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    CK(launch_select_k(d_d, n, k, p, m, d_oi, d_od, st));
+    CK(launch_select_k(d_d, n, k, p, m, d_oi, d_od, 0, st));
     CK(cudaMemcpyAsync(out_indices, d_oi, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
     if (out_distances) CK(cudaMemcpyAsync(out_distances, d_od, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

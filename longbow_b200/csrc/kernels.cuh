@@ -101,7 +101,7 @@ cudaError_t launch_rescore(const RescoreArgs& a, cudaStream_t st);
 cudaError_t launch_batch_flat(int metric, int dtype, const void* db, int64_t n, int dim, const void* query,
                               float* out, int negate_dot, cudaStream_t st);
 cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_partial, uint64_t* scratch_merged,
-                            int64_t* out_idx, float* out_d, cudaStream_t st);
+                            int64_t* out_idx, float* out_d, int64_t id_base, cudaStream_t st);
 cudaError_t launch_merge_topk(const float* in_d, const int64_t* in_l, int parts, int nq, int k_in, int k,
                               float* out_d, int64_t* out_l, cudaStream_t st);
 

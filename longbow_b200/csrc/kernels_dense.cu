@@ -966,7 +966,8 @@ __global__ void unpack_topk_kernel(const uint64_t* __restrict__ merged, int nq, 
 }
 
 cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_partial, uint64_t* scratch_merged,
-                            int64_t* out_idx, float* out_d, cudaStream_t st) {
+                            int64_t* out_idx, float* out_d, int64_t id_base, cudaStream_t st) {
+    if (k > MERGE_BUF / 2) return cudaErrorInvalidValue;  // the streaming merge keeps k entries and needs room to refill
     int kc = k;
     int chunks = (int)((n + MERGE_BUF - 1) / MERGE_BUF);
     if (chunks == 0) chunks = 1;
@@ -974,7 +975,7 @@ cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_
     count_launch();
     merge_partials_kernel<<<1, 256, 0, st>>>(scratch_partial, chunks, 1, kc, scratch_merged);
     count_launch();
-    unpack_topk_kernel<<<(k + 127) / 128, 128, 0, st>>>(scratch_merged, 1, kc, k, 0, out_d, out_idx);
+    unpack_topk_kernel<<<(k + 127) / 128, 128, 0, st>>>(scratch_merged, 1, kc, k, id_base, out_d, out_idx);
     count_launch();
     return cudaGetLastError();
 }

@@ -597,3 +597,32 @@ def test_search_hybrid_and_device_filters(lbgpu, oracle):
     wd, wl = oracle.search(L2, db, q[None, :], k, allow=lbgpu.pack_bitmap(mask))
     assert np.array_equal(ol.cpu().numpy(), wl) and np.array_equal(od.cpu().numpy(), wd)
     idx.close()
+
+
+# ------------------------------------------------------------------ k beyond the fused selector
+@pytest.mark.parametrize("dtype,metric", [(np.float32, L2), (np.float16, COS), (np.int8, DOT)])
+def test_large_k_exact_path(lbgpu, oracle, dtype, metric):
+    """SearchHybrid asks the GPU index for k * 10 candidates (internal/store/hnsw_gpu.go:85): k = 100 means 1000
+    neighbours, beyond the fused selector (k <= 704).  Those searches take the exhaustive exact kernel."""
+    rng = np.random.default_rng(123)
+    n, dim, nq, k = 6000, 64, 3, 1000
+    db, q = make_db(rng, n, dim, dtype), make_db(rng, nq, dim, dtype)
+    idx = lbgpu.DenseIndex(dim, dtype, metric)
+    idx.add(db)
+    tomb = random_bitmap(rng, n, 0.1)
+    idx.set_tombstones(tomb)
+    gd, gl = idx.search(q, k)
+    wd, wl = oracle.search(metric, db, q, k, tomb=lbgpu.pack_bitmap(tomb))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "k = 1000")
+    gd, gl = idx.search(q[:1], 2048)
+    wd, wl = oracle.search(metric, db, q[:1], 2048, tomb=lbgpu.pack_bitmap(tomb))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "k = 2048")
+    idx.close()
+    if dtype == np.float32:
+        from longbow_b200 import store
+        g = lbgpu.NewIndexWithConfig(lbgpu.GPUConfig(DeviceID=0, Dimension=dim))
+        g.Add(list(range(n)), db)
+        res = store.SearchHybrid(g, q[0], 100, n)          # 1000 candidates through faiss_gpu_index_search
+        wd, wl = oracle.search(L2, db, q[:1], 100)
+        assert [r.ID for r in res] == [int(i) for i in wl[0]]
+        g.Close()
