@@ -718,8 +718,7 @@ int lb_index_search(lb_index* idx, const void* queries, int64_t nq, int k, const
     if (idx->max_norm2 != nullptr && g_opt_certify.load(std::memory_order_relaxed)) {
         CK(scr.get((void**)&d_flags, (size_t)nq * 4));
         CK(scr.get((void**)&d_count, 4));
-        CK(cudaMemsetAsync(d_count, 0, 4, st));
-        CK(cudaMemsetAsync(d_flags, 0, (size_t)nq * 4, st));
+        CK(cudaMemsetAsync(d_count, 0, 4, st));  // (every flag is written by its re-score block)
     }
     rc = search_core(idx, d_q, nq, k, d_allow, d_d, d_l, st, d_flags, d_count);
     if (rc) { cudaStreamSynchronize(st); return rc; }
