@@ -626,3 +626,23 @@ def test_large_k_exact_path(lbgpu, oracle, dtype, metric):
         wd, wl = oracle.search(L2, db, q[:1], 100)
         assert [r.ID for r in res] == [int(i) for i in wl[0]]
         g.Close()
+
+
+# ------------------------------------------------------------------ short rows on the tensor-core path
+@pytest.mark.parametrize("dtype,dims", [(np.float32, (4, 8, 12, 16, 24)), (np.float16, (8, 16, 24, 40)), (np.int8, (16, 32, 48))])
+def test_tensor_core_short_rows(lbgpu, oracle, scan_mode, dtype, dims):
+    """Rows shorter than one 128-byte k-block (TMA boxes reach past the row: zero fill) on the forced and the
+    automatic path, several query blocks."""
+    rng = np.random.default_rng(321)
+    for dim in dims:
+        n, nq, k = 5000, 260, 10
+        db, q = make_db(rng, n, dim, dtype), make_db(rng, nq, dim, dtype)
+        for metric in ((L2, DOT) if dtype == np.int8 else (L2, COS, DOT)):
+            idx = lbgpu.DenseIndex(dim, dtype, metric)
+            idx.add(db)
+            wd, wl = oracle.search(metric, db, q, k)
+            for mode in (2, 0):
+                scan_mode(mode)
+                gd, gl = idx.search(q, k)
+                assert_topk_equal(gd, gl, wd, wl, 0.0, f"dim {dim} {dtype.__name__} metric {metric} mode {mode}")
+            idx.close()
