@@ -646,3 +646,27 @@ def test_tensor_core_short_rows(lbgpu, oracle, scan_mode, dtype, dims):
                 gd, gl = idx.search(q, k)
                 assert_topk_equal(gd, gl, wd, wl, 0.0, f"dim {dim} {dtype.__name__} metric {metric} mode {mode}")
             idx.close()
+
+
+# ------------------------------------------------------------------ growth, query chunking
+def test_grow_after_search_and_query_chunks(lbgpu, oracle):
+    """fp32 index: the 3xTF32 low parts are built by the first search and must follow later adds / reserves;
+    more than 4096 queries are processed in chunks (certification flags included)."""
+    rng = np.random.default_rng(55)
+    dim, k = 64, 5
+    db = rng.random((9000, dim), dtype=np.float32)
+    q = rng.random((5000, dim), dtype=np.float32)
+    idx = lbgpu.DenseIndex(dim, np.float32, L2)
+    idx.add(db[:3000])
+    gd, gl = idx.search(q[:100], k)
+    wd, wl = oracle.search(L2, db[:3000], q[:100], k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "first third")
+    idx.add(db[3000:6000])          # grows the mirror (and the low parts on the next search)
+    idx.reserve(9000)
+    idx.add(db[6000:])
+    assert len(idx) == 9000
+    gd, gl = idx.search(q, k)       # 5000 queries: two chunks
+    wd, wl = oracle.search(L2, db, q, k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "all rows, 5000 queries")
+    assert idx.last_uncertified() == 0
+    idx.close()
