@@ -95,14 +95,14 @@ int lb_index_set_id_base(lb_index *idx, int64_t id_base);
 int lb_index_set_tombstones(lb_index *idx, const uint64_t *bitmap, int64_t nbits);
 int lb_index_set_tombstones_device(lb_index *idx, const uint64_t *d_bitmap, int64_t nbits, void *stream);
 
-/* k <= 704 uses the fused scan + selector; 704 < k <= 2048 (e.g. SearchHybrid's k*10 candidates,
- * internal/store/hnsw_gpu.go:85) takes an exhaustive exact kernel, one query at a time; larger k is
- * LB_ERR_UNSUPPORTED.
- * Batched exact k-NN: nq queries (row-major [nq*dim], same dtype as the index) -> [nq*k]
+/* Batched exact k-NN: nq queries (row-major [nq*dim], same dtype as the index) -> [nq*k]
  * distances and labels.  allow: optional predicate bitmap over local rows shared by the
  * batch (one Filters set per VectorSearchRequest, internal/query/requests.go:4-20), nbits
  * must cover the index.  Replaces the per-query loop at
- * internal/store/vector_search_action.go:73. */
+ * internal/store/vector_search_action.go:73.
+ * k <= 704 uses the fused scan + selector (one query: HBM-bound streaming scan; more: tensor-core scan);
+ * 704 < k <= 2048 (e.g. SearchHybrid's k*10 candidates, internal/store/hnsw_gpu.go:85) takes an
+ * exhaustive exact kernel, one query at a time; larger k is LB_ERR_UNSUPPORTED. */
 int lb_index_search(lb_index *idx, const void *queries, int64_t nq, int k, const uint64_t *allow,
                     float *distances, int64_t *labels);
 int lb_index_search_device(lb_index *idx, const void *d_queries, int64_t nq, int k,
