@@ -52,9 +52,9 @@ def _worker(rank, world, port, ret):
 def test_two_rank_shard_gather_merge():
     import torch.multiprocessing as mp
     port = _free_port()
-    mgr = mp.Manager()
-    ret = mgr.dict()
     ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    ret = mgr.dict()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
     for p in procs:
         p.start()
