@@ -268,7 +268,7 @@ def main():
         # The reference serves searches from many goroutines under a read lock (internal/gpu/faiss_gpu.go:108);
         # the C ABI is thread-safe the same way.  Two concurrent callers let one call's PCIe copies overlap the
         # other's kernels.  Every step still does its own H2D of the queries and D2H of the results.
-        callers = 2
+        callers = int(os.environ.get("LB_BENCH_CALLERS", "2"))
         bufs = [(torch.empty((NQ, K), dtype=torch.float32).pin_memory().numpy(),
                  torch.empty((NQ, K), dtype=torch.int64).pin_memory().numpy()) for _ in range(callers)]
         last = [None] * callers
