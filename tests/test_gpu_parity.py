@@ -670,3 +670,19 @@ def test_grow_after_search_and_query_chunks(lbgpu, oracle):
     assert_topk_equal(gd, gl, wd, wl, 0.0, "all rows, 5000 queries")
     assert idx.last_uncertified() == 0
     idx.close()
+
+
+@pytest.mark.parametrize("dims,M,K,n", [(32, 4, 16, 100), (268, 4, 16, 34), (91, 91, 1, 2), (64, 8, 256, 600)])
+def test_pq_train_reference_fuzz_shapes(oracle, dims, M, K, n):
+    """Shapes and the deterministic data generator of the reference's fuzz harness and its seed corpus
+    (internal/pq/fuzz_test.go:9-30, internal/pq/testdata/fuzz/FuzzPQEncoder_TrainAndEncode/*): odd sub-vector
+    length 67, K = 1 with two samples, many empty clusters (the data is a ramp, so rows repeat)."""
+    from longbow_b200 import pq
+    data = np.array([[np.float32(i + j) / np.float32(n) for j in range(dims)] for i in range(n)], np.float32)
+    rng = np.random.default_rng(dims + n)
+    init = np.stack([rng.permutation(n)[:K] for _ in range(M)]).astype(np.int32)
+    cb, iters = pq.train_codebooks(dims, M, K, data, init_idx=init)
+    wcb, witers = oracle.pq_train(data, M, K, init)
+    assert np.array_equal(iters, witers)
+    assert np.array_equal(cb, wcb)
+    assert cb.shape == (M, K, dims // M)
