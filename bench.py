@@ -253,6 +253,7 @@ def main():
 
     # ---- end-to-end arm: host buffers through the C ABI, H2D + D2H inside the timed region
     e2e = None
+    checks = {}  # result cross-checks between the arms (reported, and shouted about on stderr if one fails)
     if world == 1:
         hq = qs.pin_memory().numpy()
         hd = torch.empty((NQ, K), dtype=torch.float32).pin_memory().numpy()
@@ -264,7 +265,7 @@ def main():
         for s in range(steps):
             sidx.index.search_into(hq[warm + s], K, hd, hl)
         dt1 = time.perf_counter() - t0
-        assert np.array_equal(hl, check_l), "host-API and device-API results differ"
+        checks["host_api_equals_device_api"] = bool(np.array_equal(hl, check_l))
         # The reference serves searches from many goroutines under a read lock (internal/gpu/faiss_gpu.go:108);
         # the C ABI is thread-safe the same way.  Two concurrent callers let one call's PCIe copies overlap the
         # other's kernels.  Every step still does its own H2D of the queries and D2H of the results.
@@ -292,7 +293,7 @@ def main():
         dt = run_callers(warm, steps)
         # the last step of caller 0 must equal a fresh single-caller answer for the same batch
         sidx.index.search_into(hq[last[0]], K, hd, hl)
-        assert np.array_equal(hl, bufs[0][1]) and np.array_equal(hd, bufs[0][0]), "concurrent callers disagree"
+        checks["concurrent_callers_agree"] = bool(np.array_equal(hl, bufs[0][1]) and np.array_equal(hd, bufs[0][0]))
         e2e = {"value": NQ * steps / dt, "unit": "queries/s", "h2d_bytes_per_step": NQ * DIM * 2,
                "d2h_bytes_per_step": NQ * K * 12, "ms_per_step": dt / steps * 1e3, "callers": callers,
                "single_caller_value": NQ * steps / dt1, "single_caller_ms_per_step": dt1 / steps * 1e3}
@@ -399,7 +400,11 @@ def main():
                        "streams": ("batches alternate between 2 CUDA streams (tail kernels overlap the next scan)"
                                    if world == 1 else "one stream per rank, NCCL exchange in order")},
             "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof,
+            "checks": checks,
         }
+        for name, ok in checks.items():
+            if not ok:
+                print(f"[bench] CHECK FAILED: {name}", file=sys.stderr, flush=True)
         if not args.no_cpu and world == 1:
             out["cpu_baseline"] = cpu_baseline(db.numpy(), qs[0].numpy(), K)
         emit(out)
