@@ -107,3 +107,14 @@ def test_simd_mirror_validation():
     with pytest.raises(simd.SimdError, match="invalid m"):
         simd.ADCDistanceBatch(np.zeros(256, np.float32), np.zeros(4, np.uint8), 0, np.zeros(1, np.float32))
     simd.EuclideanDistanceBatchFlat(q, np.zeros(0, np.float32), 0, 4, np.zeros(0, np.float32))  # n == 0: no-op
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 on its own (no C++ / CUDA / torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "longbow_b200.h")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
