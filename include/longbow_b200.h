@@ -109,6 +109,21 @@ int lb_index_search_device(lb_index *idx, const void *d_queries, int64_t nq, int
                            const uint64_t *d_allow, float *d_distances, int64_t *d_labels,
                            void *stream);
 
+/* lb_index_search_device + certification outputs, still without any host synchronisation:
+ * d_uncert_flags [nq] receives 1 for every query whose coarse-stage margin did not cover the coarse error bound
+ * (a row outside its candidate set might belong to the top-k) and 0 otherwise; *d_uncert_count is INCREMENTED
+ * by the number of such queries (the caller zeroes it, and may let it accumulate over many batches).  Either
+ * may be NULL.  Nothing is re-done here: the caller reads the count when convenient and repairs flagged
+ * queries with lb_index_search_exact_device.  (lb_index_search, the host entry point, does both itself.) */
+int lb_index_search_device_cert(lb_index *idx, const void *d_queries, int64_t nq, int k, const uint64_t *d_allow,
+                                float *d_distances, int64_t *d_labels, uint32_t *d_uncert_flags,
+                                uint32_t *d_uncert_count, void *stream);
+/* Exhaustive exact search -- the reference's arithmetic for every live row, no coarse stage -- of the queries
+ * whose HOST flag h_flags[q] is non-zero (h_flags NULL = all), written into the same [nq*k] layout; the other
+ * rows of the outputs are left untouched.  Queries and outputs are device pointers. */
+int lb_index_search_exact_device(lb_index *idx, const void *d_queries, int64_t nq, int k, const uint64_t *d_allow,
+                                 const uint32_t *h_flags, float *d_distances, int64_t *d_labels, void *stream);
+
 /* Re-rank: per query a list of c candidate VectorIDs (uint32, internal/core/types.go:7);
  * ids that are out of range, tombstoned or fail `allow` are dropped; exact distances of the
  * rest; ascending; first k.  ArrowHNSW.RerankBatch / processChunkInternal. */
@@ -125,8 +140,8 @@ int lb_index_distances(lb_index *idx, const void *query, float *out);
 /* Number of queries of the last lb_index_search (host) call on this handle whose coarse-stage result could not
  * be CERTIFIED -- the margin between the kc-th coarse key and the k-th exact distance did not cover the coarse
  * error bound, so a row outside the candidate set might have belonged to the top-k -- and which were therefore
- * recomputed by an exhaustive exact scan before returning (DESIGN.md 4.1 "certification").  The *_device entry
- * points do not certify. */
+ * recomputed by an exhaustive exact scan before returning (DESIGN.md 4.1 "certification").
+ * lb_index_search_device does not certify; lb_index_search_device_cert reports the flags on the device. */
 int64_t lb_index_last_uncertified(const lb_index *idx);
 /* Diagnostics: the COARSE ranking keys the tensor-core scan computes for rows [0, n_rows) of nq queries
  * (out: [nq][n_rows]): |x|^2 - 2 q.x (L2), -q.x/|x| (cosine), -q.x (dot).  They only rank candidates -- every
@@ -157,6 +172,42 @@ int lb_merge_topk(int device, const float *distances, const int64_t *labels, int
 int lb_merge_topk_device(int device, const float *d_distances, const int64_t *d_labels, int parts,
                          int64_t nq, int k_in, int k, float *d_out_distances, int64_t *d_out_labels,
                          void *stream);
+
+/* Same merge over PACKED per-part records, the layout of the multi-GPU exchange (one all-gather or one peer
+ * push per batch): part p's record starts at d_records + p * part_stride and holds [nq*k_in] f32 distances at
+ * offset 0 and [nq*k_in] i64 labels at label_offset (both multiples of 8 bytes). */
+int lb_merge_topk_packed_device(int device, const void *d_records, size_t part_stride, size_t label_offset,
+                                int parts, int64_t nq, int k_in, int k, float *d_out_distances,
+                                int64_t *d_out_labels, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3b. Multi-GPU exchange: all-gather of the per-GPU top-k records + merge, as our own kernels over
+ *     NVLink peer memory (replaces the concat + sort tail of ShardedHNSW.SearchVectors,
+ *     internal/store/sharded_hnsw.go:432-503, and MergeSortedStreams, result_merger.go:34-100).
+ *     One lb_exchange per rank (= GPU).  Ranks in different processes connect through CUDA IPC handles
+ *     shipped over any host channel (lb_exchange_handle / lb_exchange_connect_ipc); ranks in one process
+ *     connect directly (lb_exchange_connect_local).  Per batch, on every rank and in the same order:
+ *       lb_exchange_slot            -> where the local search writes its [nq*k] distances / labels
+ *       (local search on `stream`)
+ *       lb_exchange_all_gather_merge -> push to all peers, signal, wait for all records, merge -> outputs
+ *     All of it is enqueued on the caller's stream; nothing synchronises the host.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct lb_exchange lb_exchange;
+int lb_exchange_create(int device, int rank, int world, size_t max_record_bytes, lb_exchange **out);
+void lb_exchange_free(lb_exchange *ex);
+/* 64-byte CUDA IPC handle of this rank's receive buffer. */
+int lb_exchange_handle(lb_exchange *ex, void *handle64);
+/* handles: [world][64] bytes, entry r = rank r's handle (own entry ignored). */
+int lb_exchange_connect_ipc(lb_exchange *ex, const void *handles);
+/* all: [world] exchange handles of this process, entry r = rank r (enables peer access as needed). */
+int lb_exchange_connect_local(lb_exchange *ex, lb_exchange *const *all);
+/* Starts the next batch: device pointers of the local record (inside this rank's own receive slot).
+ * Record size = round16(nq*k*4) + nq*k*8 bytes <= max_record_bytes. */
+int lb_exchange_slot(lb_exchange *ex, int64_t nq, int k, float **d_distances, int64_t **d_labels);
+int lb_exchange_all_gather_merge(lb_exchange *ex, int64_t nq, int k_in, int k, float *d_out_distances,
+                                 int64_t *d_out_labels, void *stream);
+/* LB_OK unless a merge gave up waiting for a peer (synchronises the device). */
+int lb_exchange_error(lb_exchange *ex);
 
 /* ------------------------------------------------------------------------------------------
  * 4. Product quantisation (internal/pq): ADC LUT build, ADC code scan + top-k', fp32 re-rank.

@@ -43,6 +43,8 @@ SIGNATURES = {
     "lb_index_set_tombstones_device": (i32, [vp, vp, i64, vp]),
     "lb_index_search": (i32, [vp, vp, i64, i32, vp, vp, vp]),
     "lb_index_search_device": (i32, [vp, vp, i64, i32, vp, vp, vp, vp]),
+    "lb_index_search_device_cert": (i32, [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]),
+    "lb_index_search_exact_device": (i32, [vp, vp, i64, i32, vp, vp, vp, vp, vp]),
     "lb_index_rerank": (i32, [vp, vp, i64, vp, i32, i32, vp, vp, vp]),
     "lb_index_rerank_device": (i32, [vp, vp, i64, vp, i32, i32, vp, vp, vp, vp]),
     "lb_index_distances": (i32, [vp, vp, vp]),
@@ -53,6 +55,15 @@ SIGNATURES = {
     "lb_select_k": (i32, [i32, vp, i64, i32, vp, vp]),
     "lb_merge_topk": (i32, [i32, vp, vp, i32, i64, i32, i32, vp, vp]),
     "lb_merge_topk_device": (i32, [i32, vp, vp, i32, i64, i32, i32, vp, vp, vp]),
+    "lb_merge_topk_packed_device": (i32, [i32, vp, sz, sz, i32, i64, i32, i32, vp, vp, vp]),
+    "lb_exchange_create": (i32, [i32, i32, i32, sz, C.POINTER(vp)]),
+    "lb_exchange_free": (None, [vp]),
+    "lb_exchange_handle": (i32, [vp, vp]),
+    "lb_exchange_connect_ipc": (i32, [vp, vp]),
+    "lb_exchange_connect_local": (i32, [vp, C.POINTER(vp)]),
+    "lb_exchange_slot": (i32, [vp, i64, i32, C.POINTER(vp), C.POINTER(vp)]),
+    "lb_exchange_all_gather_merge": (i32, [vp, i64, i32, i32, vp, vp, vp]),
+    "lb_exchange_error": (i32, [vp]),
     "lb_pq_create": (i32, [i32, vp, sz, C.POINTER(vp)]),
     "lb_pq_free": (None, [vp]),
     "lb_pq_params": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),

@@ -71,6 +71,12 @@ static int use_device(int device) {
     return LB_OK;
 }
 
+// the same helpers for the other translation units with C-ABI entry points (exchange.cu, shard.cu, pq_scan.cu ...)
+int api_fail(int code, const char* what) { return fail(code, what); }
+int api_fail_cuda(cudaError_t e, const char* where) { return fail_cuda(e, where); }
+int api_use_device(int device) { return use_device(device); }
+int api_sm_count(int device) { return (device >= 0 && device < 64) ? g_dev[device].sm_count : 0; }
+
 // stream-ordered scratch
 struct Scratch {
     cudaStream_t st;
@@ -130,7 +136,7 @@ struct lb_index {
     void* rows = nullptr;  // [capacity][dim]
     float* aux = nullptr;  // [capacity + 256] coarse-key auxiliaries
     float* nrm = nullptr;  // [capacity] cosine only: exact |x|^2 in reference lane order
-    float* max_norm2 = nullptr;  // device scalar: max |x|^2 over the rows (certification bound), float dtypes only
+    float* max_norm2 = nullptr;  // device scalar: max |x|^2 over the rows (certification bound)
     float* lo = nullptr;   // fp32 only, built on first tensor-core search: x - tf32(x) for the 3xTF32 scan
     int64_t lo_rows = 0, lo_cap = 0;
     std::mutex lo_mu;
@@ -295,7 +301,7 @@ int lb_index_create(int device, int dim, int dtype, int metric, lb_index** out) 
     if (!idx) return fail(LB_ERR_OOM, "host allocation failed");
     idx->device = device; idx->dim = dim; idx->dtype = dtype; idx->metric = metric;
     idx->sm_count = g_dev[device].sm_count;
-    if (dtype != DT_I8) {
+    {
         cudaError_t e = cudaMalloc((void**)&idx->max_norm2, 4);
         if (e == cudaSuccess) e = cudaMemset(idx->max_norm2, 0, 4);
         if (e != cudaSuccess) { if (idx->max_norm2) cudaFree(idx->max_norm2); delete idx; return fail_cuda(e, "cudaMalloc(stats)"); }
@@ -508,6 +514,7 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         uint64_t *partial, *merged;
         int parts;
         bool merged_done = false;
+        bool simt_keys = false;  // the SIMT scan ranks L2 by |q - x|^2, the other scans by |x|^2 - 2 q.x
         if (use_stream) {
             a.debug = 0;
             // bootstrap sample ~1% of the rows (2048..8192), skipped for small indexes
@@ -630,6 +637,7 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
             a.partial = partial;
             ProfScope prof(st, (double)cq * (double)idx->size);
             CK(launch_dense_scan_simt(a, st));
+            simt_keys = true;
         }
         if (merged_done) {
         } else if (parts > 1) {
@@ -645,13 +653,21 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
         r.dim = idx->dim; r.queries = a.queries; r.nq = cq; r.packed = merged; r.ids32 = nullptr;
         r.c = kc; r.k = k; r.tomb = nullptr; r.tomb_bits = 0; r.allow = nullptr; r.id_base = idx->id_base;
         r.out_d = d_dist + (size_t)qo * k; r.out_l = d_lab + (size_t)qo * k; r.negate_dot = 1;
-        if (d_cert_flags != nullptr && idx->max_norm2 != nullptr) {
+        // int8 coarse keys are integers carried in fp32: exact (nothing to certify, ties are ordered by the packed
+        // (key, id) compare) while |x|^2 + 2|q.x| < 2^24, i.e. dim * 127^2 * 3 < 2^24; longer int8 rows round and
+        // are certified like the float types
+        const bool keys_exact = idx->dtype == DT_I8 && (int64_t)idx->dim * 16129 * 3 < (1 << 24);
+        if ((d_cert_flags != nullptr || d_cert_count != nullptr) && keys_exact) {
+            if (d_cert_flags) CK(cudaMemsetAsync(d_cert_flags + qo, 0, (size_t)cq * 4, st));
+        } else if (d_cert_flags != nullptr && idx->max_norm2 != nullptr) {
             r.cert_flags = d_cert_flags + qo; r.cert_count = d_cert_count; r.max_norm2 = idx->max_norm2;
+            r.key_space = (simt_keys && idx->metric == METRIC_L2) ? 1 : 0;
             // coarse-key error bound relative to |q||x|: truncating fp32 accumulation over dim terms (measured
             // ~4e-6 at dim 256, test_coarse_keys_accuracy), plus the 3xTF32 operand residue for fp32 rows
             float beta = (float)idx->dim * 1.2e-7f;
             if (beta < 8e-6f) beta = 8e-6f;
             if (idx->dtype == DT_F32) beta += 1e-6f;
+            if (idx->dtype == DT_I8) beta = 1.2e-7f;  // integer products, one fp32 rounding of the total
             r.beta = beta;
         }
         CK(launch_rescore(r, st));
@@ -690,6 +706,57 @@ int lb_index_search_device(lb_index* idx, const void* d_queries, int64_t nq, int
     int rc = use_device(idx->device);
     if (rc) return rc;
     return search_core(idx, d_queries, nq, k, d_allow, d_distances, d_labels, (cudaStream_t)stream);
+}
+
+int lb_index_search_device_cert(lb_index* idx, const void* d_queries, int64_t nq, int k, const uint64_t* d_allow,
+                                float* d_distances, int64_t* d_labels, uint32_t* d_uncert_flags,
+                                uint32_t* d_uncert_count, void* stream) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    if (k <= 0 || nq < 0) return fail(LB_ERR_INVALID, "k must be positive and nq non-negative");
+    if (nq > 0 && (!d_queries || !d_distances || !d_labels)) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nq == 0) return LB_OK;
+    if (d_uncert_flags == nullptr && d_uncert_count == nullptr)
+        return search_core(idx, d_queries, nq, k, d_allow, d_distances, d_labels, st);
+    if (coarse_k(k) > 896 || idx->size == 0) {  // exhaustive exact path: nothing to certify
+        if (d_uncert_flags) CK(cudaMemsetAsync(d_uncert_flags, 0, (size_t)nq * 4, st));
+        return search_core(idx, d_queries, nq, k, d_allow, d_distances, d_labels, st);
+    }
+    // the re-score kernel needs both outputs; a caller that wants only one gets the other from scratch
+    Scratch scr(st);
+    uint32_t* flags = d_uncert_flags;
+    uint32_t* count = d_uncert_count;
+    if (!flags) CK(scr.get((void**)&flags, (size_t)nq * 4));
+    if (!count) { CK(scr.get((void**)&count, 4)); CK(cudaMemsetAsync(count, 0, 4, st)); }
+    return search_core(idx, d_queries, nq, k, d_allow, d_distances, d_labels, st, flags, count);
+}
+
+int lb_index_search_exact_device(lb_index* idx, const void* d_queries, int64_t nq, int k, const uint64_t* d_allow,
+                                 const uint32_t* h_flags, float* d_distances, int64_t* d_labels, void* stream) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    if (k <= 0 || nq < 0) return fail(LB_ERR_INVALID, "k must be positive and nq non-negative");
+    if (k > 2048) return fail(LB_ERR_UNSUPPORTED, "k > 2048");
+    if (nq > 0 && (!d_queries || !d_distances || !d_labels)) return fail(LB_ERR_INVALID, "NULL buffer");
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t qstride = (size_t)idx->dim * dtype_size(idx->dtype);
+    for (int64_t q = 0; q < nq; q++) {
+        if (h_flags && !h_flags[q]) continue;
+        if (idx->size == 0) {
+            Scratch scr0(st);
+            uint64_t* m0;
+            CK(scr0.get((void**)&m0, 8));
+            CK(launch_unpack_topk(m0, 1, 0, k, 0, d_distances + (size_t)q * k, d_labels + (size_t)q * k, st));
+            continue;
+        }
+        rc = exact_search_one(idx, (const char*)d_queries + (size_t)q * qstride, k, d_allow, d_distances + (size_t)q * k,
+                              d_labels + (size_t)q * k, st);
+        if (rc) return rc;
+    }
+    return LB_OK;
 }
 
 int lb_index_search(lb_index* idx, const void* queries, int64_t nq, int k, const uint64_t* allow, float* distances,
@@ -972,6 +1039,21 @@ int lb_merge_topk_device(int device, const float* d_distances, const int64_t* d_
     if ((int64_t)parts * k_in > 16384) return fail(LB_ERR_UNSUPPORTED, "parts * k_in > 16384");
     CK(launch_merge_topk(d_distances, d_labels, parts, (int)nq, k_in, k, d_out_distances, d_out_labels,
                          (cudaStream_t)stream));
+    return LB_OK;
+}
+
+int lb_merge_topk_packed_device(int device, const void* d_records, size_t part_stride, size_t label_offset, int parts,
+                                int64_t nq, int k_in, int k, float* d_out_distances, int64_t* d_out_labels,
+                                void* stream) {
+    if (parts <= 0 || k_in <= 0 || k <= 0 || nq < 0 || !d_records) return fail(LB_ERR_INVALID, "bad argument");
+    if ((part_stride & 7) || (label_offset & 7) || label_offset < (size_t)nq * k_in * 4 ||
+        part_stride < label_offset + (size_t)nq * k_in * 8)
+        return fail(LB_ERR_INVALID, "record layout: [nq*k_in f32 | pad to 8 | nq*k_in i64] per part");
+    int rc = use_device(device);
+    if (rc) return rc;
+    if ((int64_t)parts * k_in > 16384) return fail(LB_ERR_UNSUPPORTED, "parts * k_in > 16384");
+    CK(launch_merge_topk_strided(d_records, part_stride, (const char*)d_records + label_offset, part_stride, parts,
+                                 (int)nq, k_in, k, d_out_distances, d_out_labels, (cudaStream_t)stream));
     return LB_OK;
 }
 

@@ -284,10 +284,7 @@ static cudaError_t launch_stream_nq(const StreamArgs& a, int grid, cudaStream_t 
 #define LB_ST(LPR_, U_)                                                                                      \
     {                                                                                                        \
         auto kern = dense_scan_stream<T, METRIC, NQ, LPR_, U_>;                                              \
-        if (smem > 48 * 1024) {                                                                              \
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                  \
-        }                                                                                                    \
+        LB_SMEM_OPTIN(kern);                                                                                 \
         kern<<<grid, ST_THREADS, smem, st>>>(a);                                                             \
     }
     if (row_bytes >= 384) LB_ST(32, (NQ == 1 ? 8 : NQ == 2 ? 4 : 2)) else LB_ST(8, (NQ <= 2 ? 8 : 4))

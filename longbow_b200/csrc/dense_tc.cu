@@ -1031,9 +1031,8 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
 #define LB_TC2(KIND_, METRIC_, CAP_, CG_)                                                                      \
     {                                                                                                          \
         auto kern = dense_scan_tc<KIND_, METRIC_, CAP_, CG_>;                                                  \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        if (e != cudaSuccess) return e;                                                                        \
-        e = cudaLaunchKernelEx(&cfg, kern, mq, mdb, mqlo, mdblo, a);                                                        \
+        LB_SMEM_OPTIN(kern);                                                                                   \
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mdb, mqlo, mdblo, a);                                                        \
         if (e != cudaSuccess) return e;                                                                        \
     }
 #define LB_TC1(KIND_, METRIC_, CAP_)                                                                           \

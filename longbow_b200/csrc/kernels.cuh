@@ -1,8 +1,37 @@
 // kernels.cuh -- host-side launch interface between api.cu and the kernel translation units.
 #pragma once
+#include <atomic>
+
 #include "common.cuh"
 
 namespace lb {
+
+// Dynamic shared-memory opt-in.  cudaFuncAttributeMaxDynamicSharedMemorySize is per-function, per-device GLOBAL
+// state and searches run concurrently (Go read lock, faiss_gpu.go:108), so it is raised to the device maximum
+// ONCE per (kernel, device) and never written with a per-call size (two callers with different k could
+// otherwise interleave "set small" / "launch large").  `done` is a bit per device.
+inline cudaError_t smem_optin(const void* func, std::atomic<uint64_t>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, func);
+    if (e != cudaSuccess) return e;
+    int optin = 0;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+    if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+    return cudaSuccess;
+}
+#define LB_SMEM_OPTIN(kern)                                                     \
+    do {                                                                        \
+        static std::atomic<uint64_t> lb_done_{0};                               \
+        cudaError_t lb_e_ = ::lb::smem_optin((const void*)(kern), lb_done_);    \
+        if (lb_e_ != cudaSuccess) return lb_e_;                                 \
+    } while (0)
 
 extern bool g_rescore_legacy;
 extern bool g_tc_pair;
@@ -68,6 +97,7 @@ struct RescoreArgs {
     uint32_t* cert_count = nullptr;
     const float* max_norm2 = nullptr;  // device scalar: max |x|^2 over the index (float bits, non-negative)
     float beta = 0.f;                  // relative coarse-key error bound (of |q||x|)
+    int key_space = 0;                 // see CertArgs
 };
 
 struct CertArgs {
@@ -75,6 +105,7 @@ struct CertArgs {
     uint32_t* count;
     const float* max_norm2;
     float beta;
+    int key_space;  // 0: expanded keys (|x|^2 - 2 q.x, tensor-core / streaming scans); 1: difference form |q - x|^2 (SIMT L2)
 };
 
 cudaError_t launch_row_maxnorm(int dtype, const void* db, int64_t n, int dim, int64_t row0, float* max_norm2,
@@ -102,6 +133,13 @@ cudaError_t launch_batch_flat(int metric, int dtype, const void* db, int64_t n, 
                               float* out, int negate_dot, cudaStream_t st);
 cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_partial, uint64_t* scratch_merged,
                             int64_t* out_idx, float* out_d, int64_t id_base, cudaStream_t st);
+cudaError_t launch_merge_topk_strided(const void* in_d_base, size_t stride_d, const void* in_l_base, size_t stride_l,
+                                      int parts, int nq, int k_in, int k, float* out_d, int64_t* out_l,
+                                      cudaStream_t st);
+cudaError_t launch_merge_topk_wait(const void* in_d_base, size_t stride_d, const void* in_l_base, size_t stride_l,
+                                   int parts, int nq, int k_in, int k, float* out_d, int64_t* out_l,
+                                   const uint32_t* wait_flags, uint32_t wait_seq, int rank, uint32_t* err,
+                                   cudaStream_t st);
 cudaError_t launch_merge_topk(const float* in_d, const int64_t* in_l, int parts, int nq, int k_in, int k,
                               float* out_d, int64_t* out_l, cudaStream_t st);
 

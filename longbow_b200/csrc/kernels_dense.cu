@@ -257,8 +257,7 @@ template <typename T, int METRIC, int TQ>
 static cudaError_t launch_scan_tq(const ScanArgs& a, cudaStream_t st) {
     auto kern = dense_scan_simt<T, METRIC, TQ>;
     size_t smem = dense_scan_simt_smem(TQ, a.cap);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    LB_SMEM_OPTIN(kern);
     dim3 grid(a.parts, (a.nq + TQ - 1) / TQ);
     kern<<<grid, NT, smem, st>>>((const T*)a.db, a.aux, a.n_rows, a.dim, (const T*)a.queries, a.nq, a.tomb,
                                  a.tomb_bits, a.allow, a.kc, a.cap, a.rows_per_part, a.partial);
@@ -481,7 +480,11 @@ __device__ __forceinline__ void certify(const CertArgs& ca, int q, const uint64_
         const float c_last = key_of(last), dk = key_of(kth);
         const float qn = sqrtf(qn2), xn2 = *ca.max_norm2, xn = sqrtf(xn2);
         float ek, eps;
-        if (METRIC == METRIC_L2) { ek = dk * dk - qn2; eps = 2.f * ca.beta * qn * xn + 4e-6f * (xn2 + qn2); }
+        if (METRIC == METRIC_L2 && ca.key_space == 1) {
+            // SIMT scan: keys are |q - x|^2 accumulated in fp32 (its own order): error relative to the value itself
+            ek = dk * dk;
+            eps = (ca.beta + 4e-6f) * fmaxf(c_last, ek);
+        } else if (METRIC == METRIC_L2) { ek = dk * dk - qn2; eps = 2.f * ca.beta * qn * xn + 4e-6f * (xn2 + qn2); }
         else if (METRIC == METRIC_COSINE) { ek = (dk - 1.f) * qn; eps = ca.beta * qn + 2e-6f * qn; }
         else { ek = dk; eps = ca.beta * qn * xn; }
         cert = (c_last - ek) > 2.f * eps;
@@ -770,7 +773,7 @@ template <typename T>
 static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
     int n2 = next_pow2(max(a.c, 32));
     if (n2 > 1024) return cudaErrorInvalidValue;
-    const CertArgs ca{a.cert_flags, a.cert_count, a.max_norm2, a.beta};
+    const CertArgs ca{a.cert_flags, a.cert_count, a.max_norm2, a.beta, a.key_space};
     // cooperative-gather kernel whenever rows are 16-byte aligned multiples of 16 bytes
     const size_t row_bytes = (size_t)a.dim * sizeof(T);
     const bool coop = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.db) & 15) == 0) &&
@@ -781,8 +784,7 @@ static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
 #define LB_RC(M)                                                                                            \
     {                                                                                                       \
         auto kern = rescore_coop_kernel<T, M>;                                                              \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                     \
+        LB_SMEM_OPTIN(kern);                                                                                \
         kern<<<a.nq, RC_WARPS * 32, smem, st>>>((const T*)a.db, a.n_rows, a.dim, (const T*)a.queries, a.nq, \
                                                 a.packed, a.ids32, a.c, a.k, n2, a.tomb, a.tomb_bits, a.allow, \
                                                 a.id_base, a.out_d, a.out_l, a.negate_dot, a.nrm, ca);      \
@@ -800,10 +802,7 @@ static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
 #define LB_RS(M)                                                                                            \
     {                                                                                                       \
         auto kern = rescore_kernel<T, M>;                                                                   \
-        if (smem > 48 * 1024) {                                                                             \
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                 \
-        }                                                                                                   \
+        LB_SMEM_OPTIN(kern);                                                                                \
         kern<<<a.nq, n2, smem, st>>>((const T*)a.db, a.n_rows, a.dim, (const T*)a.queries, a.nq, a.packed,  \
                                      a.ids32, a.c, a.k, a.tomb, a.tomb_bits, a.allow, a.id_base, a.out_d,   \
                                      a.out_l, a.negate_dot, a.nrm, ca);                                     \
@@ -982,77 +981,119 @@ cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_
 
 // Shard merge: (distance,label) lists with int64 labels.  Lists are short (parts * k_in), so one
 // block per query sorts (distance, slot) keys and then maps slots back to labels.
+// Shard merge: [parts] sorted (distance, int64 label) lists per query -> the k best by (distance, label).
+// Part pp's lists start at in_d_base + pp * stride_d (distances, [nq][k_in] f32) and in_l_base + pp * stride_l
+// (labels, [nq][k_in] i64), strides in bytes: two separate [parts][nq][k_in] arrays and the packed per-rank
+// exchange records ([distances | labels] per rank: one all-gather, or one peer push) are the same kernel with
+// different strides.
+// Order: sort by (distance, slot), then every run of equal distances that starts inside the first k outputs is
+// re-ranked by label -- O(run) label reads per entry (the earlier version re-derived the whole ranking per
+// output thread, O(run^2) each).
 __global__ void __launch_bounds__(256)
-merge_topk_kernel(const float* __restrict__ in_d, const int64_t* __restrict__ in_l, int parts, int nq, int k_in,
-                  int k, float* __restrict__ out_d, int64_t* __restrict__ out_l) {
+merge_topk_kernel(const char* __restrict__ in_d_base, size_t stride_d, const char* __restrict__ in_l_base,
+                  size_t stride_l, int parts, int nq, int k_in, int k, float* __restrict__ out_d,
+                  int64_t* __restrict__ out_l, const uint32_t* wait_flags, uint32_t wait_seq, uint32_t* err) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (wait_flags != nullptr) {
+        // exchange.cu: the records of this batch are pushed by the peers; wait until every source's flag has
+        // reached the batch's sequence number (acquire at system scope), at most ~10 s
+        if (threadIdx.x == 0) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (int p = 0; p < parts; p++) {
+                for (;;) {
+                    uint32_t v;
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(wait_flags + p) : "memory");
+                    if ((int32_t)(v - wait_seq) >= 0) break;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 10000000000ull) { atomicExch(err, 1u); break; }
+                    __nanosleep(200);
+                }
+            }
+        }
+        __syncthreads();
+    }
     const int total = parts * k_in;
     const int n2 = next_pow2(max(total, 2));
     uint64_t* hi = reinterpret_cast<uint64_t*>(smem_raw);  // [n2] (ordered distance << 32 | slot)
     const int q = blockIdx.x;
-    // Two-key order (distance, label): labels are int64, so sort by distance first with the slot as
-    // payload, then fix ties by label with a rank pass over equal-distance runs (runs are tiny).
+    auto dist_at = [&](int t) {
+        const int pp = t / k_in, j = t - pp * k_in;
+        return __ldcg(reinterpret_cast<const float*>(in_d_base + (size_t)pp * stride_d) + (size_t)q * k_in + j);
+    };
+    auto label_at = [&](int t) {
+        const int pp = t / k_in, j = t - pp * k_in;
+        return __ldcg(reinterpret_cast<const long long*>(in_l_base + (size_t)pp * stride_l) + (size_t)q * k_in + j);
+    };
     for (int t = threadIdx.x; t < n2; t += blockDim.x) {
         uint64_t p = kInvalid;
-        if (t < total) {
-            int pp = t / k_in, j = t % k_in;
-            size_t o = ((size_t)pp * nq + q) * k_in + j;
-            if (in_l[o] >= 0) p = ((uint64_t)float_to_ordered(in_d[o]) << 32) | (uint32_t)t;
-        }
+        if (t < total && label_at(t) >= 0) p = ((uint64_t)float_to_ordered(dist_at(t)) << 32) | (uint32_t)t;
         hi[t] = p;
     }
     __syncthreads();
     block_bitonic_sort(hi, n2);
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        uint64_t p = (j < n2) ? hi[j] : kInvalid;
-        if (p == kInvalid) {
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {  // padding slots (disjoint from the valid ones below)
+        if (j >= n2 || hi[j] == kInvalid) {
             out_d[(size_t)q * k + j] = 3.402823466e+38f;
             out_l[(size_t)q * k + j] = -1;
-            continue;
         }
-        // rank within the run of equal distances by label
-        uint32_t dkey = (uint32_t)(p >> 32);
-        int lo = j, hi_i = j;
-        while (lo > 0 && (uint32_t)(hi[lo - 1] >> 32) == dkey) lo--;
-        while (hi_i + 1 < n2 && hi[hi_i + 1] != kInvalid && (uint32_t)(hi[hi_i + 1] >> 32) == dkey) hi_i++;
-        auto label_of = [&](int pos) {
-            int t = (int)(uint32_t)hi[pos];
-            int pp = t / k_in, jj = t % k_in;
-            return in_l[((size_t)pp * nq + q) * k_in + jj];
-        };
-        int64_t my = label_of(j);
-        if (lo != hi_i) {
-            // the (j - lo)-th smallest label of the run
-            int want = j - lo;
-            for (int a = lo; a <= hi_i; a++) {
-                int64_t la = label_of(a);
-                int rank = 0;
-                for (int b = lo; b <= hi_i; b++) {
-                    int64_t lb_ = label_of(b);
-                    rank += (lb_ < la) || (lb_ == la && b < a);
-                }
-                if (rank == want) { my = la; break; }
+    }
+    for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+        const uint64_t p = hi[t];
+        if (p == kInvalid) continue;
+        const uint32_t dkey = (uint32_t)(p >> 32);
+        const bool tie_prev = t > 0 && (uint32_t)(hi[t - 1] >> 32) == dkey;
+        const bool tie_next = t + 1 < n2 && hi[t + 1] != kInvalid && (uint32_t)(hi[t + 1] >> 32) == dkey;
+        int pos = t;
+        const int64_t my = label_at((int)(uint32_t)p);
+        if (tie_prev || tie_next) {
+            int lo = t;
+            while (lo > 0 && (uint32_t)(hi[lo - 1] >> 32) == dkey) lo--;
+            if (lo >= k) continue;  // the whole run lies beyond the outputs
+            int rank = 0;
+            for (int b = lo; b < n2; b++) {
+                const uint64_t pb = hi[b];
+                if (pb == kInvalid || (uint32_t)(pb >> 32) != dkey) break;
+                if (b == t) continue;
+                const int64_t lb_ = label_at((int)(uint32_t)pb);
+                rank += (lb_ < my) || (lb_ == my && b < t);
             }
+            pos = lo + rank;
         }
-        out_d[(size_t)q * k + j] = ordered_to_float(dkey);
-        out_l[(size_t)q * k + j] = my;
+        if (pos < k) {
+            out_d[(size_t)q * k + pos] = ordered_to_float(dkey);
+            out_l[(size_t)q * k + pos] = my;
+        }
     }
 }
 
-cudaError_t launch_merge_topk(const float* in_d, const int64_t* in_l, int parts, int nq, int k_in, int k,
-                              float* out_d, int64_t* out_l, cudaStream_t st) {
+cudaError_t launch_merge_topk_strided(const void* in_d_base, size_t stride_d, const void* in_l_base, size_t stride_l,
+                                      int parts, int nq, int k_in, int k, float* out_d, int64_t* out_l,
+                                      cudaStream_t st) {
+    return launch_merge_topk_wait(in_d_base, stride_d, in_l_base, stride_l, parts, nq, k_in, k, out_d, out_l, nullptr, 0,
+                                  0, nullptr, st);
+}
+
+cudaError_t launch_merge_topk_wait(const void* in_d_base, size_t stride_d, const void* in_l_base, size_t stride_l,
+                                   int parts, int nq, int k_in, int k, float* out_d, int64_t* out_l,
+                                   const uint32_t* wait_flags, uint32_t wait_seq, int /*rank*/, uint32_t* err,
+                                   cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     int total = parts * k_in;
     int n2 = next_pow2(total < 2 ? 2 : total);
     size_t smem = (size_t)n2 * 8;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    merge_topk_kernel<<<nq, 256, smem, st>>>(in_d, in_l, parts, nq, k_in, k, out_d, out_l);
+    LB_SMEM_OPTIN(merge_topk_kernel);
+    merge_topk_kernel<<<nq, 256, smem, st>>>((const char*)in_d_base, stride_d, (const char*)in_l_base, stride_l, parts,
+                                             nq, k_in, k, out_d, out_l, wait_flags, wait_seq, err);
     count_launch();
     return cudaGetLastError();
+}
+
+cudaError_t launch_merge_topk(const float* in_d, const int64_t* in_l, int parts, int nq, int k_in, int k,
+                              float* out_d, int64_t* out_l, cudaStream_t st) {
+    return launch_merge_topk_strided(in_d, (size_t)nq * k_in * 4, in_l, (size_t)nq * k_in * 8, parts, nq, k_in, k,
+                                     out_d, out_l, st);
 }
 
 }  // namespace lb

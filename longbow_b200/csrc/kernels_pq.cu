@@ -135,8 +135,7 @@ adc_scan_kernel(const uint8_t* __restrict__ codes, uint32_t n_rows, int M, const
 cudaError_t launch_adc_scan(const PqScanArgs& a, cudaStream_t st) {
     if (a.nq <= 0) return cudaSuccess;
     size_t smem = (size_t)a.M * 1024 + (size_t)a.cap * 8;
-    cudaError_t e = cudaFuncSetAttribute(adc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    LB_SMEM_OPTIN(adc_scan_kernel);
     dim3 grid(a.nq, a.parts);
     adc_scan_kernel<<<grid, PQ_NT, smem, st>>>(a.codes, a.n_rows, a.M, a.luts, a.tomb, a.tomb_bits, a.allow, a.kc,
                                                a.cap, a.rows_per_part, a.nq, a.partial);
@@ -165,8 +164,7 @@ adc_batch_kernel(const float* __restrict__ table, const uint8_t* __restrict__ co
 cudaError_t launch_adc_batch(const float* table, const uint8_t* codes, int M, int64_t n, float* out, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     size_t smem = (size_t)M * 1024;
-    cudaError_t e = cudaFuncSetAttribute(adc_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    LB_SMEM_OPTIN(adc_batch_kernel);
     int64_t blocks = (n + PQ_NT - 1) / PQ_NT;
     if (blocks > 148 * 8) blocks = 148 * 8;
     adc_batch_kernel<<<(unsigned)blocks, PQ_NT, smem, st>>>(table, codes, M, n, out);
@@ -213,10 +211,7 @@ cudaError_t launch_pq_encode(const float* codebooks, int M, int K, int sub, cons
                              uint8_t* codes, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     size_t smem = (size_t)K * sub * 4;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(pq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    LB_SMEM_OPTIN(pq_encode_kernel);
     dim3 grid((unsigned)((n + 127) / 128), M);
     pq_encode_kernel<<<grid, 128, smem, st>>>(codebooks, M, K, sub, vecs, n, codes);
     count_launch();
@@ -329,10 +324,7 @@ cudaError_t launch_pq_train(const float* d_data, int64_t n, int dims, int M, int
     kmeans_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_data, dims, sub, K, M, d_init_idx, d_cent);
     count_launch();
     const size_t smem = (size_t)K * sub * 4;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    LB_SMEM_OPTIN(kmeans_assign_kernel);
     for (int it = 0; it < max_iter; it++) {
         dim3 ga((unsigned)((n + 127) / 128), M);
         kmeans_assign_kernel<<<ga, 128, smem, st>>>(d_data, n, dims, sub, K, d_cent, d_assign, d_changed, d_active);

@@ -236,10 +236,31 @@ class DenseIndex:
         return out
 
     # -- search (device tensors, asynchronous on `stream`)
-    def search_device(self, q, k: int, out_d, out_l, allow=None, stream=None):
-        check(self._lib.lb_index_search_device(self._h, q.data_ptr(), q.shape[0], int(k),
-                                               None if allow is None else allow.data_ptr(), out_d.data_ptr(),
-                                               out_l.data_ptr(), _stream_ptr(stream)))
+    def search_device(self, q, k: int, out_d, out_l, allow=None, stream=None, uncert_flags=None, uncert_count=None):
+        """out_d / out_l: device tensors or raw device addresses (ints).  uncert_flags [nq] u32 / uncert_count [1]
+        u32 (device tensors, optional): certification outputs of lb_index_search_device_cert -- the count
+        ACCUMULATES, so one counter can watch a whole run."""
+        pd = out_d if isinstance(out_d, int) else out_d.data_ptr()
+        pl = out_l if isinstance(out_l, int) else out_l.data_ptr()
+        pa = None if allow is None else allow.data_ptr()
+        if uncert_flags is None and uncert_count is None:
+            check(self._lib.lb_index_search_device(self._h, q.data_ptr(), q.shape[0], int(k), pa, pd, pl,
+                                                   _stream_ptr(stream)))
+        else:
+            check(self._lib.lb_index_search_device_cert(
+                self._h, q.data_ptr(), q.shape[0], int(k), pa, pd, pl,
+                None if uncert_flags is None else uncert_flags.data_ptr(),
+                None if uncert_count is None else uncert_count.data_ptr(), _stream_ptr(stream)))
+
+    def search_exact_device(self, q, k: int, out_d, out_l, flags_host=None, allow=None, stream=None):
+        """Exhaustive exact search of the queries whose host flag is set (None = all): the repair step for
+        queries lb_index_search_device_cert flagged."""
+        fl = None
+        if flags_host is not None:
+            fl = np.ascontiguousarray(flags_host, dtype=np.uint32)
+        check(self._lib.lb_index_search_exact_device(self._h, q.data_ptr(), q.shape[0], int(k),
+                                                     None if allow is None else allow.data_ptr(), _ptr(fl),
+                                                     out_d.data_ptr(), out_l.data_ptr(), _stream_ptr(stream)))
 
     def rerank_device(self, q, cand_ids, k: int, out_d, out_l, allow=None, stream=None):
         check(self._lib.lb_index_rerank_device(self._h, q.data_ptr(), q.shape[0], cand_ids.data_ptr(),

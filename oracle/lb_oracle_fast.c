@@ -62,6 +62,16 @@ LBF_API int lbf_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the timed CPU baseline sets its own thread count
+ * (all host cores the process may run on) so the N>1 reference arm is not a 1-thread run. */
+LBF_API void lbf_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* three partial sums of one pair: dot, |a|^2, |b|^2, or the squared diff */
 typedef struct { float dot, na, nb, l2; } acc_t;
 

@@ -230,5 +230,16 @@ def fast_threads() -> int:
     return int(fast().lbf_threads())
 
 
+def fast_use_all_cores() -> int:
+    """Give the timed CPU baseline every core this process may run on, whatever OMP_NUM_THREADS says
+    (torchrun exports OMP_NUM_THREADS=1 to its ranks).  Returns the thread count now in use."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    fast().lbf_set_threads(int(n))
+    return fast_threads()
+
+
 def fast_isa() -> str:
     return {2: "avx512", 1: "avx2", 0: "scalar"}[int(fast().lbf_isa())]
