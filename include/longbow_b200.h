@@ -246,6 +246,14 @@ int lb_pq_search(lb_pq *pq, const float *queries, int64_t nq, int k, int kprime,
                  float *distances, int64_t *labels);
 int lb_pq_search_device(lb_pq *pq, const float *d_queries, int64_t nq, int k, int kprime,
                         const uint64_t *d_allow, float *d_distances, int64_t *d_labels, void *stream);
+/* The scan is a coarse pass over an integer-quantised, bank-conflict-free LUT followed by the reference's
+ * sequential fp32 sum on the surviving candidates and a certification test.  lb_pq_search
+ * re-does uncertified queries with the exhaustive fp32 kernel before returning and reports how many there were
+ * here; the device entry point reports flags / an accumulating count instead (either may be NULL). */
+int64_t lb_pq_last_uncertified(const lb_pq *pq);
+int lb_pq_search_device_cert(lb_pq *pq, const float *d_queries, int64_t nq, int k, int kprime,
+                             const uint64_t *d_allow, float *d_distances, int64_t *d_labels,
+                             uint32_t *d_uncert_flags, uint32_t *d_uncert_count, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * 5. Predicate -> dense bitmap (internal/simd/simd.go:572-761 compare kernels,
@@ -272,7 +280,8 @@ int64_t lb_kernel_launch_count(void);
  * "dense_scan" 3 = force the streaming scan (1..8 queries).  "tc_pair": CTA-pair MMAs on/off.
  * "f32_tc": 3xTF32 tensor-core scan for fp32 indexes on/off.  "tc_boot_tiles": bootstrap sample size.
  * "tc_boot": 1 (default) = bootstrap-threshold pre-scan for the tensor-core path, 0 = off.
- * "tc_debug": timing probes of the tensor-core scan; results are INVALID when non-zero. */
+ * "tc_debug": timing probes of the tensor-core scan; results are INVALID when non-zero.
+ * "pq_scan": 0 = auto, 1 = exhaustive fp32 ADC kernel, 2 = coarse scan one query per pass, 3 = four per pass. */
 int lb_set_option(const char *name, int value);
 /* Profiling hook for bench.py's roofline: when enabled, every search brackets its dominant
  * kernel (the coarse distance scan: dense or ADC) with CUDA events on the launching stream.

@@ -98,6 +98,7 @@ static std::atomic<int> g_opt_dense_scan{0};
 static std::atomic<int> g_opt_tc_debug{0};
 static std::atomic<int> g_opt_tc_boot_tiles{0};  // 0 = auto
 static std::atomic<int> g_opt_f32_tc{1};         // fp32 indexes: 3xTF32 tensor-core scan (0: SIMT scan)
+static std::atomic<int> g_opt_pq_scan{0};  // 0 auto, 1 exhaustive fp32 kernel, 2 coarse (1 query / pass), 3 coarse (4 / pass)
 static std::atomic<int> g_opt_certify{1};        // host searches: certify the coarse stage, redo flagged queries exactly
 static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off (A/B timing)    // timing probes of the tensor-core scan (results invalid when != 0)  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
 
@@ -151,8 +152,11 @@ struct lb_index {
 struct lb_pq {
     int device, dims, M, K, sub;
     float* codebooks = nullptr;  // [M][K][sub]
-    uint8_t* codes = nullptr;    // [capacity][M]
+    uint8_t* codes = nullptr;    // [capacity][M] row-major (flatCodes, adc_table.go:57): exhaustive fp32 scan, fallback
+    uint8_t* tiled = nullptr;    // the same codes as 32-row tiles of rotated 16-byte chunks (pq_scan.cu): coarse scan
+    int64_t tiled_cap = 0;       // rows (multiple of 32)
     int64_t size = 0, capacity = 0;
+    std::atomic<int64_t> last_uncertified{0};
     lb_index* raw = nullptr;
     uint32_t* tomb = nullptr;
     int64_t tomb_bits = 0;
@@ -245,6 +249,11 @@ int lb_set_option(const char* name, int value) {
     }
     if (strcmp(name, "tc_debug") == 0) {
         g_opt_tc_debug.store(value);
+        return LB_OK;
+    }
+    if (strcmp(name, "pq_scan") == 0) {
+        if (value < 0 || value > 3) return fail(LB_ERR_INVALID, "pq_scan: 0 auto, 1 exhaustive fp32, 2 coarse x1, 3 coarse x4");
+        g_opt_pq_scan.store(value);
         return LB_OK;
     }
     return fail(LB_ERR_INVALID, "unknown option");
@@ -1115,6 +1124,7 @@ void lb_pq_free(lb_pq* pq) {
         cudaDeviceSynchronize();
         if (pq->codebooks) cudaFree(pq->codebooks);
         if (pq->codes) cudaFree(pq->codes);
+        if (pq->tiled) cudaFree(pq->tiled);
         if (pq->tomb) cudaFree(pq->tomb);
     }
     cudaGetLastError();
@@ -1142,6 +1152,21 @@ static int pq_add_common(lb_pq* pq, const uint8_t* src, int64_t n, bool on_devic
     if (rc) return rc;
     CK(cudaMemcpyAsync(pq->codes + (size_t)pq->size * pq->M, src, (size_t)n * pq->M,
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (pq->M <= 96) {  // the coarse scan's mirror (pq_scan.cu)
+        const int Mp = ((pq->M + 31) / 32) * 32;
+        const int64_t need = ((pq->capacity + 31) / 32) * 32;
+        if (need > pq->tiled_cap) {
+            uint8_t* nt = nullptr;
+            CK(cudaMalloc((void**)&nt, (size_t)need * Mp));
+            CK(cudaDeviceSynchronize());
+            if (pq->tiled && pq->size > 0)
+                CK(cudaMemcpy(nt, pq->tiled, (size_t)(((pq->size + 31) / 32) * 32) * Mp, cudaMemcpyDeviceToDevice));
+            if (pq->tiled) cudaFree(pq->tiled);
+            pq->tiled = nt;
+            pq->tiled_cap = need;
+        }
+        CK(launch_pq_tile_codes(pq->codes + (size_t)pq->size * pq->M, n, pq->M, Mp, pq->size, pq->tiled, st));
+    }
     pq->size += n;
     if (!on_device) CK(cudaStreamSynchronize(st));
     return LB_OK;
@@ -1255,20 +1280,72 @@ int lb_pq_train(int device, const float* vectors, int64_t n, int dims, int m, in
     return LB_OK;
 }
 
+
+static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+// The round-1 path: every code row gets the reference's sequential fp32 sum (adc_scan_kernel).  Exact keys, no
+// certification needed.  Still the path for M > 96, very large k', and the repair of uncertified queries.
+static int pq_search_exhaustive(lb_pq* pq, const float* q, int cq, const float* luts, int k, int kc, bool rerank,
+                                const uint64_t* d_allow, float* d_dist, int64_t* d_lab, Scratch& scr, cudaStream_t st) {
+    PqScanArgs a;
+    a.codes = pq->codes; a.n_rows = (uint32_t)pq->size; a.M = pq->M; a.luts = luts; a.nq = cq;
+    a.tomb = pq->tomb; a.tomb_bits = (uint32_t)(pq->tomb_bits > 0xffffffffll ? 0xffffffffll : pq->tomb_bits);
+    a.allow = (const uint32_t*)d_allow;
+    a.kc = kc; a.cap = next_pow2(kc + 256);
+    int target = 4 * pq->sm_count;
+    int parts = (target + cq - 1) / cq;
+    int64_t max_parts = (pq->size + 2047) / 2048;
+    if (parts > max_parts) parts = (int)max_parts;
+    if (parts < 1) parts = 1;
+    int64_t rpp = (pq->size + parts - 1) / parts;
+    rpp = ((rpp + 255) / 256) * 256;
+    parts = (int)((pq->size + rpp - 1) / rpp);
+    a.parts = parts; a.rows_per_part = (uint32_t)rpp;
+    uint64_t *partial, *merged;
+    CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
+    a.partial = partial;
+    {
+        ProfScope prof(st, (double)cq * (double)pq->size);
+        CK(launch_adc_scan(a, st));
+    }
+    if (parts > 1) {
+        CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
+        CK(launch_merge_partials(partial, parts, cq, kc, merged, st));
+    } else {
+        merged = partial;
+    }
+    if (rerank) {
+        RescoreArgs r;
+        r.dtype = DT_F32; r.metric = METRIC_L2; r.db = pq->raw->rows; r.n_rows = (uint32_t)pq->raw->size;
+        r.dim = pq->dims; r.queries = q; r.nq = cq; r.packed = merged; r.ids32 = nullptr; r.c = kc; r.k = k;
+        r.tomb = nullptr; r.tomb_bits = 0; r.allow = nullptr; r.id_base = 0;
+        r.out_d = d_dist; r.out_l = d_lab; r.negate_dot = 1;
+        CK(launch_rescore(r, st));
+    } else {
+        CK(launch_unpack_topk(merged, cq, kc, k, 0, d_dist, d_lab, st));
+    }
+    return LB_OK;
+}
+
+// d_flags [nq] / d_count [1] (device, optional): certification of the coarse pass (pq_scan.cu)
 static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kprime, const uint64_t* d_allow,
-                          float* d_dist, int64_t* d_lab, cudaStream_t st) {
+                          float* d_dist, int64_t* d_lab, cudaStream_t st, uint32_t* d_flags = nullptr,
+                          uint32_t* d_count = nullptr) {
     if (nq == 0) return LB_OK;
     const bool rerank = pq->raw != nullptr;
-    const int kc = rerank ? (kprime > k ? kprime : k) : k;  // ADC keys are exact: no margin needed
-    if (kc > 1024) return fail(LB_ERR_UNSUPPORTED, "k' > 1024");
+    const int kout = rerank ? (kprime > k ? kprime : k) : k;  // exact ADC top-kout, then (optionally) the fp32 re-rank
+    if (kout > 1024) return fail(LB_ERR_UNSUPPORTED, "k' > 1024");
     if (rerank && pq->raw->size < pq->size) return fail(LB_ERR_STATE, "raw index has fewer rows than codes");
     Scratch scr(st);
     if (pq->size == 0) {
         uint64_t* merged;
         CK(scr.get((void**)&merged, 8));
         CK(launch_unpack_topk(merged, (int)nq, 0, k, 0, d_dist, d_lab, st));
+        if (d_flags) CK(cudaMemsetAsync(d_flags, 0, (size_t)nq * 4, st));
         return LB_OK;
     }
+    const int mode = g_opt_pq_scan.load(std::memory_order_relaxed);
+    const int kc = coarse_k(kout);  // coarse candidates: margin over kout absorbs the quantisation step
     const int64_t qchunk = 512;
     for (int64_t qo = 0; qo < nq; qo += qchunk) {
         const int cq = (int)((nq - qo) < qchunk ? (nq - qo) : qchunk);
@@ -1276,43 +1353,78 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
         float* luts;
         CK(scr.get((void**)&luts, (size_t)cq * pq->M * 1024));
         CK(launch_adc_lut(pq->codebooks, pq->M, pq->K, pq->sub, q, cq, luts, st));
-        PqScanArgs a;
-        a.codes = pq->codes; a.n_rows = (uint32_t)pq->size; a.M = pq->M; a.luts = luts; a.nq = cq;
-        a.tomb = pq->tomb; a.tomb_bits = (uint32_t)(pq->tomb_bits > 0xffffffffll ? 0xffffffffll : pq->tomb_bits);
-        a.allow = (const uint32_t*)d_allow;
-        a.kc = kc; a.cap = next_pow2(kc + 256);
-        int target = 4 * pq->sm_count;
-        int parts = (target + cq - 1) / cq;
-        int64_t max_parts = (pq->size + 2047) / 2048;
+        int nqpp = (mode == 2) ? 1 : (mode == 3) ? 4 : (cq >= 2 ? 4 : 1);
+        if (nqpp == 4 && !adc_coarse_eligible(pq->M, kc, 4)) nqpp = 1;
+        const bool coarse = mode != 1 && pq->tiled != nullptr && adc_coarse_eligible(pq->M, kc, nqpp) &&
+                            pq->size >= 4096;
+        if ((mode == 2 || mode == 3) && !coarse) return fail(LB_ERR_UNSUPPORTED, "coarse ADC scan not eligible");
+        if (!coarse) {
+            int rc = pq_search_exhaustive(pq, q, cq, luts, k, kout, rerank, d_allow, d_dist + (size_t)qo * k,
+                                          d_lab + (size_t)qo * k, scr, st);
+            if (rc) return rc;
+            if (d_flags) CK(cudaMemsetAsync(d_flags + qo, 0, (size_t)cq * 4, st));
+            continue;
+        }
+        const int qgroups = (cq + nqpp - 1) / nqpp;
+        const int64_t n_tiles = (pq->size + 31) / 32;
+        int unit = pq->sm_count / gcd_i(qgroups, pq->sm_count);
+        int parts = unit;
+        const int64_t max_parts = (n_tiles + 63) / 64;  // at least 2048 rows per part
         if (parts > max_parts) parts = (int)max_parts;
         if (parts < 1) parts = 1;
-        int64_t rpp = (pq->size + parts - 1) / parts;
-        rpp = ((rpp + 255) / 256) * 256;
-        parts = (int)((pq->size + rpp - 1) / rpp);
-        a.parts = parts; a.rows_per_part = (uint32_t)rpp;
-        uint64_t *partial, *merged;
-        CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
-        a.partial = partial;
+        const uint32_t tpp = (uint32_t)((n_tiles + parts - 1) / parts);
+        parts = (int)((n_tiles + tpp - 1) / tpp);
+        const size_t stride = (size_t)parts * kc;
+        uint8_t* lutq; void* params; uint64_t *compact, *merged, *exact; uint32_t *out_cnt, *g_tau;
+        CK(scr.get((void**)&lutq, adc_lutq_bytes(pq->M, cq, nqpp)));
+        CK(scr.get(&params, adc_params_bytes(cq)));
+        CK(scr.get((void**)&compact, (size_t)cq * stride * 8));
+        CK(scr.get((void**)&out_cnt, (size_t)cq * 4));
+        CK(scr.get((void**)&g_tau, (size_t)cq * 4));
+        CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
+        CK(scr.get((void**)&exact, (size_t)cq * kout * 8));
+        CK(cudaMemsetAsync(out_cnt, 0, (size_t)cq * 4, st));
+        CK(cudaMemsetAsync(g_tau, 0xff, (size_t)cq * 4, st));
         {
             ProfScope prof(st, (double)cq * (double)pq->size);
-            CK(launch_adc_scan(a, st));
+            CK(launch_adc_coarse(pq->tiled, (uint32_t)pq->size, pq->M, luts, cq, nqpp, pq->tomb,
+                                 (uint32_t)(pq->tomb_bits > 0xffffffffll ? 0xffffffffll : pq->tomb_bits),
+                                 (const uint32_t*)d_allow, kc, parts, tpp, lutq, params, compact, out_cnt, stride, g_tau,
+                                 st));
         }
-        if (parts > 1) {
-            CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
-            CK(launch_merge_partials(partial, parts, cq, kc, merged, st));
-        } else {
-            merged = partial;
-        }
+        CK(launch_merge_select_compact(nullptr, compact, out_cnt, stride, cq, kc, merged, nullptr, nullptr, st));
+        uint32_t* flags = d_flags ? d_flags + qo : nullptr;
+        if (!flags && d_count) CK(scr.get((void**)&flags, (size_t)cq * 4));
+        CK(launch_adc_exact(pq->tiled, pq->M, luts, merged, cq, kc, kout, params, exact, flags, d_count, st));
         if (rerank) {
             RescoreArgs r;
             r.dtype = DT_F32; r.metric = METRIC_L2; r.db = pq->raw->rows; r.n_rows = (uint32_t)pq->raw->size;
-            r.dim = pq->dims; r.queries = q; r.nq = cq; r.packed = merged; r.ids32 = nullptr; r.c = kc; r.k = k;
+            r.dim = pq->dims; r.queries = q; r.nq = cq; r.packed = exact; r.ids32 = nullptr; r.c = kout; r.k = k;
             r.tomb = nullptr; r.tomb_bits = 0; r.allow = nullptr; r.id_base = 0;
             r.out_d = d_dist + (size_t)qo * k; r.out_l = d_lab + (size_t)qo * k; r.negate_dot = 1;
             CK(launch_rescore(r, st));
         } else {
-            CK(launch_unpack_topk(merged, cq, kc, k, 0, d_dist + (size_t)qo * k, d_lab + (size_t)qo * k, st));
+            CK(launch_unpack_topk(exact, cq, kout, k, 0, d_dist + (size_t)qo * k, d_lab + (size_t)qo * k, st));
         }
+    }
+    return LB_OK;
+}
+
+// exhaustive repair of the queries whose host flag is set (device pointers in / out)
+static int pq_repair(lb_pq* pq, const float* d_q, int64_t nq, int k, int kprime, const uint64_t* d_allow,
+                     const uint32_t* h_flags, float* d_dist, int64_t* d_lab, cudaStream_t st) {
+    const bool rerank = pq->raw != nullptr;
+    const int kout = rerank ? (kprime > k ? kprime : k) : k;
+    Scratch scr(st);
+    for (int64_t qi = 0; qi < nq; qi++) {
+        if (!h_flags[qi]) continue;
+        const float* q = d_q + (size_t)qi * pq->dims;
+        float* luts;
+        CK(scr.get((void**)&luts, (size_t)pq->M * 1024));
+        CK(launch_adc_lut(pq->codebooks, pq->M, pq->K, pq->sub, q, 1, luts, st));
+        int rc = pq_search_exhaustive(pq, q, 1, luts, k, kout, rerank, d_allow, d_dist + (size_t)qi * k,
+                                      d_lab + (size_t)qi * k, scr, st);
+        if (rc) return rc;
     }
     return LB_OK;
 }
@@ -1346,12 +1458,39 @@ int lb_pq_search(lb_pq* pq, const float* queries, int64_t nq, int k, int kprime,
         CK(scr.get((void**)&d_allow, words * 8));
         CK(cudaMemcpyAsync(d_allow, allow, words * 8, cudaMemcpyHostToDevice, st));
     }
-    rc = pq_search_core(pq, d_q, nq, k, kprime, d_allow, d_d, d_l, st);
+    uint32_t *d_flags, *d_count;
+    CK(scr.get((void**)&d_flags, (size_t)nq * 4));
+    CK(scr.get((void**)&d_count, 4));
+    CK(cudaMemsetAsync(d_count, 0, 4, st));
+    rc = pq_search_core(pq, d_q, nq, k, kprime, d_allow, d_d, d_l, st, d_flags, d_count);
     if (rc) { cudaStreamSynchronize(st); return rc; }
+    uint32_t n_uncert = 0;
+    CK(cudaMemcpyAsync(&n_uncert, d_count, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    pq->last_uncertified.store((int64_t)n_uncert);
+    if (n_uncert > 0) {  // coarse margin did not cover the quantisation bound: redo those queries exhaustively
+        std::vector<uint32_t> flags((size_t)nq);
+        CK(cudaMemcpy(flags.data(), d_flags, (size_t)nq * 4, cudaMemcpyDeviceToHost));
+        rc = pq_repair(pq, d_q, nq, k, kprime, d_allow, flags.data(), d_d, d_l, st);
+        if (rc) { cudaStreamSynchronize(st); return rc; }
+    }
     CK(cudaMemcpyAsync(distances, d_d, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(labels, d_l, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return LB_OK;
+}
+
+int64_t lb_pq_last_uncertified(const lb_pq* pq) { return pq ? pq->last_uncertified.load() : -1; }
+
+int lb_pq_search_device_cert(lb_pq* pq, const float* d_queries, int64_t nq, int k, int kprime, const uint64_t* d_allow,
+                             float* d_distances, int64_t* d_labels, uint32_t* d_uncert_flags,
+                             uint32_t* d_uncert_count, void* stream) {
+    if (!pq) return fail(LB_ERR_INVALID, "pq is NULL");
+    if (k <= 0 || nq < 0) return fail(LB_ERR_INVALID, "k must be positive");
+    int rc = use_device(pq->device);
+    if (rc) return rc;
+    return pq_search_core(pq, d_queries, nq, k, kprime, d_allow, d_distances, d_labels, (cudaStream_t)stream,
+                          d_uncert_flags, d_uncert_count);
 }
 
 // ----------------------------------------------------------------------------------- predicates

@@ -145,6 +145,11 @@ class PQEncoder:
         check(self._lib.lb_pq_search(self._h, _ptr(q), q.shape[0], int(k), int(kprime), _ptr(bm), _ptr(d), _ptr(l)))
         return d, l
 
+    def last_uncertified(self) -> int:
+        """Queries of the last host search whose coarse pass could not be certified (they were re-done with the
+        exhaustive fp32 kernel before the call returned)."""
+        return int(self._lib.lb_pq_last_uncertified(self._h))
+
     def search_into(self, q, k, kprime, d, l):
         check(self._lib.lb_pq_search(self._h, q.ctypes.data, q.shape[0], int(k), int(kprime), None, d.ctypes.data,
                                      l.ctypes.data))

@@ -91,8 +91,10 @@ def test_device_path_certification(oracle):
     idx.search_device(dq, k, od, ol, uncert_flags=flags, uncert_count=count)
     idx.search_device(dq, k, od, ol, uncert_flags=flags, uncert_count=count)  # the counter accumulates
     f = flags.cpu().numpy()
-    assert f[0] == 1 and f[1] == 0 and f[2] == 0, f
-    assert int(count.item()) == 2
+    # query 0 sits inside the 300-row near-tie cluster; row 17 (the cluster's centre) is the 26th nearest row of
+    # query 1, so the cluster straddles its rank-100 boundary as well; query 2 is far from it
+    assert f[0] == 1 and f[1] == 1 and f[2] == 0, f
+    assert int(count.item()) == 4
     idx.search_exact_device(dq, k, od, ol, flags_host=f)
     wd, wl = oracle.search(COS, db, q, k)
     assert_topk_equal(od.cpu().numpy(), ol.cpu().numpy(), wd, wl, 0.0, "device path after repair")

@@ -25,7 +25,7 @@ HBM = PEAKS.get("hbm_gbs", 6650.0)
 TF = PEAKS.get("bf16_tflops", 1590.0)
 dev = torch.device("cuda", 0)
 STEPS = int(os.environ.get("STEPS", "10"))
-for _opt in ("tc_pair", "dense_scan", "tc_boot_tiles"):
+for _opt in ("tc_pair", "dense_scan", "tc_boot_tiles", "pq_scan"):
     if os.environ.get(_opt.upper()):
         _lib.set_option(_opt, int(os.environ[_opt.upper()]))
 
@@ -112,6 +112,13 @@ def c3():
     enc.add_codes_device(codes)
     od = torch.empty((Q, K), dtype=torch.float32, device=dev)
     ol = torch.empty((Q, K), dtype=torch.int64, device=dev)
+    for nq1 in (1, 4):
+        q1 = qs[:nq1].contiguous()
+        o1d = torch.empty((nq1, K), dtype=torch.float32, device=dev)
+        o1l = torch.empty((nq1, K), dtype=torch.int64, device=dev)
+        ms, sm = timed(lambda: enc.search_device(q1, K, 0, o1d, o1l), steps=STEPS, warm=2)
+        report(f"C3 PQ ADC scan, {nq1} quer{'y' if nq1 == 1 else 'ies'} per pass over {N} x 96 codes (HBM-bound: N*M bytes per pass)",
+               ms, sm, nq1, N * M, None)
     ms, sm = timed(lambda: enc.search_device(qs, K, 0, od, ol), steps=max(2, STEPS // 3), warm=1)
     report(f"C3 PQ ADC scan M=96 over {N} x 96 codes, {Q} queries, k=10 (no re-rank)", ms, sm, Q, None, None,
            f"ADC lookups/s = {Q * N * M / (ms * 1e-3):.3e}; code bytes per pass {N * M / 1e6:.0f} MB; "
