@@ -1375,7 +1375,7 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
         const uint32_t tpp = (uint32_t)((n_tiles + parts - 1) / parts);
         parts = (int)((n_tiles + tpp - 1) / tpp);
         const size_t stride = (size_t)parts * kc;
-        uint8_t* lutq; void* params; uint64_t *compact, *merged, *exact; uint32_t *out_cnt, *g_tau;
+        uint8_t* lutq; void* params; uint64_t *compact, *merged, *exact; uint32_t *out_cnt, *g_tau, *g_min, *ovf;
         CK(scr.get((void**)&lutq, adc_lutq_bytes(pq->M, cq, nqpp)));
         CK(scr.get(&params, adc_params_bytes(cq)));
         CK(scr.get((void**)&compact, (size_t)cq * stride * 8));
@@ -1383,19 +1383,25 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
         CK(scr.get((void**)&g_tau, (size_t)cq * 4));
         CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
         CK(scr.get((void**)&exact, (size_t)cq * kout * 8));
+        // one allocation: [out_cnt | overflow] zeroed, [g_tau | g_min] set to 0xffffffff
+        const size_t nmin = (size_t)adc_min_slots(parts);
+        CK(scr.get((void**)&ovf, (size_t)cq * 4));
+        CK(scr.get((void**)&g_min, (size_t)cq * nmin * 4));
         CK(cudaMemsetAsync(out_cnt, 0, (size_t)cq * 4, st));
+        CK(cudaMemsetAsync(ovf, 0, (size_t)cq * 4, st));
         CK(cudaMemsetAsync(g_tau, 0xff, (size_t)cq * 4, st));
+        CK(cudaMemsetAsync(g_min, 0xff, (size_t)cq * nmin * 4, st));
         {
             ProfScope prof(st, (double)cq * (double)pq->size);
             CK(launch_adc_coarse(pq->tiled, (uint32_t)pq->size, pq->M, luts, cq, nqpp, pq->tomb,
                                  (uint32_t)(pq->tomb_bits > 0xffffffffll ? 0xffffffffll : pq->tomb_bits),
                                  (const uint32_t*)d_allow, kc, parts, tpp, lutq, params, compact, out_cnt, stride, g_tau,
-                                 st));
+                                 g_min, ovf, st));
         }
         CK(launch_merge_select_compact(nullptr, compact, out_cnt, stride, cq, kc, merged, nullptr, nullptr, st));
         uint32_t* flags = d_flags ? d_flags + qo : nullptr;
         if (!flags && d_count) CK(scr.get((void**)&flags, (size_t)cq * 4));
-        CK(launch_adc_exact(pq->tiled, pq->M, luts, merged, cq, kc, kout, params, exact, flags, d_count, st));
+        CK(launch_adc_exact(pq->tiled, pq->M, luts, merged, cq, kc, kout, params, ovf, exact, flags, d_count, st));
         if (rerank) {
             RescoreArgs r;
             r.dtype = DT_F32; r.metric = METRIC_L2; r.db = pq->raw->rows; r.n_rows = (uint32_t)pq->raw->size;

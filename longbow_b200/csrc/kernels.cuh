@@ -188,13 +188,15 @@ cudaError_t launch_pq_tile_codes(const uint8_t* flat, int64_t n, int M, int Mp, 
 bool adc_coarse_eligible(int M, int kc, int nq_per_pass);
 size_t adc_lutq_bytes(int M, int nq, int nq_per_pass);
 size_t adc_params_bytes(int nq);
+int adc_min_slots(int parts);
 cudaError_t launch_adc_coarse(const uint8_t* tiled, uint32_t n_rows, int M, const float* luts, int nq, int nq_per_pass,
                               const uint32_t* tomb, uint32_t tomb_bits, const uint32_t* allow, int kc, int parts,
                               uint32_t tiles_per_part, uint8_t* lutq, void* params, uint64_t* compact,
-                              uint32_t* out_cnt, size_t stride, uint32_t* g_tau, cudaStream_t st);
+                              uint32_t* out_cnt, size_t stride, uint32_t* g_tau, uint32_t* g_min, uint32_t* overflow,
+                              cudaStream_t st);
 cudaError_t launch_adc_exact(const uint8_t* tiled, int M, const float* luts, const uint64_t* coarse, int nq, int kc,
-                             int k_out, const void* params, uint64_t* out, uint32_t* cert_flags, uint32_t* cert_count,
-                             cudaStream_t st);
+                             int k_out, const void* params, const uint32_t* overflow, uint64_t* out,
+                             uint32_t* cert_flags, uint32_t* cert_count, cudaStream_t st);
 cudaError_t launch_unpack_topk(const uint64_t* merged, int nq, int kc, int k, int64_t id_base, float* out_d,
                                int64_t* out_l, cudaStream_t st);
 

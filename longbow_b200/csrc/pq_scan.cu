@@ -37,7 +37,7 @@
 
 namespace lb {
 
-constexpr int PQS_THREADS = 512;
+constexpr int PQS_THREADS = 640;   // 20 warps, one CTA per SM, <= 102 registers: room for two tiles of codes per lane
 constexpr int PQS_WARPS = PQS_THREADS / 32;
 constexpr int PQS_GROUP_BYTES = 65536;  // one group's table: 256 codes x 256 B
 
@@ -97,25 +97,34 @@ struct PqQParams {
     double smax_sum;   // upper bound of any real sum (for the fp32 summation error bound)
 };
 
+// grid = (query groups, QSPLIT): every block recomputes the (cheap) per-query statistics and fills its slice of
+// the group's table, so a single query's table build is spread over QSPLIT SMs.
+constexpr int PQS_QSPLIT = 16;
+
 template <int NQ>
 __global__ void __launch_bounds__(256)
 adc_quantise_kernel(const float* __restrict__ luts, int M, int G, int nq, uint8_t* __restrict__ lutq,
                     PqQParams* __restrict__ params) {
-    __shared__ float s_min[4][256];   // [q][j] (M <= 96 here; sized for safety to 256)
-    __shared__ double s_rng[4][256];
-    __shared__ double s_scale[4];
-    const int qg = blockIdx.x, tid = threadIdx.x;
-    for (int qi = 0; qi < NQ; qi++) {
+    __shared__ float s_min[NQ][96];
+    __shared__ double s_rng[NQ][96];
+    __shared__ double s_scale[NQ];
+    const int qg = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // statistics: one warp per (query, sub-quantiser), lanes stride the 256 codes (coalesced)
+    for (int w = warp; w < NQ * M; w += 8) {
+        const int qi = w / M, j = w - qi * M;
         const int q = qg * NQ + qi;
-        for (int j = tid; j < M; j += blockDim.x) {
-            float mn = INFINITY, mx = -INFINITY;
-            if (q < nq) {
-                const float* t = luts + ((size_t)q * M + j) * 256;
-                for (int c = 0; c < 256; c++) { const float v = t[c]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
-            } else { mn = 0.f; mx = 0.f; }
-            s_min[qi][j] = mn;
-            s_rng[qi][j] = (double)mx - (double)mn;
-        }
+        float mn = INFINITY, mx = -INFINITY;
+        if (q < nq) {
+            const float* t = luts + ((size_t)q * M + j) * 256;
+#pragma unroll
+            for (int c = 0; c < 8; c++) { const float v = __ldg(t + c * 32 + lane); mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+        } else { mn = 0.f; mx = 0.f; }
+        if (lane == 0) { s_min[qi][j] = mn; s_rng[qi][j] = (double)mx - (double)mn; }
     }
     __syncthreads();
     if (tid < NQ) {
@@ -129,7 +138,7 @@ adc_quantise_kernel(const float* __restrict__ luts, int M, int G, int nq, uint8_
         const double smax = (NQ == 1) ? floor(4294960000.0 / (double)M) : 4095.0;  // sums stay below 2^32 - 1
         const double scale = (R > 0 && isfinite(R)) ? smax / R : 0.0;
         s_scale[tid] = scale;
-        if (q < nq) {
+        if (q < nq && blockIdx.y == 0) {
             params[q].base = base;
             params[q].inv_scale = scale > 0 ? 1.0 / scale : 0.0;
             params[q].smax_sum = top;
@@ -143,12 +152,12 @@ adc_quantise_kernel(const float* __restrict__ luts, int M, int G, int nq, uint8_
         const double scale = s_scale[0];
         uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
         const int total = G * 256 * 64;
-        for (int e = tid; e < total; e += blockDim.x) {
+        for (int e = blockIdx.y * 256 + tid; e < total; e += gridDim.y * 256) {
             const int s = e & 63, c = (e >> 6) & 255, g = e >> 14;
             const int j = g * 32 + (s & 31);
             uint32_t v = 0;
             if (j < M && q < nq) {
-                const double x = ((double)luts[((size_t)q * M + j) * 256 + c] - (double)s_min[0][j]) * scale;
+                const double x = ((double)__ldg(luts + ((size_t)q * M + j) * 256 + c) - (double)s_min[0][j]) * scale;
                 v = (uint32_t)llrint(x);
             }
             o32[e] = v;
@@ -157,16 +166,16 @@ adc_quantise_kernel(const float* __restrict__ luts, int M, int G, int nq, uint8_
         // [g][code][32 slots] of 4 x u16
         uint2* o64 = reinterpret_cast<uint2*>(out);
         const int total = G * 256 * 32;
-        for (int e = tid; e < total; e += blockDim.x) {
+        for (int e = blockIdx.y * 256 + tid; e < total; e += gridDim.y * 256) {
             const int s = e & 31, c = (e >> 5) & 255, g = e >> 13;
             const int j = g * 32 + s;
             uint32_t v[4] = {0, 0, 0, 0};
             if (j < M) {
 #pragma unroll
-                for (int qi = 0; qi < 4; qi++) {
-                    const int q = qg * 4 + qi;
+                for (int qi = 0; qi < NQ; qi++) {
+                    const int q = qg * NQ + qi;
                     if (q < nq) {
-                        const double x = ((double)luts[((size_t)q * M + j) * 256 + c] - (double)s_min[qi][j]) * s_scale[qi];
+                        const double x = ((double)__ldg(luts + ((size_t)q * M + j) * 256 + c) - (double)s_min[qi][j]) * s_scale[qi];
                         v[qi] = (uint32_t)llrint(x);
                     }
                 }
@@ -198,10 +207,122 @@ struct PqCoarseArgs {
     uint64_t* compact;        // [nq][stride]  (key << 32 | row)
     uint32_t* out_cnt;        // [nq], zeroed by the caller
     size_t stride;            // >= parts * kc
-    // shared progressive threshold: the smallest kc-th-best key any CTA of the query has published.  Some CTA
-    // holds kc live rows at or below it, so no row above it can be among the global kc best.
-    uint32_t* g_tau;          // [nq], initialised to 0xffffffff by the caller
+    // Shared progressive threshold, two sources (both only ever shrink; stale reads are safe):
+    //  g_tau [nq]: the smallest kc-th-best key any CTA of the query has published after compacting its list --
+    //    that CTA holds kc live rows at or below it;
+    //  g_min [nq][nmin]: the smallest live key every WARP of every CTA has seen so far (nmin = parts * 16 disjoint
+    //    row sets).  The kc-th smallest of those minima is an upper bound of the global kc-th best key: kc
+    //    different live rows lie at or below it.  With thousands of small row sets this bound sits within a few
+    //    percent of the true kc-th best after a fraction of the scan, with no sorting at all.
+    uint32_t* g_tau;          // initialised to 0xffffffff by the caller
+    uint32_t* g_min;          // initialised to 0xffffffff by the caller
+    int nmin;
+    // [nq], zeroed by the caller: set when a candidate had to be dropped because a CTA's list was full between two
+    // overflow checks (only degenerate tables can do that); the exact stage then reports the query uncertified
+    uint32_t* overflow;
 };
+
+// kc-th smallest (rounded UP to a histogram bin edge: still a valid upper bound) of the set entries of v[0, n).
+// Returns 0xffffffff when fewer than kc entries are set.  All threads of the block call; s_hist: int[258].
+__device__ __forceinline__ uint32_t block_kth_upper_bound(const uint32_t* __restrict__ v, int n, int kc, int* s_hist,
+                                                          int tid) {
+    constexpr int E = (4096 + PQS_THREADS - 1) / PQS_THREADS;
+    uint32_t mine[E];
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int i = tid + e * PQS_THREADS;
+        mine[e] = (i < n) ? __ldcg(v + i) : 0xffffffffu;
+        if (mine[e] != 0xffffffffu) { lo = min(lo, mine[e]); hi = max(hi, mine[e]); cnt++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (tid < 256) s_hist[tid] = 0;
+    __shared__ uint32_t s_lo[PQS_WARPS], s_hi[PQS_WARPS];
+    __shared__ int s_c[PQS_WARPS];
+    if ((tid & 31) == 0) { s_lo[tid >> 5] = lo; s_hi[tid >> 5] = hi; s_c[tid >> 5] = cnt; }
+    __syncthreads();
+    lo = 0xffffffffu; hi = 0u; cnt = 0;
+#pragma unroll
+    for (int w = 0; w < PQS_WARPS; w++) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); cnt += s_c[w]; }
+    uint32_t result = 0xffffffffu;
+    if (cnt >= kc) {  // block-uniform
+        int shift = 0;
+        while (((hi - lo) >> shift) >= 256u) shift++;
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            if (mine[e] != 0xffffffffu) atomicAdd(&s_hist[(mine[e] - lo) >> shift], 1);
+        __syncthreads();
+        if (tid == 0) {
+            int cum = 0, b = 0;
+            for (; b < 256; b++) { cum += s_hist[b]; if (cum >= kc) break; }
+            const uint64_t edge = (uint64_t)lo + (((uint64_t)b + 1) << shift) - 1;
+            s_hist[256] = (int)(uint32_t)min(edge, (uint64_t)hi);
+        }
+        __syncthreads();
+        result = (uint32_t)s_hist[256];
+    }
+    __syncthreads();
+    return result;
+}
+
+template <int NQ, int G>
+__device__ __forceinline__ void adc_tile_keys(const uint4 (&cur)[2 * G], const unsigned char* lut, int lane, uint32_t cb,
+                                              uint32_t (&key)[NQ]) {
+    if (NQ == 1) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            // byte2 of the address = g: selector index 7 -> 0, 5 -> 1, 6 -> 2 (bytes of cb)
+            const uint32_t gsel = (g == 0) ? 7u : (g == 1) ? 5u : 6u;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint4 v = cur[g * 2 + c];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int t = c * 16 + wi * 4 + b;
+                        const uint32_t addr = prmt(w[wi], cb, 0x7004u | (gsel << 8) | ((uint32_t)b << 4));
+                        acc += *reinterpret_cast<const uint32_t*>(lut + addr + t * 4);
+                    }
+            }
+        }
+        key[0] = acc;
+    } else {
+        uint32_t tot[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint4 v = cur[g * 2 + c];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                uint32_t p01 = 0, p23 = 0;  // 2 x u16 partial sums over 16 steps (entries <= 4095)
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int t = c * 16 + wi * 4 + b;
+                        const uint32_t off = (uint32_t)((lane + t) & 31) << 3;
+                        const uint32_t addr = prmt(w[wi], off, 0x7704u | ((uint32_t)b << 4));
+                        const uint2 e = *reinterpret_cast<const uint2*>(lut + addr + g * PQS_GROUP_BYTES);
+                        p01 += e.x;
+                        p23 += e.y;
+                    }
+                tot[0] += p01 & 0xffffu; tot[1] += p01 >> 16;
+                tot[2] += p23 & 0xffffu; tot[3] += p23 >> 16;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++) key[q] = tot[q];
+    }
+}
 
 template <int NQ, int G>
 __global__ void __launch_bounds__(PQS_THREADS, 1)
@@ -211,6 +332,7 @@ adc_coarse_kernel(const PqCoarseArgs a) {
     uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw + G * PQS_GROUP_BYTES);  // [NQ][cap]
     __shared__ int s_cnt[NQ];
     __shared__ uint32_t s_tau[NQ];
+    __shared__ int s_hist[258];
     constexpr int CH = 2 * G;  // 16-byte chunks per row
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int qg = blockIdx.x, part = blockIdx.y;
@@ -228,103 +350,59 @@ adc_coarse_kernel(const PqCoarseArgs a) {
     const uint32_t tile_end = min(n_tiles, tile_begin + a.tiles_per_part);
     const uint32_t iters = (tile_end > tile_begin) ? (tile_end - tile_begin + PQS_WARPS - 1) / PQS_WARPS : 0;
 
-    uint4 cur[CH], nxt[CH];
-    {
-        const uint32_t t0 = tile_begin + warp;
-#pragma unroll
-        for (int i = 0; i < CH; i++) {
-            cur[i] = make_uint4(0, 0, 0, 0);
-            if (t0 < tile_end) cur[i] = __ldcs(a.tiles + ((size_t)t0 * CH + i) * 32 + lane);
-        }
-    }
     // lane constant for the byte permute: byte0 = 4 * lane (NQ = 1), bytes 1..3 = 1, 2, 0 (group selectors)
     const uint32_t cb = (uint32_t)(lane << 2) | (1u << 8) | (2u << 16);
+    uint32_t lmin[NQ];  // smallest LIVE key this lane has seen, per query
+#pragma unroll
+    for (int q = 0; q < NQ; q++) lmin[q] = 0xffffffffu;
 
-    for (uint32_t it = 0; it < iters; it++) {
-        const uint32_t tile = tile_begin + it * PQS_WARPS + warp;
-        const uint32_t tn = tile + PQS_WARPS;
-#pragma unroll
-        for (int i = 0; i < CH; i++) {
-            nxt[i] = make_uint4(0, 0, 0, 0);
-            if (tn < tile_end) nxt[i] = __ldcs(a.tiles + ((size_t)tn * CH + i) * 32 + lane);
-        }
+    auto consume = [&](const uint4 (&cur)[CH], uint32_t tile) {
         uint32_t key[NQ];
-        if (NQ == 1) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                // byte2 of the address = g: selector index 7 -> 0, 5 -> 1, 6 -> 2 (bytes of cb)
-                const uint32_t gsel = (g == 0) ? 7u : (g == 1) ? 5u : 6u;
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const uint4 v = cur[g * 2 + c];
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int wi = 0; wi < 4; wi++)
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            const int t = c * 16 + wi * 4 + b;
-                            const uint32_t addr = prmt(w[wi], cb, 0x7004u | (gsel << 8) | ((uint32_t)b << 4));
-                            acc += *reinterpret_cast<const uint32_t*>(lut + addr + t * 4);
-                        }
-                }
-            }
-            key[0] = acc;
-        } else {
-            uint32_t tot[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const uint4 v = cur[g * 2 + c];
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                    uint32_t p01 = 0, p23 = 0;  // 2 x u16 partial sums over 16 steps (entries <= 4095)
-#pragma unroll
-                    for (int wi = 0; wi < 4; wi++)
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            const int t = c * 16 + wi * 4 + b;
-                            const uint32_t off = (uint32_t)((lane + t) & 31) << 3;
-                            const uint32_t addr = prmt(w[wi], off, 0x7704u | ((uint32_t)b << 4));
-                            const uint2 e = *reinterpret_cast<const uint2*>(lut + addr + g * PQS_GROUP_BYTES);
-                            p01 += e.x;
-                            p23 += e.y;
-                        }
-                    tot[0] += p01 & 0xffffu; tot[1] += p01 >> 16;
-                    tot[2] += p23 & 0xffffu; tot[3] += p23 >> 16;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < NQ; q++) key[q] = tot[q];
-        }
+        adc_tile_keys<NQ, G>(cur, lut, lane, cb, key);
         const uint32_t row = (tile << 5) + lane;
         if (tile < tile_end && row < a.n_rows) {
             bool any = false;
 #pragma unroll
-            for (int q = 0; q < NQ; q++) any = any || (q < nvalid && key[q] <= s_tau[q]);
-            if (any) {
+            for (int q = 0; q < NQ; q++) any = any || (q < nvalid && (key[q] <= s_tau[q] || key[q] < lmin[q]));
+            if (any) {  // rare once the threshold is tight: only now are the bitmaps consulted
                 bool ok = true;
                 if (a.tomb != nullptr && row < a.tomb_bits && bit_set(a.tomb, row)) ok = false;
                 if (ok && a.allow != nullptr && !bit_set(a.allow, row)) ok = false;
                 if (ok) {
 #pragma unroll
                     for (int q = 0; q < NQ; q++) {
-                        if (q < nvalid && key[q] <= s_tau[q]) {
+                        if (q >= nvalid) continue;
+                        lmin[q] = min(lmin[q], key[q]);
+                        if (key[q] <= s_tau[q]) {
                             const int pos = atomicAdd(&s_cnt[q], 1);
                             if (pos < a.cap) cand[(size_t)q * a.cap + pos] = ((uint64_t)key[q] << 32) | row;
+                            else a.overflow[qg * NQ + q] = 1u;
                         }
                     }
                 }
             }
         }
+    };
+    auto prefetch = [&](uint4 (&dst)[CH], uint32_t tile) {
 #pragma unroll
-        for (int i = 0; i < CH; i++) cur[i] = nxt[i];
+        for (int i = 0; i < CH; i++) {
+            dst[i] = make_uint4(0, 0, 0, 0);
+            if (tile < tile_end) dst[i] = __ldcs(a.tiles + ((size_t)tile * CH + i) * 32 + lane);
+        }
+    };
+    auto housekeeping = [&](uint32_t it) {
+        // Block barriers only on a doubling schedule (after trips 1, 2, 4, 8, ...): list compaction and threshold
+        // refresh from the shared bounds, which improve with the logarithm of the rows scanned.  Between them the
+        // warps run free -- a barrier every trip locks their load and look-up phases together, and then HBM latency
+        // and shared-memory look-ups add up instead of overlapping (measured: 203k + 278k cycles per SM).  A list
+        // that fills up between two barriers sets the overflow flag (degenerate tables only).
+        const bool pow2 = ((it + 1) & it) == 0;
+        if (!pow2) return;  // block-uniform
         __syncthreads();
-        // compaction of any list that could overflow during the next trip (<= 512 appends per trip)
 #pragma unroll 1
-        for (int q = 0; q < NQ; q++) {
+        for (int q = 0; q < nvalid; q++) {
             const int c = min(s_cnt[q], a.cap);
-            if (c > a.cap - PQS_THREADS) {  // block-uniform
+            if (c > a.cap / 2) {  // block-uniform
                 uint64_t* buf = cand + (size_t)q * a.cap;
                 const int n2 = next_pow2(c);
                 for (int t = c + tid; t < n2; t += PQS_THREADS) buf[t] = kInvalid;
@@ -341,10 +419,43 @@ adc_coarse_kernel(const PqCoarseArgs a) {
                 __syncthreads();
             }
         }
-        // fold in what the other CTAs of the query have published (stale values are safe: it only shrinks)
-        if (tid < nvalid) s_tau[tid] = min(s_tau[tid], __ldcg(a.g_tau + qg * NQ + tid));
+        if (pow2) {
+            // publish this warp's minima, then bound the query's kc-th best by the kc-th smallest published minimum
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                uint32_t m = lmin[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0 && q < nvalid && m != 0xffffffffu)
+                    atomicMin(a.g_min + (size_t)(qg * NQ + q) * a.nmin + part * PQS_WARPS + warp, m);
+            }
+            __threadfence();
+            __syncthreads();
+#pragma unroll 1
+            for (int q = 0; q < nvalid; q++) {
+                const uint32_t b = block_kth_upper_bound(a.g_min + (size_t)(qg * NQ + q) * a.nmin, a.nmin, a.kc, s_hist, tid);
+                if (tid == 0) s_tau[q] = min(min(s_tau[q], b), __ldcg(a.g_tau + qg * NQ + q));
+            }
+        }
         __syncthreads();
+    };
+
+    // two trips per loop iteration with ping-pong register buffers: the next tile's codes are in flight while the
+    // current tile's look-ups run
+    uint4 buf0[CH], buf1[CH];
+    prefetch(buf0, tile_begin + warp);
+    uint32_t it = 0;
+#pragma unroll 1
+    for (; it + 1 < iters; it += 2) {
+        const uint32_t tile = tile_begin + it * PQS_WARPS + warp;
+        prefetch(buf1, tile + PQS_WARPS);
+        consume(buf0, tile);
+        housekeeping(it);
+        prefetch(buf0, tile + 2 * PQS_WARPS);
+        consume(buf1, tile + PQS_WARPS);
+        housekeeping(it + 1);
     }
+    if (it < iters) consume(buf0, tile_begin + it * PQS_WARPS + warp);
     __syncthreads();
     // emit: this CTA's best kc per query, restricted to entries at or below the query's shared bound, appended to
     // the query's compact global list (one global atomic per CTA and query; order is irrelevant, the merge sorts)
@@ -362,7 +473,7 @@ adc_coarse_kernel(const PqCoarseArgs a) {
             c = a.kc;
             if (tid == 0) atomicMin(a.g_tau + gq, (uint32_t)(buf[a.kc - 1] >> 32));
         }
-        if (tid == 0) { s_keep = 0; s_w = 0; s_gt = __ldcg(a.g_tau + gq); }  // ONE read: count and copy must agree
+        if (tid == 0) { s_keep = 0; s_w = 0; s_gt = min(s_tau[q], __ldcg(a.g_tau + gq)); }  // ONE value for count and copy
         __syncthreads();
         const uint32_t gt = s_gt;
         uint32_t keep = 0;
@@ -383,30 +494,50 @@ adc_coarse_kernel(const PqCoarseArgs a) {
 // ---------------------------------------------------------------------------------------------
 // Exact stage: the reference's sequential fp32 sum + sqrt for the kc coarse candidates of each query, sort by
 // (distance, id), certification, first k_out packed (distance, row) entries out (ascending; kInvalid padding).
-// grid = nq, block = 256.
+// grid = nq, block = 256.  Candidates are processed 64 at a time: all threads first fetch the 64 x M table values
+// (code byte, then LUT entry: two dependent loads, M independent pairs per candidate in flight), then thread c adds
+// candidate c's values in j order out of shared memory (row pitch M + 1: conflict free).
 // ---------------------------------------------------------------------------------------------
+constexpr int PQX_CHUNK = 64;
+
 __global__ void __launch_bounds__(256)
 adc_exact_kernel(const uint8_t* __restrict__ tiled, int M, int Mp, const float* __restrict__ luts,
                  const uint64_t* __restrict__ coarse, int kc, int k_out, const PqQParams* __restrict__ params,
-                 uint64_t* __restrict__ out, uint32_t* __restrict__ cert_flags, uint32_t* __restrict__ cert_count) {
-    __shared__ uint64_t keys[2048];
+                 const uint32_t* __restrict__ overflow, uint64_t* __restrict__ out, uint32_t* __restrict__ cert_flags,
+                 uint32_t* __restrict__ cert_count) {
+    __shared__ uint64_t keys[1024];
+    __shared__ float vals[PQX_CHUNK * 97];
     const int q = blockIdx.x, tid = threadIdx.x;
     const int n2 = next_pow2(max(kc, 2));
     const float* lut = luts + (size_t)q * M * 256;
-    for (int ci = tid; ci < n2; ci += blockDim.x) {
-        uint64_t mine = kInvalid;
-        if (ci < kc) {
-            const uint64_t p = coarse[(size_t)q * kc + ci];
-            if (p != kInvalid) {
-                const uint32_t row = (uint32_t)p;
-                float sum = 0.f;
-                for (int j = 0; j < M; j++) sum = __fadd_rn(sum, __ldg(lut + j * 256 + tiled_code(tiled, Mp, row, j)));
-                mine = pack_key(__fsqrt_rn(sum), row);
+    const int pitch = M + 1;
+    for (int c0 = 0; c0 < n2; c0 += PQX_CHUNK) {
+        for (int e = tid; e < PQX_CHUNK * M; e += blockDim.x) {
+            const int c = e / M, j = e - c * M;
+            const int ci = c0 + c;
+            float v = 0.f;
+            if (ci < kc) {
+                const uint64_t p = coarse[(size_t)q * kc + ci];
+                if (p != kInvalid) v = __ldg(lut + j * 256 + tiled_code(tiled, Mp, (uint32_t)p, j));
             }
+            vals[c * pitch + j] = v;
         }
-        keys[ci] = mine;
+        __syncthreads();
+        if (tid < PQX_CHUNK && c0 + tid < n2) {
+            const int ci = c0 + tid;
+            uint64_t mine = kInvalid;
+            if (ci < kc) {
+                const uint64_t p = coarse[(size_t)q * kc + ci];
+                if (p != kInvalid) {
+                    float sum = 0.f;
+                    for (int j = 0; j < M; j++) sum = __fadd_rn(sum, vals[tid * pitch + j]);
+                    mine = pack_key(__fsqrt_rn(sum), (uint32_t)p);
+                }
+            }
+            keys[ci] = mine;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     block_bitonic_sort(keys, n2);
     if (tid == 0 && cert_flags != nullptr) {
         // every row outside the candidate set has an integer key >= the largest candidate key (the list holds the
@@ -424,6 +555,7 @@ adc_exact_kernel(const uint8_t* __restrict__ tiled, int M, int Mp, const float* 
             const double dk = (double)key_of(kth);
             cert = pr.inv_scale > 0.0 && lb > 0.0 && sqrt(lb) * (1.0 - 2.0e-7) > dk;
         }
+        if (overflow != nullptr && overflow[q]) cert = false;
         cert_flags[q] = cert ? 0u : 1u;
         if (!cert && cert_count != nullptr) atomicAdd(cert_count, 1u);
     }
@@ -435,8 +567,8 @@ adc_exact_kernel(const uint8_t* __restrict__ tiled, int M, int Mp, const float* 
 // ---------------------------------------------------------------------------------------------
 bool adc_coarse_eligible(int M, int kc, int nq_per_pass) {
     if (M < 1 || M > 96) return false;
-    if (nq_per_pass == 4) return kc <= 512;
-    return kc <= 1024;
+    if (nq_per_pass == 4) return kc <= 256;
+    return kc <= 768;
 }
 
 size_t adc_lutq_bytes(int M, int nq, int nq_per_pass) {
@@ -457,16 +589,19 @@ static cudaError_t launch_coarse_t(const PqCoarseArgs& a, int qgroups, int parts
 }
 
 // luts: fp32 [nq][M*256] (adc_lut_kernel).  Scratch supplied by the caller: lutq (adc_lutq_bytes), params
-// (adc_params_bytes), compact [nq][stride >= parts * kc] u64, out_cnt [nq] zeroed, g_tau [nq] set to 0xff bytes.
+// (adc_params_bytes), compact [nq][stride >= parts * kc] u64, out_cnt [nq] + overflow [nq] zeroed, g_tau [nq] and
+// g_min [nq][adc_min_slots(parts)] set to 0xff bytes.
 cudaError_t launch_adc_coarse(const uint8_t* tiled, uint32_t n_rows, int M, const float* luts, int nq, int nq_per_pass,
                               const uint32_t* tomb, uint32_t tomb_bits, const uint32_t* allow, int kc, int parts,
                               uint32_t tiles_per_part, uint8_t* lutq, void* params, uint64_t* compact,
-                              uint32_t* out_cnt, size_t stride, uint32_t* g_tau, cudaStream_t st) {
+                              uint32_t* out_cnt, size_t stride, uint32_t* g_tau, uint32_t* g_min, uint32_t* overflow,
+                              cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     const int G = (M + 31) / 32;
     const int qgroups = (nq + nq_per_pass - 1) / nq_per_pass;
-    if (nq_per_pass == 1) adc_quantise_kernel<1><<<qgroups, 256, 0, st>>>(luts, M, G, nq, lutq, (PqQParams*)params);
-    else adc_quantise_kernel<4><<<qgroups, 256, 0, st>>>(luts, M, G, nq, lutq, (PqQParams*)params);
+    const dim3 qgrid(qgroups, qgroups >= 64 ? 4 : PQS_QSPLIT);
+    if (nq_per_pass == 1) adc_quantise_kernel<1><<<qgrid, 256, 0, st>>>(luts, M, G, nq, lutq, (PqQParams*)params);
+    else adc_quantise_kernel<4><<<qgrid, 256, 0, st>>>(luts, M, G, nq, lutq, (PqQParams*)params);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -474,8 +609,8 @@ cudaError_t launch_adc_coarse(const uint8_t* tiled, uint32_t n_rows, int M, cons
     a.tiles = reinterpret_cast<const uint4*>(tiled); a.n_rows = n_rows; a.tiles_per_part = tiles_per_part;
     a.lutq = lutq; a.tomb = tomb; a.tomb_bits = tomb_bits; a.allow = allow;
     a.kc = kc; a.nq = nq; a.compact = compact; a.out_cnt = out_cnt; a.stride = stride; a.g_tau = g_tau;
+    a.g_min = g_min; a.nmin = parts * PQS_WARPS; a.overflow = overflow;
     a.cap = (nq_per_pass == 1) ? 2048 : 1024;
-    if (a.cap < next_pow2(kc + PQS_THREADS)) a.cap = next_pow2(kc + PQS_THREADS);
 #define LB_PQC(NQ_, G_) return launch_coarse_t<NQ_, G_>(a, qgroups, parts, st)
     if (nq_per_pass == 1) {
         if (G == 1) LB_PQC(1, 1);
@@ -489,17 +624,18 @@ cudaError_t launch_adc_coarse(const uint8_t* tiled, uint32_t n_rows, int M, cons
 }
 
 cudaError_t launch_adc_exact(const uint8_t* tiled, int M, const float* luts, const uint64_t* coarse, int nq, int kc,
-                             int k_out, const void* params, uint64_t* out, uint32_t* cert_flags, uint32_t* cert_count,
-                             cudaStream_t st) {
+                             int k_out, const void* params, const uint32_t* overflow, uint64_t* out,
+                             uint32_t* cert_flags, uint32_t* cert_count, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    if (kc > 2048) return cudaErrorInvalidValue;
+    if (kc > 1024 || M > 96) return cudaErrorInvalidValue;
     const int Mp = ((M + 31) / 32) * 32;
-    adc_exact_kernel<<<nq, 256, 0, st>>>(tiled, M, Mp, luts, coarse, kc, k_out, (const PqQParams*)params, out,
+    adc_exact_kernel<<<nq, 256, 0, st>>>(tiled, M, Mp, luts, coarse, kc, k_out, (const PqQParams*)params, overflow, out,
                                          cert_flags, cert_count);
     count_launch();
     return cudaGetLastError();
 }
 
 size_t adc_params_bytes(int nq) { return (size_t)nq * sizeof(PqQParams); }
+int adc_min_slots(int parts) { return parts * PQS_WARPS; }  // one published minimum per warp of every CTA
 
 }  // namespace lb

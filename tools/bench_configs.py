@@ -125,6 +125,9 @@ def c3():
            f"per-query pass rate {Q * N * M / (ms * 1e-3) / 1e9:.1f} GB/s of codes consumed")
     # with the fp32 re-rank of k'=100 candidates (raw vectors: decode(codes) + noise)
     NR = int(os.environ.get("C3_RAW", N))
+    if NR < N:  # the re-rank needs the raw vector of every coded row
+        enc.close()
+        return
     raw = gpu.DenseIndex(D, np.float32, _lib.METRIC_L2)
     raw.reserve(NR)
     step = 500_000
