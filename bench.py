@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                 util = nv.nvmlDeviceGetUtilizationRates(h).gpu
                 mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.sm.append((mhz, util))
+                self.sm.append((mhz, util, time.time(), r))
                 for n, bit in names.items():
                     if r & bit:
                         self.reasons.add(n)
@@ -87,10 +87,25 @@ class ClockSampler(threading.Thread):
         except Exception as e:  # NVML missing: report nothing rather than die
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
+    NAMES = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+             "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10}
+
     def summary(self):
-        vals = [m for m, _ in self.sm]
+        vals = [s[0] for s in self.sm]
         return {"sm_mhz": statistics.median(vals) if vals else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(vals)}
+
+    def window(self, t0, t1):
+        """Clock record of one config's timed region [t0, t1] (wall clock)."""
+        sel = [s for s in self.sm if t0 <= s[2] <= t1]
+        reasons = set()
+        for s in sel:
+            for n, bit in self.NAMES.items():
+                if s[3] & bit:
+                    reasons.add(n)
+        vals = [s[0] for s in sel]
+        return {"sm_mhz": statistics.median(vals) if vals else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(vals)}
 
 
 def cpu_baseline(db_np, q_np, k):
@@ -150,6 +165,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--rows", type=int, default=N_ROWS, help="debug only: a smaller DB invalidates the number")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--configs", default="all", help="extra BASELINE configs in the `configs` array: all | none | C1,C3,...")
     args = ap.parse_args()
     wd = int(os.environ.get("LB_WATCHDOG", "0"))
     if wd > 0:  # debug: dump all Python stacks and exit if the run wedges
@@ -254,9 +270,7 @@ def main():
             run_steps(warm + steps, 2)
         join_streams()
         torch.cuda.synchronize()
-    sampler.stop_flag = True
-    sampler.join(timeout=5)
-    log("clock sampler joined")
+    main_clocks = sampler.summary()
     uncertified = sidx.uncertified()
     if world > 1:
         sidx.check_exchange()
@@ -304,6 +318,8 @@ def main():
         # the last step of caller 0 must equal a fresh single-caller answer for the same batch
         sidx.index.search_into(hq[last[0]], K, hd, hl)
         checks["concurrent_callers_agree"] = bool(np.array_equal(hl, bufs[0][1]) and np.array_equal(hd, bufs[0][0]))
+        sidx.index.search_into(hq[0], K, hd, hl)
+        c2_first_d, c2_first_l = hd.copy(), hl.copy()
         e2e = {"value": NQ * steps / dt, "unit": "queries/s", "h2d_bytes_per_step": NQ * DIM * 2,
                "d2h_bytes_per_step": NQ * K * 12, "ms_per_step": dt / steps * 1e3, "callers": callers,
                "single_caller_value": NQ * steps / dt1, "single_caller_ms_per_step": dt1 / steps * 1e3}
@@ -374,12 +390,32 @@ def main():
                         "scan_kernel_ms": k_ms / k_n, "bytes_per_launch": rows_scanned * DIM * 2,
                         "achieved_gbs": rows_scanned * DIM * 2 / (k_ms / k_n * 1e-3) / 1e9}
 
+    # ---- the other BASELINE configs (C1, C3, C5 at N = 1; C4 at every N, row-sharded at N > 1): bench_extra.py
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    extra = []
+    if args.configs != "none" and n_rows == N_ROWS:
+        import bench_extra
+        from longbow_b200 import gpu as _gpu2, pq as _pq2
+        sidx.close()  # free the C2 shard before the large configs
+        del d_qs
+        torch.cuda.empty_cache()
+        ctx = {"torch": torch, "_lib": _lib, "gpu": _gpu2, "pq": _pq2, "dev": dev, "local": local, "rank": rank,
+               "world": world, "steps": max(6, steps // 2), "peaks": peaks, "cpu": (not args.no_cpu) and world == 1,
+               "timer": bench_extra.Timer(torch, _lib, sampler),
+               "only": None if args.configs == "all" else [c.strip().upper() for c in args.configs.split(",")]}
+        extra = bench_extra.run_all(ctx)
+        for r in extra:
+            for name, ok in (r.get("checks") or {}).items():
+                checks[f"{r['name']}.{name}"] = ok
+    sampler.stop_flag = True
+    sampler.join(timeout=5)
+    log("clock sampler joined")
+
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         peak_tf = peaks.get("bf16_tflops", 1590.0)
         peak_src = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1.59 PFLOP/s"
         rows_local = hi - lo
@@ -423,14 +459,22 @@ def main():
                        "streams": ("batches alternate between 2 CUDA streams (tail kernels overlap the next scan)"
                                    + ("" if world == 1 else "; exchange (peer-memory push + signal + merge) in batch "
                                       "order on one side stream"))},
-            "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof,
-            "checks": checks, "uncertified": uncertified,
+            "e2e": e2e, "gpu_launches": launches, "clocks": main_clocks, "roofline": roof,
+            "checks": checks, "uncertified": uncertified, "configs": extra,
         }
         failed = [name for name, ok in checks.items() if ok is False]
         for name in failed:
             print(f"[bench] CHECK FAILED: {name}", file=sys.stderr, flush=True)
         if not args.no_cpu and world == 1:
             out["cpu_baseline"] = cpu_baseline(db.numpy(), qs[0].numpy(), K)
+            # the CPU sample doubles as a checker: the GPU's answers for the sample's queries must equal the port's
+            # (O-exact, the reference's lane order: ids and distances bit-equal)
+            from oracle import oracle as _o
+            nqs = 16
+            wd_, wl_ = _o.search(_o.COSINE, db.numpy(), qs[0].numpy()[:nqs], K)
+            out["checks"]["C2.equals_exact_oracle_16q"] = bool(np.array_equal(c2_first_l[:nqs], wl_) and
+                                                               np.array_equal(c2_first_d[:nqs], wd_))
+            failed = [name for name, ok in out["checks"].items() if ok is False]
         emit(out)
     if world > 1:
         dist.barrier()

@@ -1,0 +1,376 @@
+"""bench_extra.py -- the other BASELINE.json configs (C1, C3, C4, C5) as driver-visible entries of bench.py's JSON
+line (`configs`).  bench.py's headline stays C2; each entry here carries its own value (QPS, device-resident,
+CUDA events), e2e (host buffers through the C ABI), roofline (algorithmic bytes / flops per SURVEY.md 8(d) over
+the CUDA-event time of the dominant kernel), clocks sampled during its timed region, a bounded CPU baseline
+(oracle port, all host cores) and a parity check of the GPU answers for the CPU sample's queries.
+
+Synthetic inputs follow SURVEY.md 8(d) (distributions, sizes); they are generated on the GPU with seeded torch
+generators and copied to the host only where the CPU sample needs them.
+"""
+import os
+import time
+
+import numpy as np
+
+
+def _peaks(root):
+    import json
+    try:
+        return json.load(open(os.path.join(root, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class Timer:
+    """W warm-up + K timed calls of fn with CUDA events on the current stream; dominant-kernel time from lb_prof."""
+
+    def __init__(self, torch, _lib, sampler):
+        self.torch, self._lib, self.sampler = torch, _lib, sampler
+
+    def run(self, fn, steps, warm=3):
+        torch, _lib = self.torch, self._lib
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        _lib.prof_read(reset=True)
+        _lib.prof_enable(True)
+        l0 = _lib.launch_count()
+        t0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        _lib.prof_enable(False)
+        k_ms, k_n, k_units = _lib.prof_read(reset=True)
+        return {"ms": e0.elapsed_time(e1) / steps, "kernel_ms": (k_ms / k_n) if k_n else None,
+                "kernel_launches": k_n, "launches": _lib.launch_count() - l0,
+                "clocks": self.sampler.window(t0, t1) if self.sampler else None}
+
+
+def _host_timer(fn, steps, warm=2):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    return (time.perf_counter() - t0) / steps * 1e3
+
+
+def _roof_hbm(bytes_per_launch, kernel_ms, peaks, kernel, traffic=None):
+    peak = peaks.get("hbm_gbs", 6650.0)
+    ach = bytes_per_launch / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+            "traffic": traffic, "kernel": kernel, "avg_launch_ms": kernel_ms,
+            "algorithmic_bytes_per_launch": bytes_per_launch,
+            "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s"}
+
+
+def _roof_tensor(flops_per_launch, kernel_ms, peaks, kernel, note=None):
+    peak = peaks.get("bf16_tflops", 1590.0)
+    ach = flops_per_launch / (kernel_ms * 1e-3) / 1e12 if kernel_ms else None
+    out = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
+           "traffic": None, "kernel": kernel, "avg_launch_ms": kernel_ms,
+           "algorithmic_flops_per_launch": flops_per_launch,
+           "peak_source": "measured burst bf16 (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1.59 PFLOP/s"}
+    if note:
+        out["note"] = note
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- C1
+def config_c1(ctx):
+    torch, _lib, gpu, dev = ctx["torch"], ctx["_lib"], ctx["gpu"], ctx["dev"]
+    N, D, Q, K = 100_000, 128, 1000, 10
+    g = torch.Generator(device=dev).manual_seed(1001)
+    db = torch.rand((N, D), generator=g, device=dev)
+    g2 = torch.Generator(device=dev).manual_seed(1002)
+    qs = torch.rand((Q, D), generator=g2, device=dev)
+    idx = gpu.DenseIndex(D, np.float32, _lib.METRIC_L2, ctx["local"])
+    idx.add_device(db)
+    od = torch.empty((Q, K), dtype=torch.float32, device=dev)
+    ol = torch.empty((Q, K), dtype=torch.int64, device=dev)
+    t = ctx["timer"].run(lambda: idx.search_device(qs, K, od, ol), ctx["steps"])
+    hq = qs.cpu().numpy()
+    hd, hl = np.empty((Q, K), np.float32), np.empty((Q, K), np.int64)
+    e2e_ms = _host_timer(lambda: idx.search_into(hq, K, hd, hl), max(3, ctx["steps"] // 2))
+    out = {"name": "C1", "workload": "brute-force L2 k=10, 100k x 128 fp32 U[0,1), 1000 queries (the reference's CPU-runnable case)",
+           "value": Q / (t["ms"] * 1e-3), "unit": "queries/s", "ms_per_step": t["ms"], "steps": ctx["steps"], "dtype": "f32",
+           "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 12},
+           "roofline": _roof_tensor(2.0 * Q * N * D, t["kernel_ms"], ctx["peaks"], "dense_scan_tc<tf32 x3> (3xTF32 split: "
+                                    "three MMAs per k-step; flops counted once)",
+                                    "51 MB database is L2-resident: launch/latency-bound, 5 kernels per search"),
+           "gpu_launches": t["launches"], "clocks": t["clocks"], "checks": {}}
+    if ctx["cpu"]:
+        from oracle import oracle
+        cores = oracle.fast_use_all_cores()
+        dbh = db.cpu().numpy()
+        t0 = time.perf_counter()
+        wd, wl = oracle.search(oracle.L2, dbh, hq, K, impl="fast")
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": Q / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                               "sample": f"the full config: {Q} queries x {N} x {D} fp32, {oracle.fast_isa()} + OpenMP, {dt:.2f} s"}
+        ed, el = oracle.search(oracle.L2, dbh, hq[:64], K)  # O-exact on 64 queries
+        out["checks"]["equals_exact_oracle_64q"] = bool(np.array_equal(hl[:64], el) and np.array_equal(hd[:64], ed))
+    idx.close()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- C3
+def config_c3(ctx):
+    torch, _lib, gpu, pq, dev = ctx["torch"], ctx["_lib"], ctx["gpu"], ctx["pq"], ctx["dev"]
+    N, D, M, K, KP, Q = ctx.get("c3_rows", 10_000_000), 768, 96, 10, 100, 256
+    g = torch.Generator(device=dev).manual_seed(3001)
+    codes = torch.randint(0, 256, (N, M), generator=g, device=dev, dtype=torch.uint8)
+    g = torch.Generator(device=dev).manual_seed(3002)
+    cb = torch.randn((M, 256, D // M), generator=g, device=dev)
+    g = torch.Generator(device=dev).manual_seed(3004)
+    qs = torch.randn((Q, D), generator=g, device=dev)
+    enc = pq.PQEncoder(D, M, 256, cb.cpu().numpy(), ctx["local"])
+    enc.add_codes_device(codes)
+    # raw vectors for the fp32 re-rank: decode(codes) + N(0, 0.05)  (30.7 GB at 10 M rows)
+    raw = gpu.DenseIndex(D, np.float32, _lib.METRIC_L2, ctx["local"])
+    raw.reserve(N)
+    g = torch.Generator(device=dev).manual_seed(3003)
+    step = 250_000
+    for lo in range(0, N, step):
+        hi = min(N, lo + step)
+        c = codes[lo:hi].long()
+        v = torch.stack([cb[m][c[:, m]] for m in range(M)], dim=1).reshape(hi - lo, D)
+        v += 0.05 * torch.randn(v.shape, generator=g, device=dev)
+        raw.add_device(v.contiguous())
+    del v, c
+    enc.attach_raw(raw)
+    od = torch.empty((Q, K), dtype=torch.float32, device=dev)
+    ol = torch.empty((Q, K), dtype=torch.int64, device=dev)
+    steps = max(2, ctx["steps"] // 4)
+    t = ctx["timer"].run(lambda: enc.search_device(qs, K, KP, od, ol), steps, warm=1)
+    # one query per pass: the HBM-bound form of the scan (N * M code bytes per pass)
+    q1 = qs[:1].contiguous()
+    o1d = torch.empty((1, K), dtype=torch.float32, device=dev)
+    o1l = torch.empty((1, K), dtype=torch.int64, device=dev)
+    t1 = ctx["timer"].run(lambda: enc.search_device(q1, K, KP, o1d, o1l), ctx["steps"])
+    hq = qs.cpu().numpy()
+    hd, hl = np.empty((Q, K), np.float32), np.empty((Q, K), np.int64)
+    e2e_ms = _host_timer(lambda: enc.search_into(hq, K, KP, hd, hl), 2, warm=1)
+    lookups = float(Q) * N * M
+    out = {"name": "C3", "workload": f"PQ ADC scan M=96 nbits=8 over {N} x 768 codes + fp32 re-rank k'=100 -> k=10, 256 queries",
+           "value": Q / (t["ms"] * 1e-3), "unit": "queries/s", "ms_per_step": t["ms"], "steps": steps, "dtype": "u8 codes, u16/u32 coarse sums, f32 exact",
+           "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 12, "uncertified": enc.last_uncertified()},
+           "roofline": _roof_hbm(float(N) * M, t1["kernel_ms"], ctx["peaks"],
+                                 "adc_coarse_kernel<1,3> (one query per pass: N*M code bytes)"),
+           "batch_scan": {"queries_per_pass": 4, "passes": Q // 4, "kernel_ms": t["kernel_ms"],
+                          "lookups_per_s": lookups / (t["kernel_ms"] * 1e-3) if t["kernel_ms"] else None,
+                          "bound": "shared-memory look-up rate: 8 B per (row, sub-quantiser) for 4 queries, "
+                                   "128 B/clk/SM (tools/micro/lds_rate.cu)",
+                          "smem_bytes_per_s": lookups * 2 / (t["kernel_ms"] * 1e-3) if t["kernel_ms"] else None},
+           "single_query": {"ms_per_call": t1["ms"], "scan_kernel_ms": t1["kernel_ms"]},
+           "gpu_launches": t["launches"], "clocks": t["clocks"], "checks": {}}
+    if ctx["cpu"]:
+        from oracle import oracle
+        cores = oracle.fast_use_all_cores()
+        nqs = min(Q, max(8, cores))
+        ch, cbh = codes.cpu().numpy(), cb.cpu().numpy()
+        t0 = time.perf_counter()
+        wd, wl = oracle.pq_search(cbh, ch, None, hq[:nqs], K, 0, impl="fast")
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": nqs / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                               "sample": f"{nqs} queries x full {N} x 96 codes, ADC scan + top-10 without the fp32 re-rank "
+                                         f"(raw vectors stay on the GPU), {oracle.fast_isa()} gather + OpenMP, {dt:.2f} s"}
+        enc.attach_raw(None)
+        gd, gl = enc.search(hq[:nqs], K)
+        out["checks"]["adc_topk_equals_oracle"] = bool(np.array_equal(gl, wl) and np.array_equal(gd, wd))
+    enc.close()
+    raw.close()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- C4
+def _c4_shard(torch, dev, rank, rows):
+    g = torch.Generator(device=dev).manual_seed(4001 + rank)
+    return torch.randint(-128, 128, (rows, 128), generator=g, device=dev, dtype=torch.int8)
+
+
+def config_c4(ctx):
+    torch, _lib, gpu, dev = ctx["torch"], ctx["_lib"], ctx["gpu"], ctx["dev"]
+    world, rank = ctx["world"], ctx["rank"]
+    ROWS, D, Q, K = ctx.get("c4_rows", 12_500_000), 128, 1024, 10
+    from longbow_b200.shard import ShardedIndex
+    sidx = ShardedIndex(D, np.int8, _lib.METRIC_DOT, ROWS * world, rank, world, ctx["local"])
+    sidx.index.reserve(ROWS)
+    sidx.add_local_device(_c4_shard(torch, dev, rank, ROWS))
+    g = torch.Generator(device=dev).manual_seed(4002)
+    nb = 4
+    qs = torch.randint(-128, 128, (nb, Q, D), generator=g, device=dev, dtype=torch.int8)
+    od = torch.empty((Q, K), dtype=torch.float32, device=dev)
+    ol = torch.empty((Q, K), dtype=torch.int64, device=dev)
+    steps = max(4, ctx["steps"] // 2)
+    it = [0]
+
+    def step():
+        sidx.search_device(qs[it[0] % nb], K, od, ol)
+        it[0] += 1
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    t = ctx["timer"].run(step, steps)
+    ms = t["ms"]
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    last_q = qs[(it[0] - 1) % nb]
+    got_d, got_l = od.cpu().numpy(), ol.cpu().numpy()
+    out = {"name": "C4", "workload": f"int8 dot-product k=10 over {ROWS * world} x 128 int8 "
+                                     f"({'one GPU shard of the 100M-row config' if world == 1 else f'row-sharded over {world} GPUs, peer-memory all-gather + merge'}), 1024 queries",
+           "value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "steps": steps, "dtype": "i8 (s32 accumulate)",
+           "n_gpus": world, "scaling": "weak (12.5 M rows per GPU)",
+           "roofline": _roof_tensor(2.0 * Q * ROWS * D, t["kernel_ms"], ctx["peaks"], "dense_scan_tc<i8,dot> (integer MMA, kind::i8)",
+                                    "fraction quoted against the measured bf16 peak; the int8 dense peak is 2x that. 128-byte "
+                                    "rows: one k-block per tile, bound by the TMEM drain of the epilogue (DESIGN.md)"),
+           "gpu_launches": t["launches"], "clocks": t["clocks"], "checks": {}, "uncertified": sidx.uncertified()}
+    if world > 1:
+        sidx.check_exchange()
+    if world == 1:
+        hq = last_q.cpu().numpy()
+        hd, hl = np.empty((Q, K), np.float32), np.empty((Q, K), np.int64)
+        e2e_ms = _host_timer(lambda: sidx.index.search_into(hq, K, hd, hl), max(3, steps // 2))
+        out["e2e"] = {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                      "h2d_bytes_per_step": Q * D, "d2h_bytes_per_step": Q * K * 12}
+        out["checks"]["host_api_equals_device_api"] = bool(np.array_equal(hl, got_l) and np.array_equal(hd, got_d))
+        # one query per call: HBM-bound pass over the shard
+        q1 = qs[0, :1].contiguous()
+        o1d = torch.empty((1, K), dtype=torch.float32, device=dev)
+        o1l = torch.empty((1, K), dtype=torch.int64, device=dev)
+        t1 = ctx["timer"].run(lambda: sidx.index.search_device(q1, K, o1d, o1l), ctx["steps"])
+        out["single_query"] = {"ms_per_call": t1["ms"],
+                               "roofline": _roof_hbm(float(ROWS) * D, t1["kernel_ms"], ctx["peaks"], "dense_scan_stream<int8,dot>")}
+        if ctx["cpu"]:
+            from oracle import oracle
+            cores = oracle.fast_use_all_cores()
+            nqs = max(8, cores)
+            dbh = _c4_shard(torch, dev, rank, ROWS).cpu().numpy()
+            t0 = time.perf_counter()
+            wd, wl = oracle.search(oracle.DOT, dbh, hq[:nqs], K, impl="fast")
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": nqs / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                                   "sample": f"{nqs} queries x the full {ROWS} x 128 int8 shard, {oracle.fast_isa()} + OpenMP, {dt:.2f} s"}
+            out["checks"]["equals_oracle"] = bool(np.array_equal(hl[:nqs], wl) and np.array_equal(hd[:nqs], wd))
+    elif rank == 0:
+        # the merged answer of the last timed batch against ONE index holding every rank's rows (12.8 GB at 8 GPUs)
+        full = gpu.DenseIndex(D, np.int8, _lib.METRIC_DOT, ctx["local"])
+        full.reserve(ROWS * world)
+        for r in range(world):
+            full.add_device(_c4_shard(torch, dev, r, ROWS))
+        rd, rl = full.search(last_q.cpu().numpy(), K)
+        out["checks"]["multi_gpu_equals_single"] = bool(np.array_equal(rl, got_l) and np.array_equal(rd, got_d))
+        full.close()
+    sidx.close()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- C5
+def config_c5(ctx):
+    torch, _lib, gpu, dev = ctx["torch"], ctx["_lib"], ctx["gpu"], ctx["dev"]
+    N, D, Q, C, K = ctx.get("c5_rows", 10_000_000), 384, 4096, 128, 10
+    idx = gpu.DenseIndex(D, np.float32, _lib.METRIC_L2, ctx["local"])
+    idx.reserve(N)
+    g = torch.Generator(device=dev).manual_seed(5001)
+    db = torch.empty((N, D), dtype=torch.float32, device=dev)  # kept for the CPU sample's row gather (15.4 GB)
+    step = 1_000_000
+    for lo in range(0, N, step):
+        db[lo:lo + step] = torch.randn((min(step, N - lo), D), generator=g, device=dev)
+    idx.add_device(db)
+    g = torch.Generator(device=dev).manual_seed(5002)
+    qs = torch.randn((Q, D), generator=g, device=dev)
+    # candidate lists shaped like an ef=128 frontier: the exact 64 nearest rows (what a converged
+    # walk holds) + 64 random ids (what it visited on the way), shuffled
+    top_d = torch.empty((Q, 64), dtype=torch.float32, device=dev)
+    top_l = torch.empty((Q, 64), dtype=torch.int64, device=dev)
+    idx.search_device(qs, 64, top_d, top_l)
+    g = torch.Generator(device=dev).manual_seed(5003)
+    rnd = torch.randint(0, N, (Q, C - 64), generator=g, device=dev, dtype=torch.int64)
+    cand = torch.cat([top_l, rnd], dim=1)
+    perm = torch.argsort(torch.rand((Q, C), generator=g, device=dev), dim=1)
+    cand = torch.gather(cand, 1, perm).to(torch.uint32).contiguous()
+    g = torch.Generator(device=dev).manual_seed(5004)
+    tomb = (torch.rand(N, generator=g, device=dev) < 0.05)
+    g = torch.Generator(device=dev).manual_seed(5005)
+    allow = (torch.rand(N, generator=g, device=dev) < 0.30)
+    tomb_h, allow_h = tomb.cpu().numpy(), allow.cpu().numpy()
+    idx.set_tombstones(tomb_h)
+    allow_packed = gpu.pack_bitmap(allow_h)
+    allow_d = torch.from_numpy(allow_packed.view(np.int64)).to(dev)
+    od = torch.empty((Q, K), dtype=torch.float32, device=dev)
+    ol = torch.empty((Q, K), dtype=torch.int64, device=dev)
+    t = ctx["timer"].run(lambda: idx.rerank_device(qs, cand, K, od, ol, allow=allow_d), ctx["steps"])
+    live = (~tomb & allow)[cand.long()].float().mean().item()
+    hq, hc = qs.cpu().numpy(), cand.cpu().numpy()
+    hd, hl = np.empty((Q, K), np.float32), np.empty((Q, K), np.int64)
+    lib = _lib.load()
+
+    def host_call():
+        _lib.check(lib.lb_index_rerank(idx._h, hq.ctypes.data, Q, hc.ctypes.data, C, K, allow_packed.ctypes.data,
+                                       hd.ctypes.data, hl.ctypes.data))
+    e2e_ms = _host_timer(host_call, max(3, ctx["steps"] // 3))
+    bytes_gathered = Q * C * live * D * 4 + Q * C * 4
+    out = {"name": "C5", "workload": f"HNSW-shaped re-rank: batch 4096 x ef=128 candidate ids (exact top-64 + 64 random), {N} x 384 fp32, "
+                                     "tombstones 5% + predicate allow-bitmap 30% applied in-kernel, k=10",
+           "value": Q / (t["ms"] * 1e-3), "unit": "queries/s", "ms_per_step": t["ms"], "steps": ctx["steps"], "dtype": "f32",
+           "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": Q * D * 4 + Q * C * 4 + allow_packed.nbytes, "d2h_bytes_per_step": Q * K * 12},
+           "roofline": _roof_hbm(bytes_gathered, t["ms"], ctx["peaks"],
+                                 "rescore_coop_kernel<float,L2> (gather of the live candidates' rows + ids)"),
+           "live_candidate_fraction": live, "gpu_launches": t["launches"], "clocks": t["clocks"],
+           "checks": {"host_api_equals_device_api": bool(np.array_equal(hl, ol.cpu().numpy()) and np.array_equal(hd, od.cpu().numpy()))}}
+    # without bitmaps: every candidate row is gathered (805 MB per batch)
+    idx.set_tombstones(None)
+    t2 = ctx["timer"].run(lambda: idx.rerank_device(qs, cand, K, od, ol), ctx["steps"])
+    out["all_candidates_live"] = {"ms_per_step": t2["ms"], "value": Q / (t2["ms"] * 1e-3),
+                                  "roofline": _roof_hbm(Q * C * D * 4.0 + Q * C * 4, t2["ms"], ctx["peaks"], "rescore_coop_kernel<float,L2>")}
+    if ctx["cpu"]:
+        from oracle import oracle
+        cores = oracle.fast_use_all_cores()
+        nqs = 256
+        # the CPU sample re-ranks against a compact copy of just the rows its candidates name (same arithmetic)
+        ids = cand[:nqs].long().reshape(-1)
+        uniq, inv = torch.unique(ids, return_inverse=True)
+        subh = db[uniq].cpu().numpy()
+        candh = inv.reshape(nqs, C).cpu().numpy().astype(np.int64)
+        tomb_s = gpu.pack_bitmap(tomb_h[uniq.cpu().numpy()])
+        allow_s = gpu.pack_bitmap(allow_h[uniq.cpu().numpy()])
+        t0 = time.perf_counter()
+        wd, wl = oracle.rerank(oracle.L2, subh, hq[:nqs], candh, K, tomb=tomb_s, allow=allow_s, impl="fast")
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": nqs / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                               "sample": f"{nqs} queries x 128 candidates re-ranked against a compact copy of the rows they name "
+                                         f"(bitmaps remapped), {oracle.fast_isa()} + OpenMP, {dt:.3f} s"}
+        uq = uniq.cpu().numpy()
+        wl_global = np.where(wl >= 0, uq[np.clip(wl, 0, None)], -1)
+        out["checks"]["equals_oracle_256q"] = bool(np.array_equal(hl[:nqs], wl_global) and np.array_equal(hd[:nqs], wd))
+    idx.close()
+    del db
+    return out
+
+
+def run_all(ctx):
+    """Every extra config the rank count allows: C4 always (row-sharded at N > 1); C1 / C3 / C5 at N = 1."""
+    out = []
+    names = ctx.get("only") or (["C1", "C3", "C4", "C5"] if ctx["world"] == 1 else ["C4"])
+    fns = {"C1": config_c1, "C3": config_c3, "C4": config_c4, "C5": config_c5}
+    for n in names:
+        t0 = time.time()
+        try:
+            r = fns[n](ctx)
+        except Exception as e:  # one config failing must not take the headline down with it -- but it is reported
+            import traceback
+            traceback.print_exc()
+            r = {"name": n, "error": f"{type(e).__name__}: {e}", "checks": {"ran": False}}
+        r["wall_s"] = round(time.time() - t0, 1)
+        ctx["torch"].cuda.empty_cache()
+        out.append(r)
+    return out

@@ -531,7 +531,7 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
             if (S < 2048) S = 2048;
             if (S > 8192) S = 8192;
             if (!g_opt_tc_boot.load(std::memory_order_relaxed) || S * 4 > idx->size) S = 0;
-            int grid = dense_stream_grid(idx->sm_count);
+            int grid = dense_stream_grid(idx->sm_count, cq);
             const int64_t max_grid = (idx->size - S + 255) / 256;
             if (grid > max_grid) grid = (int)max_grid;
             if (grid < 1) grid = 1;

@@ -27,10 +27,12 @@ template <typename T> struct StreamQ;   // how a query piece multiplies a row pi
 template <> struct StreamQ<__half> {
     using QT = float;                    // query element type in shared memory
     static constexpr int kV = 8;
-    __device__ static __forceinline__ float dot16(const uint4& row, const float* q) {
+    // q points at the piece's first float4; the second one lives `plane` floats further (two planes, so that the
+    // 32 lanes of a warp read 32 consecutive float4: no bank conflicts -- the interleaved layout was 2-way)
+    __device__ static __forceinline__ float dot16(const uint4& row, const float* q, int plane) {
         float x[8];
         unpack16<__half>(row, x);
-        const float4 a = *reinterpret_cast<const float4*>(q), b = *reinterpret_cast<const float4*>(q + 4);
+        const float4 a = *reinterpret_cast<const float4*>(q), b = *reinterpret_cast<const float4*>(q + plane);
         float s = x[0] * a.x;
         s = fmaf(x[1], a.y, s); s = fmaf(x[2], a.z, s); s = fmaf(x[3], a.w, s);
         s = fmaf(x[4], b.x, s); s = fmaf(x[5], b.y, s); s = fmaf(x[6], b.z, s); s = fmaf(x[7], b.w, s);
@@ -40,7 +42,7 @@ template <> struct StreamQ<__half> {
 template <> struct StreamQ<float> {
     using QT = float;
     static constexpr int kV = 4;
-    __device__ static __forceinline__ float dot16(const uint4& row, const float* q) {
+    __device__ static __forceinline__ float dot16(const uint4& row, const float* q, int) {
         const float4 a = *reinterpret_cast<const float4*>(q);
         float s = __uint_as_float(row.x) * a.x;
         s = fmaf(__uint_as_float(row.y), a.y, s);
@@ -52,7 +54,7 @@ template <> struct StreamQ<float> {
 template <> struct StreamQ<int8_t> {
     using QT = int8_t;
     static constexpr int kV = 16;
-    __device__ static __forceinline__ float dot16(const uint4& row, const int8_t* q) {
+    __device__ static __forceinline__ float dot16(const uint4& row, const int8_t* q, int) {
         const uint4 a = *reinterpret_cast<const uint4*>(q);
         int s = __dp4a((int)row.x, (int)a.x, 0);
         s = __dp4a((int)row.y, (int)a.y, s);
@@ -89,7 +91,7 @@ struct StreamArgs {
 // while the total stays below 2^24, which holds for dim <= 1024 (|dot| <= dim * 2^14).  Larger int8 rows
 // still rank correctly up to fp32 rounding and are re-scored exactly afterwards.
 template <typename T, int METRIC, int NQ, int LPR, int U>
-__global__ void __launch_bounds__(ST_THREADS, 3)
+__global__ void __launch_bounds__(ST_THREADS, (NQ == 1 ? 4 : 3))
 dense_scan_stream(const StreamArgs a) {
     using SQ = StreamQ<T>;
     using QT = typename SQ::QT;
@@ -119,7 +121,12 @@ dense_scan_stream(const StreamArgs a) {
             if constexpr (sizeof(T) == 1) v = reinterpret_cast<const int8_t*>(a.queries)[(size_t)q * a.dim + e];
             else v = Elem<T>::widen(reinterpret_cast<const T*>(a.queries)[(size_t)q * a.dim + e]);
         }
-        qs[i] = v;
+        int di = e;
+        if constexpr (sizeof(T) == 2) {  // fp16 rows: two planes of float4 per query (see StreamQ<__half>::dot16)
+            const int pc = e >> 3, w = e & 7;
+            di = (w < 4) ? (pc * 4 + w) : ((a.dim >> 1) + pc * 4 + (w - 4));
+        }
+        qs[(size_t)q * a.dim + di] = v;
     }
     if (tid < NQ) {
         s_cnt[tid] = 0;
@@ -160,9 +167,9 @@ dense_scan_stream(const StreamArgs a) {
             }
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
-                const QT* qp = qs + (size_t)q * a.dim + (size_t)p * V;
+                const QT* qp = qs + (size_t)q * a.dim + (size_t)p * (sizeof(T) == 2 ? 4 : V);
 #pragma unroll
-                for (int u = 0; u < U; u++) acc[u][q] += SQ::dot16(raw[u], qp);
+                for (int u = 0; u < U; u++) acc[u][q] += SQ::dot16(raw[u], qp, a.dim >> 1);
             }
         }
         // reduce the partial dots across the LPR lanes of each row
@@ -274,7 +281,10 @@ bool dense_stream_eligible(int dtype, int dim, const void* db, int nq, int kc) {
     return true;
 }
 
-int dense_stream_grid(int sm_count) { return 4 * sm_count; }
+// One wave exactly: the grid-stride loop gives every CTA the same share of rows, so the grid must equal the number
+// of CTAs that are resident at once (round 1 launched 4 per SM with 3 resident: a second, one-third-full wave
+// cost 15 % of the kernel, ncu "SM Active Cycles" 498k of 584k).  Single-query kernels fit 4 per SM (64 registers).
+int dense_stream_grid(int sm_count, int nq) { return (nq == 1 ? 4 : 3) * sm_count; }
 
 template <typename T, int METRIC, int NQ>
 static cudaError_t launch_stream_nq(const StreamArgs& a, int grid, cudaStream_t st) {

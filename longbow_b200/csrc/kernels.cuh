@@ -154,7 +154,7 @@ cudaError_t launch_split_lo(const float* x, float* lo, size_t n, cudaStream_t st
 
 // ---- streaming scan for small query batches (dense_stream.cu)
 bool dense_stream_eligible(int dtype, int dim, const void* db, int nq, int kc);
-int dense_stream_grid(int sm_count);
+int dense_stream_grid(int sm_count, int nq);
 cudaError_t launch_dense_scan_stream(const ScanArgs& s, int grid, uint32_t row_begin, uint32_t dump_rows,
                                      uint32_t* out_cnt, size_t out_stride, cudaStream_t st);
 
