@@ -405,7 +405,7 @@ def main():
         torch.cuda.empty_cache()
         ctx = {"torch": torch, "_lib": _lib, "gpu": _gpu2, "pq": _pq2, "dev": dev, "local": local, "rank": rank,
                "world": world, "steps": max(6, steps // 2), "peaks": peaks, "cpu": (not args.no_cpu) and world == 1,
-               "timer": bench_extra.Timer(torch, _lib, sampler),
+               "timer": bench_extra.Timer(torch, _lib, sampler, adaptive=(world == 1)),
                "only": None if args.configs == "all" else [c.strip().upper() for c in args.configs.split(",")]}
         extra = bench_extra.run_all(ctx)
         for r in extra:

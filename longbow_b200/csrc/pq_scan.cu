@@ -33,6 +33,8 @@
 //
 // Roofline: HBM for one query per pass (N * Mp bytes; C3: 960 MB), shared-memory bandwidth when four queries
 // share a pass (8 B per (row, sub-quantiser) look-up for 4 queries).
+#include <cstdio>
+
 #include "kernels.cuh"
 
 namespace lb {
@@ -396,13 +398,17 @@ adc_coarse_kernel(const PqCoarseArgs a) {
         // warps run free -- a barrier every trip locks their load and look-up phases together, and then HBM latency
         // and shared-memory look-ups add up instead of overlapping (measured: 203k + 278k cycles per SM).  A list
         // that fills up between two barriers sets the overflow flag (degenerate tables only).
+        // Every 8th trip is an overflow check only (compaction if a list is more than half full).
         const bool pow2 = ((it + 1) & it) == 0;
-        if (!pow2) return;  // block-uniform
+        const bool chk = ((it + 1) & 7) == 0;
+        if (!pow2 && !chk) return;  // block-uniform
         __syncthreads();
 #pragma unroll 1
         for (int q = 0; q < nvalid; q++) {
             const int c = min(s_cnt[q], a.cap);
-            if (c > a.cap / 2) {  // block-uniform
+            // scheduled refresh: keep the local kc-th best current (the sort is short, the list holds about kc entries
+            // plus what arrived since the last refresh); overflow check: only a list that is half full
+            if (pow2 ? (c > a.kc) : (c > a.cap / 2)) {  // block-uniform
                 uint64_t* buf = cand + (size_t)q * a.cap;
                 const int n2 = next_pow2(c);
                 for (int t = c + tid; t < n2; t += PQS_THREADS) buf[t] = kInvalid;
@@ -555,6 +561,14 @@ adc_exact_kernel(const uint8_t* __restrict__ tiled, int M, int Mp, const float* 
             const double dk = (double)key_of(kth);
             cert = pr.inv_scale > 0.0 && lb > 0.0 && sqrt(lb) * (1.0 - 2.0e-7) > dk;
         }
+#ifdef LB_PQ_DEBUG
+        if (!cert || (overflow != nullptr && overflow[q])) {
+            const PqQParams pr = params[q];
+            printf("q %d uncert: ovf %u last %llx kth %llx klast %u base %f inv %g smax %f dk %f n2 %d\n", q, overflow ? overflow[q] : 0u,
+                   (unsigned long long)last, (unsigned long long)kth, (uint32_t)(last >> 32), pr.base, pr.inv_scale, pr.smax_sum,
+                   (double)key_of(kth), n2);
+        }
+#endif
         if (overflow != nullptr && overflow[q]) cert = false;
         cert_flags[q] = cert ? 0u : 1u;
         if (!cert && cert_count != nullptr) atomicAdd(cert_count, 1u);
