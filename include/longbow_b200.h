@@ -256,6 +256,39 @@ int lb_pq_search_device_cert(lb_pq *pq, const float *d_queries, int64_t nq, int 
                              uint32_t *d_uncert_flags, uint32_t *d_uncert_count, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * 4b. HNSW layer search on the GPU: ArrowHNSW.searchLayer
+ *     (internal/store/arrow_hnsw.go:1108-1385) for a batch of queries, one warp per query, same algorithm
+ *     step for step (candidate min-heap, result max-heap of ef, strict acceptance test, stop test), so the
+ *     frontier equals the CPU walk's; heaps order on (distance, id).  The graph is built on the host; its layer
+ *     arrays are mirrored as they lie in GraphData (internal/store/types/graph_data.go:605-670): per node
+ *     `counts[id]` neighbours at neighbors[id * max_degree ...] (the 1024-node chunks concatenated).
+ *     Node ids are rows of the lb_index the graph was created on.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct lb_graph lb_graph;
+int lb_graph_create(lb_index *idx, int max_degree, lb_graph **out);
+void lb_graph_free(lb_graph *g);
+/* neighbors [n][max_degree] uint32 (ids >= n are ignored: 0xffffffff padding), counts [n] int32 or NULL. */
+int lb_graph_set_layer(lb_graph *g, const uint32_t *neighbors, const int32_t *counts, int64_t n);
+int lb_graph_set_layer_device(lb_graph *g, const uint32_t *d_neighbors, const int32_t *d_counts, int64_t n,
+                              void *stream);
+/* searchLayer from one entry point per query: ids / distances [nq*ef] ascending (0xffffffff / FLT_MAX padding),
+ * visited [nq] (optional) = distances computed per query. */
+int lb_graph_search_layer(lb_graph *g, const void *queries, int64_t nq, const uint32_t *entry_points, int ef,
+                          uint32_t *ids, float *distances, uint32_t *visited);
+/* Config 5 end to end: the walk, then the re-rank of its ef candidates with the index's tombstones and the
+ * `allow` predicate bitmap applied in-kernel (lb_index_rerank) -> [nq*k]. */
+int lb_graph_search(lb_graph *g, const void *queries, int64_t nq, const uint32_t *entry_points, int ef, int k,
+                    const uint64_t *allow, float *distances, int64_t *labels);
+/* Device-pointer forms.  *d_fail_count (caller-zeroed) is incremented for every query whose walk outgrew its
+ * visited-set or candidate limits (their outputs are padding); the host forms retry those with larger tables. */
+int lb_graph_search_layer_device(lb_graph *g, const void *d_queries, int64_t nq, const uint32_t *d_entry_points,
+                                 int ef, uint32_t *d_ids, float *d_distances, uint32_t *d_visited,
+                                 uint32_t *d_fail_count, void *stream);
+int lb_graph_search_device(lb_graph *g, const void *d_queries, int64_t nq, const uint32_t *d_entry_points, int ef,
+                           int k, const uint64_t *d_allow, float *d_distances, int64_t *d_labels,
+                           uint32_t *d_fail_count, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * 5. Predicate -> dense bitmap (internal/simd/simd.go:572-761 compare kernels,
  *    internal/query/filter_evaluator.go:700-758).  op: 0 ==, 1 !=, 2 >, 3 >=, 4 <, 5 <=.
  *    The result is AND-ed into `bitmap` when and_into != 0, else overwrites it.

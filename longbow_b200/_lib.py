@@ -79,6 +79,14 @@ SIGNATURES = {
     "lb_pq_search_device": (i32, [vp, vp, i64, i32, i32, vp, vp, vp, vp]),
     "lb_pq_last_uncertified": (i64, [vp]),
     "lb_pq_search_device_cert": (i32, [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "lb_graph_create": (i32, [vp, i32, C.POINTER(vp)]),
+    "lb_graph_free": (None, [vp]),
+    "lb_graph_set_layer": (i32, [vp, vp, vp, i64]),
+    "lb_graph_set_layer_device": (i32, [vp, vp, vp, i64, vp]),
+    "lb_graph_search_layer": (i32, [vp, vp, i64, vp, i32, vp, vp, vp]),
+    "lb_graph_search": (i32, [vp, vp, i64, vp, i32, i32, vp, vp, vp]),
+    "lb_graph_search_layer_device": (i32, [vp, vp, i64, vp, i32, vp, vp, vp, vp, vp]),
+    "lb_graph_search_device": (i32, [vp, vp, i64, vp, i32, i32, vp, vp, vp, vp, vp]),
     "lb_filter_i64": (i32, [i32, vp, i64, i32, i64, i32, vp]),
     "lb_filter_f32": (i32, [i32, vp, i64, i32, fp, i32, vp]),
     "lb_filter_i64_device": (i32, [i32, vp, i64, i32, i64, i32, vp, vp]),

@@ -205,6 +205,15 @@ static int grow(void** buf, int64_t* cap, int64_t need, size_t row_bytes, int64_
     return LB_OK;
 }
 
+namespace lb {
+int api_index_view(const lb_index* idx, IndexView* out) {
+    if (!idx || !out) return fail(LB_ERR_INVALID, "index is NULL");
+    out->rows = idx->rows; out->size = idx->size; out->dim = idx->dim; out->dtype = idx->dtype;
+    out->metric = idx->metric; out->device = idx->device;
+    return LB_OK;
+}
+}  // namespace lb
+
 static bool supported(int dtype, int metric) {
     if (metric < 0 || metric > 2) return false;
     if (dtype == DT_F32 || dtype == DT_F16) return true;
@@ -843,6 +852,15 @@ static int rerank_core(lb_index* idx, const void* d_q, int64_t nq, const uint32_
     CK(launch_rescore(r, st));
     return LB_OK;
 }
+
+}  // extern "C"
+namespace lb {
+int api_rerank_device(lb_index* idx, const void* d_q, int64_t nq, const uint32_t* d_ids, int c, int k,
+                      const uint64_t* d_allow, float* d_dist, int64_t* d_lab, cudaStream_t st) {
+    return rerank_core(idx, d_q, nq, d_ids, c, k, d_allow, d_dist, d_lab, st);
+}
+}  // namespace lb
+extern "C" {
 
 int lb_index_rerank_device(lb_index* idx, const void* d_queries, int64_t nq, const uint32_t* d_cand_ids, int c,
                            int k, const uint64_t* d_allow, float* d_distances, int64_t* d_labels, void* stream) {

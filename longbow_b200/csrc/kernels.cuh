@@ -200,6 +200,9 @@ cudaError_t launch_adc_exact(const uint8_t* tiled, int M, const float* luts, con
 cudaError_t launch_unpack_topk(const uint64_t* merged, int nq, int kc, int k, int64_t id_base, float* out_d,
                                int64_t* out_l, cudaStream_t st);
 
+// what the translation units outside api.cu may know about an lb_index handle
+struct IndexView { const void* rows; int64_t size; int dim, dtype, metric, device; };
+
 // ---- predicates (kernels_filter.cu)
 cudaError_t launch_filter_i64(const int64_t* col, int64_t n, int op, int64_t val, int and_into, uint32_t* bitmap,
                               cudaStream_t st);

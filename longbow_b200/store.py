@@ -168,3 +168,98 @@ def GenerateFilterBitset(column, op: int, value, bitmap=None, device: int = 0):
     else:
         raise TypeError("filter columns: int64 or float32")
     return bm
+
+
+class HNSWGraph:
+    """GPU mirror of the search half of ``ArrowHNSW`` (internal/store/arrow_hnsw.go): the adjacency arrays of one
+    layer as they lie in ``GraphData`` (internal/store/types/graph_data.go:605-670) over the rows of a resident
+    ``DenseIndex``.  ``SearchLayer`` is ``searchLayer`` (:1108-1385) for a batch of queries; ``Search`` adds the
+    re-rank with tombstones + predicate bitmap applied in-kernel (parallel_search.go:147-365) -- BASELINE config 5.
+    Graph construction and the upper-layer descent to the entry points stay on the host."""
+
+    def __init__(self, index: DenseIndex, max_degree: int):
+        import ctypes as C
+        self._lib = _lib.load()
+        self.index = index
+        self.max_degree = int(max_degree)
+        h = C.c_void_p()
+        check(self._lib.lb_graph_create(index._h, self.max_degree, C.byref(h)))
+        self._h = h
+
+    def SetNeighbors(self, neighbors, counts=None):
+        nb = np.ascontiguousarray(neighbors, np.uint32).reshape(-1, self.max_degree)
+        ct = None if counts is None else np.ascontiguousarray(counts, np.int32)
+        check(self._lib.lb_graph_set_layer(self._h, _ptr(nb), _ptr(ct), nb.shape[0]))
+
+    def SearchLayer(self, queries, entry_points, ef: int):
+        """-> (ids [nq, ef] uint32 ascending by (distance, id), 0xffffffff padded; distances; visited counts)."""
+        q = np.ascontiguousarray(queries, self.index.np_dtype).reshape(-1, self.index.dim)
+        ep = np.ascontiguousarray(entry_points, np.uint32).reshape(-1)
+        nq = q.shape[0]
+        ids = np.empty((nq, ef), np.uint32)
+        d = np.empty((nq, ef), np.float32)
+        vis = np.empty(nq, np.uint32)
+        check(self._lib.lb_graph_search_layer(self._h, _ptr(q), nq, _ptr(ep), int(ef), _ptr(ids), _ptr(d), _ptr(vis)))
+        return ids, d, vis
+
+    def Search(self, queries, entry_points, ef: int, k: int, allow=None):
+        from .gpu import _bitmap
+        q = np.ascontiguousarray(queries, self.index.np_dtype).reshape(-1, self.index.dim)
+        ep = np.ascontiguousarray(entry_points, np.uint32).reshape(-1)
+        nq = q.shape[0]
+        d = np.empty((nq, k), np.float32)
+        l = np.empty((nq, k), np.int64)
+        bm = _bitmap(allow, len(self.index))
+        check(self._lib.lb_graph_search(self._h, _ptr(q), nq, _ptr(ep), int(ef), int(k), _ptr(bm), _ptr(d), _ptr(l)))
+        return d, l
+
+    def search_device(self, q, entry_points, ef: int, k: int, out_d, out_l, fail_count, allow=None, stream=None):
+        from .gpu import _stream_ptr
+        check(self._lib.lb_graph_search_device(self._h, q.data_ptr(), q.shape[0], entry_points.data_ptr(), int(ef), int(k),
+                                               None if allow is None else allow.data_ptr(), out_d.data_ptr(),
+                                               out_l.data_ptr(), fail_count.data_ptr(), _stream_ptr(stream)))
+
+    def Close(self):
+        if getattr(self, "_h", None):
+            self._lib.lb_graph_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Close()
+        except Exception:
+            pass
+
+
+# ---- Arrow compute operator registry (internal/store/arrow_kernels.go:20-111): the two functions the reference
+# registers with compute.GetFunctionRegistry(), backed by the GPU library.
+_ARROW_FUNCTIONS = {}
+_kernelsRegistered = False
+
+
+def RegisterHNSWKernels():
+    """Idempotent, like the reference's init() hook (arrow_kernels.go:20-31)."""
+    global _kernelsRegistered
+    if _kernelsRegistered:
+        return
+    _ARROW_FUNCTIONS["l2_distance"] = lambda left, right, device=0: L2DistanceOp(left, right, device)
+    _ARROW_FUNCTIONS["select_k_neighbors"] = lambda distances, ids, k, device=0: _select_k_op(distances, ids, k, device)
+    _kernelsRegistered = True
+
+
+def _select_k_op(distances, ids, k, device=0):
+    """selectKExec (arrow_kernels.go:230-345): INDICES (uint32) of the k smallest distances; `ids` only has to
+    match in length (the caller applies Take)."""
+    d = np.ascontiguousarray(distances, np.float32)
+    if ids is not None and len(ids) != d.size:
+        raise ValueError("distances and ids must have the same length")
+    idx, _ = SelectTopKNeighbors(d, min(int(k), d.size), device)
+    return idx.astype(np.uint32)
+
+
+def CallFunction(name: str, *args, **kwargs):
+    """compute.CallFunction(ctx, name, ...) for the registered vector-search functions."""
+    RegisterHNSWKernels()
+    if name not in _ARROW_FUNCTIONS:
+        raise KeyError(f"function not found: {name}")
+    return _ARROW_FUNCTIONS[name](*args, **kwargs)

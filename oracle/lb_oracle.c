@@ -635,3 +635,116 @@ LBO_API int lbo_pq_train(const float *data, int64_t n, int dims, int M, int K, i
     free(assign); free(counts); free(sums);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * HNSW layer search: ArrowHNSW.searchLayer (internal/store/arrow_hnsw.go:1108-1385) over the adjacency
+ * layout of GraphData (internal/store/types/graph_data.go:605-670: per node `counts[id]` neighbours at
+ * neighbors[id * max_degree ...]).
+ *   candidates: min-heap of nodes to expand; result set: max-heap of the best <= ef nodes found so far.
+ *   pop the closest candidate; stop when it is strictly worse than the worst result and the result set is full
+ *   (arrow_hnsw.go:1322-1329); for every not-yet-visited neighbour (in list order) compute the distance and, if the
+ *   result set is not full or the distance is strictly below its worst, push it on both heaps and evict the
+ *   worst result when the set exceeds ef (:1349-1370).  Output ascending by distance (:1377-1383).
+ * The reference's container/heap orders on Dist only, so the pop order among EQUAL distances is an artefact of
+ * Go's heap algorithm (unpinned); here both heaps order on (distance, id).
+ * -------------------------------------------------------------------------------------------- */
+typedef struct { float d; uint32_t id; } hn_cand;
+static inline int hn_less(hn_cand a, hn_cand b) { return a.d < b.d || (a.d == b.d && a.id < b.id); }
+
+static void hn_push(hn_cand *h, int *n, hn_cand c, int maxheap) {
+    int i = (*n)++;
+    h[i] = c;
+    while (i > 0) {
+        int p = (i - 1) / 2;
+        int up = maxheap ? hn_less(h[p], h[i]) : hn_less(h[i], h[p]);
+        if (!up) break;
+        hn_cand t = h[p]; h[p] = h[i]; h[i] = t;
+        i = p;
+    }
+}
+static hn_cand hn_pop(hn_cand *h, int *n, int maxheap) {
+    hn_cand top = h[0];
+    h[0] = h[--(*n)];
+    int i = 0;
+    for (;;) {
+        int l = 2 * i + 1, r = l + 1, b = i;
+        if (l < *n && (maxheap ? hn_less(h[b], h[l]) : hn_less(h[l], h[b]))) b = l;
+        if (r < *n && (maxheap ? hn_less(h[b], h[r]) : hn_less(h[r], h[b]))) b = r;
+        if (b == i) break;
+        hn_cand t = h[b]; h[b] = h[i]; h[i] = t;
+        i = b;
+    }
+    return top;
+}
+
+/* One query.  out_ids / out_d: [ef] ascending, padded with 0xffffffff / FLT_MAX.  Returns the number of results;
+ * *n_visited (optional) = nodes whose distance was computed (the entry point included). */
+LBO_API int lbo_hnsw_search_layer(int metric, int dtype, const void *db, int64_t n, int dim,
+                                  const uint32_t *neighbors, const int32_t *counts, int max_degree,
+                                  const void *query, uint32_t entry, int ef, uint32_t *out_ids, float *out_d,
+                                  int64_t *n_visited) {
+    if (ef <= 0 || n <= 0 || entry >= (uint64_t)n) return -1;
+    const size_t es = elem_size(dtype);
+    uint8_t *visited = (uint8_t *)calloc((size_t)(n + 7) / 8, 1);
+    /* every push onto the candidate heap is also a result-set push, but evictions do not remove candidates:
+     * the candidate heap can hold every node that was ever accepted */
+    int cap = 1024, nc = 0, nr = 0;
+    hn_cand *cand = (hn_cand *)malloc(sizeof(hn_cand) * cap);
+    hn_cand *res = (hn_cand *)malloc(sizeof(hn_cand) * (ef + 2));
+    int64_t nv = 0;
+/* pair_distance: the dot metric is already negated (a distance, distance_resolvers.go:11-16) */
+#define HN_DIST(id) pair_distance(metric, dtype, query, (const char *)db + (size_t)(id) * dim * es, dim)
+    hn_cand ep = {HN_DIST(entry), entry};
+    nv++;
+    hn_push(cand, &nc, ep, 0);
+    hn_push(res, &nr, ep, 1);
+    visited[entry >> 3] |= (uint8_t)(1u << (entry & 7));
+    while (nc > 0) {
+        hn_cand cur = hn_pop(cand, &nc, 0);
+        if (nr > 0 && cur.d > res[0].d && nr >= ef) break;
+        const int cnt = counts ? counts[cur.id] : max_degree;
+        for (int i = 0; i < cnt && i < max_degree; i++) {
+            const uint32_t nb = neighbors[(size_t)cur.id * max_degree + i];
+            if (nb >= (uint64_t)n) continue; /* padding / dangling id */
+            if (visited[nb >> 3] & (1u << (nb & 7))) continue;
+            visited[nb >> 3] |= (uint8_t)(1u << (nb & 7));
+            hn_cand c = {HN_DIST(nb), nb};
+            nv++;
+            if (nr < ef || c.d < res[0].d) {
+                if (nc + 1 >= cap) { cap *= 2; cand = (hn_cand *)realloc(cand, sizeof(hn_cand) * cap); }
+                hn_push(cand, &nc, c, 0);
+                hn_push(res, &nr, c, 1);
+                if (nr > ef) hn_pop(res, &nr, 1);
+            }
+        }
+    }
+#undef HN_DIST
+    const int count = nr;
+    for (int i = count - 1; i >= 0; i--) {
+        hn_cand c = hn_pop(res, &nr, 1);
+        out_ids[i] = c.id;
+        out_d[i] = c.d;
+    }
+    for (int i = count; i < ef; i++) { out_ids[i] = 0xffffffffu; out_d[i] = 3.402823466e+38f; }
+    if (n_visited) *n_visited = nv;
+    free(visited); free(cand); free(res);
+    return count;
+}
+
+/* Batch of queries (OpenMP over queries), entry point per query. */
+LBO_API int lbo_hnsw_search_layer_batch(int metric, int dtype, const void *db, int64_t n, int dim,
+                                        const uint32_t *neighbors, const int32_t *counts, int max_degree,
+                                        const void *queries, int64_t nq, const uint32_t *entries, int ef,
+                                        uint32_t *out_ids, float *out_d, int64_t *n_visited) {
+    const size_t qs = (size_t)dim * elem_size(dtype);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t q = 0; q < nq; q++) {
+        int rc = lbo_hnsw_search_layer(metric, dtype, db, n, dim, neighbors, counts, max_degree,
+                                       (const char *)queries + (size_t)q * qs, entries[q], ef,
+                                       out_ids + (size_t)q * ef, out_d + (size_t)q * ef,
+                                       n_visited ? n_visited + q : NULL);
+        if (rc < 0) bad = 1;
+    }
+    return bad ? -1 : 0;
+}

@@ -226,6 +226,27 @@ def pq_search(codebooks: np.ndarray, codes: np.ndarray, raw_vecs, queries: np.nd
     return od, oi
 
 
+def hnsw_search_layer(metric: int, db: np.ndarray, neighbors: np.ndarray, counts, queries: np.ndarray,
+                      entries: np.ndarray, ef: int):
+    """ArrowHNSW.searchLayer (internal/store/arrow_hnsw.go:1108-1385) for a batch: returns (ids [nq, ef] uint32
+    ascending by (distance, id), 0xffffffff padded; distances [nq, ef]; visited counts [nq])."""
+    db, queries = _c(db), _c(queries)
+    neighbors = _c(neighbors, np.uint32)
+    n, dim = db.shape
+    max_degree = neighbors.shape[1]
+    counts = None if counts is None else _c(counts, np.int32)
+    entries = _c(entries, np.uint32)
+    nq = queries.shape[0]
+    ids = np.empty((nq, ef), np.uint32)
+    d = np.empty((nq, ef), np.float32)
+    nv = np.zeros(nq, np.int64)
+    rc = exact().lbo_hnsw_search_layer_batch(metric, dtype_code(db), _p(db), C.c_int64(n), dim, _p(neighbors),
+                                            _p(counts), max_degree, _p(queries), C.c_int64(nq), _p(entries), ef,
+                                            _p(ids), _p(d), _p(nv))
+    assert rc == 0
+    return ids, d, nv
+
+
 def fast_threads() -> int:
     return int(fast().lbf_threads())
 
