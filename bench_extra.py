@@ -372,11 +372,93 @@ def config_c5(ctx):
     return out
 
 
+# ----------------------------------------------------------------------------------------------- C5w
+def config_c5_walk(ctx):
+    """Config 5 with the REAL walk: a navigable graph (24 exact nearest neighbours + 8 random long-range edges per
+    node, built on this GPU with the library's own brute-force search) over 1 M x 384 fp32 rows; batch 4096, ef=128;
+    the GPU runs ArrowHNSW.searchLayer for every query (csrc/hnsw.cu) and re-ranks the frontier with tombstones +
+    predicate bitmap in-kernel.  The 10 M-row graph of the config cannot be BUILT inside a benchmark run; the walk's
+    cost per query depends on ef and the degree, not on N, so the 1 M graph is the bounded stand-in (stated)."""
+    torch, _lib, gpu, dev = ctx["torch"], ctx["_lib"], ctx["gpu"], ctx["dev"]
+    from longbow_b200 import store
+    N, D, Q, EF, K, DEG, KNN = ctx.get("c5w_rows", 1_000_000), 384, 4096, 128, 10, 32, 24
+    g = torch.Generator(device=dev).manual_seed(5101)
+    db = torch.randn((N, D), generator=g, device=dev)
+    idx = gpu.DenseIndex(D, np.float32, _lib.METRIC_L2, ctx["local"])
+    idx.reserve(N)
+    idx.add_device(db)
+    nbrs = torch.empty((N, DEG), dtype=torch.int64, device=dev)
+    od = torch.empty((4096, KNN + 1), dtype=torch.float32, device=dev)
+    ol = torch.empty((4096, KNN + 1), dtype=torch.int64, device=dev)
+    t0 = time.time()
+    for lo in range(0, N, 4096):
+        hi = min(N, lo + 4096)
+        idx.search_device(db[lo:hi], KNN + 1, od[:hi - lo], ol[:hi - lo])
+        nbrs[lo:hi, :KNN] = ol[:hi - lo, 1:]  # rank 0 is the row itself
+    nbrs[:, KNN:] = torch.randint(0, N, (N, DEG - KNN), generator=g, device=dev)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    graph = store.HNSWGraph(idx, DEG)
+    nb32 = nbrs.to(torch.uint32).contiguous()
+    _lib.check(_lib.load().lb_graph_set_layer_device(graph._h, nb32.data_ptr(), None, N,
+                                                     torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    g = torch.Generator(device=dev).manual_seed(5102)
+    qs = torch.randn((Q, D), generator=g, device=dev)
+    entries = torch.zeros(Q, dtype=torch.int32, device=dev)
+    g = torch.Generator(device=dev).manual_seed(5104)
+    tomb = (torch.rand(N, generator=g, device=dev) < 0.05).cpu().numpy()
+    g = torch.Generator(device=dev).manual_seed(5105)
+    allow = (torch.rand(N, generator=g, device=dev) < 0.30).cpu().numpy()
+    idx.set_tombstones(tomb)
+    allow_packed = gpu.pack_bitmap(allow)
+    allow_d = torch.from_numpy(allow_packed.view(np.int64)).to(dev)
+    out_d = torch.empty((Q, K), dtype=torch.float32, device=dev)
+    out_l = torch.empty((Q, K), dtype=torch.int64, device=dev)
+    fail = torch.zeros(1, dtype=torch.int32, device=dev)
+    t = ctx["timer"].run(lambda: graph.search_device(qs, entries, EF, K, out_d, out_l, fail, allow=allow_d), max(3, ctx["steps"] // 2), warm=2)
+    hq, he = qs.cpu().numpy(), np.zeros(Q, np.uint32)
+    e2e_ms = _host_timer(lambda: graph.Search(hq, he, EF, K, allow=allow_packed), 3, warm=1)
+    gi, gd, gv = graph.SearchLayer(hq[:512], he[:512], EF)
+    visited = float(gv.mean())
+    out = {"name": "C5w", "workload": f"HNSW search ef=128, batch 4096: GPU graph walk (searchLayer, degree 32) + GPU re-rank with "
+                                      f"tombstones 5% + allow-bitmap 30%, k=10, {N} x 384 fp32 (graph of the 10 M config scaled to "
+                                      f"what can be built inside the run: {build_s:.1f} s on this GPU)",
+           "value": Q / (t["ms"] * 1e-3), "unit": "queries/s", "ms_per_step": t["ms"], "steps": t["steps"], "dtype": "f32",
+           "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": Q * D * 4 + Q * 4 + allow_packed.nbytes, "d2h_bytes_per_step": Q * K * 12},
+           "roofline": _roof_hbm(Q * visited * D * 4.0, t["ms"], ctx["peaks"],
+                                 "hnsw_search_layer_kernel<float,L2> (row gathers of the visited nodes: "
+                                 f"{visited:.0f} distance evaluations per query) + rescore_coop_kernel"),
+           "distance_evaluations_per_query": visited, "walk_failures": int(fail.item()),
+           "gpu_launches": t["launches"], "clocks": t["clocks"], "checks": {"no_walk_failures": int(fail.item()) == 0}}
+    if ctx["cpu"]:
+        from oracle import oracle
+        cores = oracle.fast_use_all_cores()
+        nqs = 256
+        dbh, nbh = db.cpu().numpy(), nb32.cpu().numpy()
+        t0 = time.perf_counter()
+        wi, wd, wv = oracle.hnsw_search_layer(oracle.L2, dbh, nbh, None, hq[:nqs], he[:nqs], EF)
+        cand = wi.astype(np.int64)
+        cand[wi == 0xFFFFFFFF] = -1
+        ed, el = oracle.rerank(oracle.L2, dbh, hq[:nqs], cand, K, tomb=gpu.pack_bitmap(tomb), allow=allow_packed)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": nqs / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                               "sample": f"{nqs} queries: searchLayer restatement (heaps, per-neighbour distance) + re-rank on the same graph, "
+                                         f"OpenMP over queries, {dt:.3f} s"}
+        gdk, glk = graph.Search(hq[:nqs], he[:nqs], EF, K, allow=allow_packed)
+        out["checks"]["frontier_equals_cpu_walk_256q"] = bool(np.array_equal(gi[:nqs], wi) and np.array_equal(gd[:nqs], wd))
+        out["checks"]["topk_equals_exact_oracle_256q"] = bool(np.array_equal(glk, el) and np.array_equal(gdk, ed))
+    graph.Close()
+    idx.close()
+    return out
+
+
 def run_all(ctx):
     """Every extra config the rank count allows: C4 always (row-sharded at N > 1); C1 / C3 / C5 at N = 1."""
     out = []
-    names = ctx.get("only") or (["C1", "C3", "C4", "C5"] if ctx["world"] == 1 else ["C4"])
-    fns = {"C1": config_c1, "C3": config_c3, "C4": config_c4, "C5": config_c5}
+    names = ctx.get("only") or (["C1", "C3", "C4", "C5", "C5W"] if ctx["world"] == 1 else ["C4"])
+    fns = {"C1": config_c1, "C3": config_c3, "C4": config_c4, "C5": config_c5, "C5W": config_c5_walk}
     for n in names:
         t0 = time.time()
         try:

@@ -182,37 +182,47 @@ hnsw_search_layer_kernel(const HnswArgs a) {
                 m &= m - 1;
                 const float dl = __shfl_sync(0xffffffffu, d, l);
                 const uint32_t nl = __shfl_sync(0xffffffffu, nb, l);
-                if (lane == 0) {
-                    if (nr < a.ef || dl < key_of(res[0])) {
-                        const uint64_t p = pack_key(dl, nl);
-                        if (nc >= a.cand_cap) {
-                            // full: the largest candidate can go if it is strictly worse than the worst result of a
-                            // full result set (it could only ever trigger the stop test)
-                            int big = 0;
-                            for (int t = 1; t < nc; t++) if (cand[t] > cand[big]) big = t;
-                            if (nr >= a.ef && key_of(cand[big]) > key_of(res[0])) {
-                                // remove element `big` from the min-heap: replace by the last, sift up (a leaf can
-                                // only need to move up)
-                                const uint64_t v = cand[--nc];
-                                int t = big;
-                                if (t < nc) {
-                                    while (t > 0) {
-                                        const int pp = (t - 1) >> 1;
-                                        if (cand[pp] <= v) break;
-                                        cand[t] = cand[pp];
-                                        t = pp;
-                                    }
-                                    cand[t] = v;
-                                }
-                            } else {
-                                failed = true;
-                            }
+                int accept = 0;
+                if (lane == 0) accept = (nr < a.ef || dl < key_of(res[0])) ? 1 : 0;
+                accept = __shfl_sync(0xffffffffu, accept, 0);
+                if (!accept) continue;
+                int ncu = __shfl_sync(0xffffffffu, nc, 0);
+                if (ncu >= a.cand_cap) {
+                    // Candidate heap full (only possible once the result set is full).  Candidates strictly worse
+                    // than the worst result can never be expanded -- the worst only improves, and popping one of
+                    // them is exactly the stop test -- so the whole warp prunes them: compact the survivors to the
+                    // front and sort them ascending (a sorted array is a min-heap).
+                    const int nru = __shfl_sync(0xffffffffu, nr, 0);
+                    const uint64_t worst = res[0];
+                    int kept = 0;
+                    if (nru >= a.ef) {
+                        for (int c0 = 0; c0 < ncu; c0 += 32) {
+                            const int t = c0 + lane;
+                            const uint64_t v = (t < ncu) ? cand[t] : kInvalid;
+                            const bool keep = (t < ncu) && !(key_of(v) > key_of(worst));
+                            const unsigned km = __ballot_sync(0xffffffffu, keep);
+                            __syncwarp();
+                            if (keep) cand[kept + __popc(km & ((1u << lane) - 1u))] = v;
+                            kept += __popc(km);
+                            __syncwarp();
                         }
-                        if (nc < a.cand_cap) heap_push(cand, nc, p, false);
-                        heap_push(res, nr, p, true);
-                        if (nr > a.ef) heap_pop(res, nr, true);
+                        const int s2 = next_pow2(max(kept, 2));
+                        for (int t = kept + lane; t < s2; t += 32) cand[t] = kInvalid;
+                        __syncwarp();
+                        warp_bitonic_sort(cand, s2, lane);
+                    } else {
+                        kept = ncu;
                     }
+                    if (kept >= a.cand_cap) failed = true;  // more exact ties with the worst than the heap can hold
+                    nc = kept;
                 }
+                if (lane == 0 && !failed) {
+                    const uint64_t p = pack_key(dl, nl);
+                    heap_push(cand, nc, p, false);
+                    heap_push(res, nr, p, true);
+                    if (nr > a.ef) heap_pop(res, nr, true);
+                }
+                __syncwarp();
             }
             __syncwarp();
         }
@@ -352,7 +362,7 @@ static int graph_walk(lb_graph* g, const void* d_q, int64_t nq, const uint32_t* 
     a.neighbors = g->neighbors; a.counts = g->counts; a.max_degree = g->max_degree;
     a.queries = d_q; a.entries = d_entries; a.ef = ef;
     const int n2 = next_pow2(ef + 1 > 2 ? ef + 1 : 2);
-    a.cand_cap = 2 * ef + 64;
+    a.cand_cap = next_pow2(2 * ef + 64);  // power of two: the prune step sorts it in place
     if (a.cand_cap < n2) a.cand_cap = n2;
     uint32_t ht = 4096;
     while (ht < (uint32_t)ef * 96u) ht <<= 1;
