@@ -210,6 +210,28 @@ int lb_exchange_all_gather_merge(lb_exchange *ex, int64_t nq, int k_in, int k, f
 int lb_exchange_error(lb_exchange *ex);
 
 /* ------------------------------------------------------------------------------------------
+ * 3c. Row-sharded multi-GPU index driven from ONE process (SURVEY.md 8b "multi-GPU handle (devices[],
+ *     row-sharded)", 8e; replaces ShardedHNSW's fan-out + merge, internal/store/sharded_hnsw.go:378-503).
+ *     Global rows are split into contiguous ranges of lb_shard_rows_per_shard() rows (a multiple of 64, so
+ *     global bitmaps are sliced by whole words); labels are global row positions.  Every device runs the
+ *     ordinary search chain and its re-score kernel stores the shard's record directly into the root GPU's
+ *     gather buffer over NVLink peer memory; the root merges by (distance, label).  Same certification
+ *     contract as lb_index_search (uncertified queries are re-done exhaustively on every shard).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct lb_shard lb_shard;
+int lb_shard_create(const int *devices, int n_devices, int dim, int dtype, int metric, int64_t total_rows,
+                    lb_shard **out);
+void lb_shard_free(lb_shard *s);
+int lb_shard_add(lb_shard *s, const void *rows, int64_t n); /* appended in global row order */
+int64_t lb_shard_size(const lb_shard *s);
+int lb_shard_count(const lb_shard *s);
+int64_t lb_shard_rows_per_shard(const lb_shard *s);
+int lb_shard_set_tombstones(lb_shard *s, const uint64_t *bitmap, int64_t nbits); /* global bitmap */
+int lb_shard_search(lb_shard *s, const void *queries, int64_t nq, int k, const uint64_t *allow, float *distances,
+                    int64_t *labels);
+int64_t lb_shard_last_uncertified(const lb_shard *s);
+
+/* ------------------------------------------------------------------------------------------
  * 4. Product quantisation (internal/pq): ADC LUT build, ADC code scan + top-k', fp32 re-rank.
  * ---------------------------------------------------------------------------------------- */
 typedef struct lb_pq lb_pq;

@@ -64,6 +64,15 @@ SIGNATURES = {
     "lb_exchange_slot": (i32, [vp, i64, i32, C.POINTER(vp), C.POINTER(vp)]),
     "lb_exchange_all_gather_merge": (i32, [vp, i64, i32, i32, vp, vp, vp]),
     "lb_exchange_error": (i32, [vp]),
+    "lb_shard_create": (i32, [C.POINTER(i32), i32, i32, i32, i32, i64, C.POINTER(vp)]),
+    "lb_shard_free": (None, [vp]),
+    "lb_shard_add": (i32, [vp, vp, i64]),
+    "lb_shard_size": (i64, [vp]),
+    "lb_shard_count": (i32, [vp]),
+    "lb_shard_rows_per_shard": (i64, [vp]),
+    "lb_shard_set_tombstones": (i32, [vp, vp, i64]),
+    "lb_shard_search": (i32, [vp, vp, i64, i32, vp, vp, vp]),
+    "lb_shard_last_uncertified": (i64, [vp]),
     "lb_pq_create": (i32, [i32, vp, sz, C.POINTER(vp)]),
     "lb_pq_free": (None, [vp]),
     "lb_pq_params": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),

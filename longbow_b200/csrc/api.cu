@@ -716,6 +716,20 @@ static int exact_search_one(lb_index* idx, const void* d_q1, int k, const uint64
     return LB_OK;
 }
 
+}  // extern "C"
+namespace lb {
+int api_search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const uint64_t* d_allow, float* d_dist,
+                    int64_t* d_lab, cudaStream_t st, uint32_t* d_flags, uint32_t* d_count) {
+    if (coarse_k(k) > 896 || idx->size == 0) d_flags = d_count = nullptr;  // exhaustive / empty: nothing to certify
+    return search_core(idx, d_q, nq, k, d_allow, d_dist, d_lab, st, d_flags, d_count);
+}
+int api_exact_search_one(lb_index* idx, const void* d_q1, int k, const uint64_t* d_allow, float* d_out_d,
+                         int64_t* d_out_l, cudaStream_t st) {
+    return exact_search_one(idx, d_q1, k, d_allow, d_out_d, d_out_l, st);
+}
+}  // namespace lb
+extern "C" {
+
 int lb_index_search_device(lb_index* idx, const void* d_queries, int64_t nq, int k, const uint64_t* d_allow,
                            float* d_distances, int64_t* d_labels, void* stream) {
     if (!idx) return fail(LB_ERR_INVALID, "index is NULL");

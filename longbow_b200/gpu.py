@@ -287,3 +287,68 @@ def _stream_ptr(stream):
     if isinstance(stream, int):
         return stream
     return stream.cuda_stream
+
+
+class ShardedDenseIndex:
+    """Row-sharded index over several GPUs driven from one process (``lb_shard_*``): what a Go host binds in
+    place of ShardedHNSW's fan-out + merge (internal/store/sharded_hnsw.go:378-503).  Labels are global rows."""
+
+    def __init__(self, devices, dim: int, dtype, metric: int, total_rows: int):
+        self._lib = _lib.load()
+        self.dim, self.np_dtype = int(dim), np.dtype(dtype)
+        if self.np_dtype not in _DT_OF:
+            raise LongbowError(_lib.LB_ERR_UNSUPPORTED, f"no kernel for dtype {self.np_dtype}")
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        check(self._lib.lb_shard_create(devs, len(devices), self.dim, _DT_OF[self.np_dtype], int(metric),
+                                        int(total_rows), C.byref(h)))
+        self._h = h
+
+    def __len__(self):
+        return int(self._lib.lb_shard_size(self._h))
+
+    def rows_per_shard(self) -> int:
+        return int(self._lib.lb_shard_rows_per_shard(self._h))
+
+    def add(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=self.np_dtype)
+        if rows.size % self.dim != 0:
+            raise ValueError(f"vector data length {rows.size} not divisible by dimension {self.dim}")
+        check(self._lib.lb_shard_add(self._h, _ptr(rows), rows.size // self.dim))
+
+    def set_tombstones(self, deleted):
+        if deleted is None:
+            check(self._lib.lb_shard_set_tombstones(self._h, None, 0))
+            return
+        bm = _bitmap(deleted, len(self))
+        check(self._lib.lb_shard_set_tombstones(self._h, _ptr(bm), bm.size * 64))
+
+    def search(self, queries, k: int, allow=None):
+        q = np.ascontiguousarray(queries, dtype=self.np_dtype).reshape(-1, self.dim)
+        nq = q.shape[0]
+        d = np.empty((nq, k), np.float32)
+        l = np.empty((nq, k), np.int64)
+        bm = None
+        if allow is not None:
+            # padded to whole shards so that every shard's word slice exists
+            total = self.rows_per_shard() * int(self._lib.lb_shard_count(self._h))
+            bm = _bitmap(allow, len(self))
+            need = (total + 63) // 64
+            if bm.size < need:
+                bm = np.concatenate([bm, np.zeros(need - bm.size, np.uint64)])
+        check(self._lib.lb_shard_search(self._h, _ptr(q), nq, int(k), _ptr(bm), _ptr(d), _ptr(l)))
+        return d, l
+
+    def last_uncertified(self) -> int:
+        return int(self._lib.lb_shard_last_uncertified(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lb_shard_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
