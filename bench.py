@@ -182,6 +182,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    for name_, val_ in os.environ.items():  # debug: LB_OPT_<option>=<int> -> lb_set_option (A/B experiments)
+        if name_.startswith("LB_OPT_"):
+            _lib.set_option(name_[7:], int(val_))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)

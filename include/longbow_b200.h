@@ -80,12 +80,20 @@ typedef struct lb_index lb_index;
 
 int lb_index_create(int device, int dim, int dtype, int metric, lb_index **out);
 void lb_index_free(lb_index *idx);
-/* Pre-size the HBM mirror (rows).  Optional; add grows geometrically otherwise. */
+/* Pre-size the HBM mirror (rows).  Optional.  The mirror lives in one virtual-address reservation per index and
+ * grows by mapping more physical memory behind it: growth never copies rows and never synchronises the device. */
 int lb_index_reserve(lb_index *idx, int64_t n_rows);
 /* Append n rows from a host buffer laid out as the Arrow child values buffer: row-major,
  * contiguous, n*dim elements (internal/store/arrow_utils.go:112-171).  gpu.Index.Add. */
 int lb_index_add(lb_index *idx, const void *rows, int64_t n);
 int lb_index_add_device(lb_index *idx, const void *d_rows, int64_t n, void *stream);
+/* Append the rows of one RecordBatch's vector column straight from its Arrow buffer: `values` is the child values
+ * buffer of the FixedSizeList<T, dim> column (values_len_bytes long), list_offset the list array's Offset().  Row r
+ * is read at element (list_offset + r) * dim, with the reference's truncated-buffer rule for IPC-flattened buffers
+ * (internal/store/arrow_utils.go:112-171).  pin != 0: the buffer is page-locked for the call and uploaded in
+ * chunks on two streams (DMA of one chunk under the row-statistics kernels of the previous one). */
+int lb_index_add_arrow(lb_index *idx, const void *values, size_t values_len_bytes, int64_t list_offset,
+                       int64_t n_rows, int pin);
 int64_t lb_index_size(const lb_index *idx);
 int lb_index_dim(const lb_index *idx);
 /* Labels returned = local row + id_base (row-sharded multi-GPU: base of this shard). */
@@ -161,6 +169,20 @@ int lb_simd_distance_batch_flat(int device, int metric, int dtype, const void *q
 /* simd.ADCDistanceBatch (batch_operations.go:119-127): table [m*256] fp32, codes [n*m]. */
 int lb_simd_adc_distance_batch(int device, const float *table, const uint8_t *flat_codes, int m,
                                int64_t n, float *results);
+/* Scalar quantisation (internal/simd/sq8.go:70-104): QuantizeSQ8 -- scale = 255/(max-min) (0 when equal),
+ * (v-min)*scale clamped to [0,255], truncated to a byte -- ComputeBounds, and the de-quantisation the HNSW
+ * distance computer applies inline (internal/store/arrow_hnsw.go:1176-1186): min + code * (max-min)/255. */
+int lb_simd_quantize_sq8(int device, const float *src, int64_t n, float min_val, float max_val, uint8_t *dst);
+int lb_simd_dequantize_sq8(int device, const uint8_t *src, int64_t n, float min_val, float max_val, float *dst);
+int lb_simd_compute_bounds(int device, const float *vec, int64_t n, float *min_val, float *max_val);
+/* One fp32 query against n SQ8 rows, de-quantised inline, single sequential fp32 accumulator, sqrt through
+ * double (arrow_hnsw.go:1176-1186: the distance an SQ8-enabled ArrowHNSW ranks by). */
+int lb_simd_sq8_dequant_distance_batch(int device, const float *query, const uint8_t *rows, int64_t n, int dim,
+                                       float min_val, float max_val, float *results);
+/* simd.FindNearestCentroid (internal/simd/simd.go:278-326): k <= 8 compares squared distances, larger k the
+ * sqrt'd batch results; strict '<' keeps the first minimum. */
+int lb_simd_find_nearest_centroid(int device, const float *query, const float *centroids, int sub_dim, int k,
+                                  int *out_index, float *out_distance);
 /* Arrow compute "select_k_neighbors" (internal/store/arrow_kernels.go:230-345): indices of the
  * k smallest distances, (distance, index) ascending. */
 int lb_select_k(int device, const float *distances, int64_t n, int k, int64_t *out_indices,
@@ -326,6 +348,15 @@ int lb_filter_i64_device(int device, const int64_t *d_column, int64_t n, int op,
                          uint64_t *d_bitmap, void *stream);
 int lb_filter_f32_device(int device, const float *d_column, int64_t n, int op, float value, int and_into,
                          uint64_t *d_bitmap, void *stream);
+
+/* The scatter step of Dataset.GenerateFilterBitset (internal/store/dataset.go:247-300): every set bit i of a
+ * record batch's match bitmap (lb_filter_*_device over that batch's column) sets bit VectorID(i) of the global
+ * allow-bitmap.  d_vector_ids [n_rows] gives the VectorID of each row (0xffffffff = the index has none, as when
+ * GetVectorID misses); NULL means the batch was indexed contiguously: VectorID = vid_base + i.  Ids >=
+ * n_vector_ids are ignored.  Call once per record batch on the same stream; the result feeds d_allow. */
+int lb_filter_scatter_device(int device, const uint64_t *d_batch_bitmap, int64_t n_rows,
+                             const uint32_t *d_vector_ids, uint32_t vid_base, int64_t n_vector_ids,
+                             uint64_t *d_global_bitmap, void *stream);
 
 /* Count of kernel launches issued by this library in this process (bench evidence). */
 int64_t lb_kernel_launch_count(void);

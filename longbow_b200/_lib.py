@@ -36,6 +36,7 @@ SIGNATURES = {
     "lb_index_reserve": (i32, [vp, i64]),
     "lb_index_add": (i32, [vp, vp, i64]),
     "lb_index_add_device": (i32, [vp, vp, i64, vp]),
+    "lb_index_add_arrow": (i32, [vp, vp, sz, i64, i64, i32]),
     "lb_index_size": (i64, [vp]),
     "lb_index_dim": (i32, [vp]),
     "lb_index_set_id_base": (i32, [vp, i64]),
@@ -52,6 +53,12 @@ SIGNATURES = {
     "lb_index_coarse_keys": (i32, [vp, vp, i64, i64, vp]),
     "lb_simd_distance_batch_flat": (i32, [i32, i32, i32, vp, vp, i64, i32, vp]),
     "lb_simd_adc_distance_batch": (i32, [i32, vp, vp, i32, i64, vp]),
+    "lb_simd_quantize_sq8": (i32, [i32, vp, i64, fp, fp, vp]),
+    "lb_simd_dequantize_sq8": (i32, [i32, vp, i64, fp, fp, vp]),
+    "lb_simd_compute_bounds": (i32, [i32, vp, i64, C.POINTER(fp), C.POINTER(fp)]),
+    "lb_simd_sq8_dequant_distance_batch": (i32, [i32, vp, vp, i64, i32, fp, fp, vp]),
+    "lb_simd_find_nearest_centroid": (i32, [i32, vp, vp, i32, i32, C.POINTER(i32), C.POINTER(fp)]),
+    "lb_filter_scatter_device": (i32, [i32, vp, i64, vp, C.c_uint32, i64, vp, vp]),
     "lb_select_k": (i32, [i32, vp, i64, i32, vp, vp]),
     "lb_merge_topk": (i32, [i32, vp, vp, i32, i64, i32, i32, vp, vp]),
     "lb_merge_topk_device": (i32, [i32, vp, vp, i32, i64, i32, i32, vp, vp, vp]),

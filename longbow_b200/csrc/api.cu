@@ -1,6 +1,9 @@
 // api.cu -- the C ABI of liblongbow_b200.so (include/longbow_b200.h): handles, HBM mirrors,
 // scratch management, launch planning.  No CPU fallback anywhere: without a CUDA device every
 // entry point fails with a code.
+#include <cuda.h>
+
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -132,6 +135,79 @@ struct ProfScope {
 using namespace lb;
 
 // ---------------------------------------------------------------------------------------------
+// Growable device buffer on the CUDA virtual-memory API: one large address reservation, physical chunks mapped
+// behind the used part as it grows.  Growing never copies and never synchronises the device (round 1's grow()
+// allocated 1.5x, device-synchronised and copied: 2.5x transient HBM on a 100 M-row mirror), the base pointer never
+// changes, and a 180 GB part can be filled to the brim.
+// ---------------------------------------------------------------------------------------------
+struct VBuf {
+    CUdeviceptr base = 0;
+    size_t reserved = 0, mapped = 0, gran = 0;
+    int device = 0;
+    std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+
+    void* ptr() const { return reinterpret_cast<void*>(base); }
+    int reserve_va(int dev, size_t max_bytes) {
+        device = dev;
+        CUmemAllocationProp prop = {};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = dev;
+        if (cuMemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0)
+            return fail(LB_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+        reserved = ((max_bytes + gran - 1) / gran) * gran;
+        if (cuMemAddressReserve(&base, reserved, 0, 0, 0) != CUDA_SUCCESS) {
+            base = 0; reserved = 0;
+            return fail(LB_ERR_OOM, "cuMemAddressReserve failed");
+        }
+        return LB_OK;
+    }
+    // make [0, bytes) usable
+    int ensure(size_t bytes) {
+        if (bytes <= mapped) return LB_OK;
+        if (bytes > reserved) return fail(LB_ERR_OOM, "index grew beyond its address reservation");
+        // grow in steps of at least 1/8 of what is mapped (bounded number of chunks), rounded to the granularity
+        size_t want = bytes - mapped;
+        const size_t step = mapped / 8;
+        if (want < step) want = step;
+        want = ((want + gran - 1) / gran) * gran;
+        if (mapped + want > reserved) want = reserved - mapped;
+        CUmemAllocationProp prop = {};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = device;
+        CUmemGenericAllocationHandle h;
+        CUresult r = cuMemCreate(&h, want, &prop, 0);
+        if (r != CUDA_SUCCESS && want > ((bytes - mapped + gran - 1) / gran) * gran) {  // retry with the exact need
+            want = ((bytes - mapped + gran - 1) / gran) * gran;
+            r = cuMemCreate(&h, want, &prop, 0);
+        }
+        if (r != CUDA_SUCCESS) return fail(LB_ERR_OOM, "cuMemCreate failed (device memory exhausted)");
+        if (cuMemMap(base + mapped, want, 0, h, 0) != CUDA_SUCCESS) { cuMemRelease(h); return fail(LB_ERR_CUDA, "cuMemMap failed"); }
+        CUmemAccessDesc acc = {};
+        acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc.location.id = device;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if (cuMemSetAccess(base + mapped, want, &acc, 1) != CUDA_SUCCESS) {
+            cuMemUnmap(base + mapped, want); cuMemRelease(h);
+            return fail(LB_ERR_CUDA, "cuMemSetAccess failed");
+        }
+        chunks.emplace_back(h, want);
+        mapped += want;
+        return LB_OK;
+    }
+    void release() {
+        if (base) {
+            size_t off = 0;
+            for (auto& c : chunks) { cuMemUnmap(base + off, c.second); cuMemRelease(c.first); off += c.second; }
+            cuMemAddressFree(base, reserved);
+        }
+        chunks.clear();
+        base = 0; reserved = mapped = 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 struct lb_index {
     int device, dim, dtype, metric;
     void* rows = nullptr;  // [capacity][dim]
@@ -142,12 +218,36 @@ struct lb_index {
     int64_t lo_rows = 0, lo_cap = 0;
     std::mutex lo_mu;
     int64_t size = 0, capacity = 0;
+    VBuf v_rows, v_aux, v_nrm, v_lo;  // backing store of rows / aux / nrm / lo (virtual-memory growth)
+    int64_t max_rows = 0;             // rows the address reservations cover
     uint32_t* tomb = nullptr;
     int64_t tomb_bits = 0, tomb_cap_words = 0;
+    std::vector<void*> retired;       // replaced bitmap buffers: freed lazily (kernels in flight may still read them)
     int64_t id_base = 0;
     int sm_count = 0;
     std::atomic<int64_t> last_uncertified{0};
 };
+
+// rows [0, need) usable: maps more physical memory behind the mirrors; never copies, never synchronises
+static int index_ensure_rows(lb_index* idx, int64_t need) {
+    if (need <= idx->capacity) return LB_OK;
+    if (need > idx->max_rows) return fail(LB_ERR_OOM, "more rows than this device can hold");
+    const size_t rb = (size_t)idx->dim * (idx->dtype == DT_F32 ? 4 : idx->dtype == DT_F16 ? 2 : 1);
+    int rc = idx->v_rows.ensure((size_t)need * rb);
+    if (rc) return rc;
+    rc = idx->v_aux.ensure(((size_t)need + 256) * 4);  // +256: tile-tail reads
+    if (rc) return rc;
+    if (idx->metric == METRIC_COSINE) { rc = idx->v_nrm.ensure((size_t)need * 4); if (rc) return rc; }
+    // capacity = what all mirrors cover
+    int64_t cap = (int64_t)(idx->v_rows.mapped / rb);
+    cap = std::min<int64_t>(cap, (int64_t)(idx->v_aux.mapped / 4) - 256);
+    if (idx->metric == METRIC_COSINE) cap = std::min<int64_t>(cap, (int64_t)(idx->v_nrm.mapped / 4));
+    idx->capacity = std::min<int64_t>(cap, idx->max_rows);
+    idx->rows = idx->v_rows.ptr();
+    idx->aux = reinterpret_cast<float*>(idx->v_aux.ptr());
+    idx->nrm = idx->metric == METRIC_COSINE ? reinterpret_cast<float*>(idx->v_nrm.ptr()) : nullptr;
+    return LB_OK;
+}
 
 struct lb_pq {
     int device, dims, M, K, sub;
@@ -320,6 +420,21 @@ int lb_index_create(int device, int dim, int dtype, int metric, lb_index** out) 
     idx->device = device; idx->dim = dim; idx->dtype = dtype; idx->metric = metric;
     idx->sm_count = g_dev[device].sm_count;
     {
+        // address reservations sized for the whole device: rows that fit its memory (at most 2^32 - 2^20 ids)
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t rb = (size_t)dim * dtype_size(dtype);
+        int64_t mr = (int64_t)(total_b / rb);
+        if (mr > 0xfff00000ll) mr = 0xfff00000ll;
+        if (mr < 1024) mr = 1024;
+        idx->max_rows = mr;
+        int rc2 = idx->v_rows.reserve_va(device, (size_t)mr * rb);
+        if (!rc2) rc2 = idx->v_aux.reserve_va(device, ((size_t)mr + 256) * 4);
+        if (!rc2 && metric == METRIC_COSINE) rc2 = idx->v_nrm.reserve_va(device, (size_t)mr * 4);
+        if (!rc2 && dtype == DT_F32) rc2 = idx->v_lo.reserve_va(device, (size_t)mr * rb);
+        if (rc2) { idx->v_rows.release(); idx->v_aux.release(); idx->v_nrm.release(); idx->v_lo.release(); delete idx; return rc2; }
+    }
+    {
         cudaError_t e = cudaMalloc((void**)&idx->max_norm2, 4);
         if (e == cudaSuccess) e = cudaMemset(idx->max_norm2, 0, 4);
         if (e != cudaSuccess) { if (idx->max_norm2) cudaFree(idx->max_norm2); delete idx; return fail_cuda(e, "cudaMalloc(stats)"); }
@@ -332,12 +447,10 @@ void lb_index_free(lb_index* idx) {
     if (!idx) return;
     if (cudaSetDevice(idx->device) == cudaSuccess) {
         cudaDeviceSynchronize();
-        if (idx->rows) cudaFree(idx->rows);
-        if (idx->aux) cudaFree(idx->aux);
-        if (idx->nrm) cudaFree(idx->nrm);
-        if (idx->lo) cudaFree(idx->lo);
+        idx->v_rows.release(); idx->v_aux.release(); idx->v_nrm.release(); idx->v_lo.release();
         if (idx->max_norm2) cudaFree(idx->max_norm2);
         if (idx->tomb) cudaFree(idx->tomb);
+        for (void* p : idx->retired) cudaFree(p);
     }
     cudaGetLastError();
     delete idx;
@@ -347,31 +460,7 @@ int lb_index_reserve(lb_index* idx, int64_t n_rows) {
     if (!idx || n_rows < 0) return fail(LB_ERR_INVALID, "bad argument");
     int rc = use_device(idx->device);
     if (rc) return rc;
-    if (n_rows <= idx->capacity) return LB_OK;
-    // exact-size reservation (180 GB parts: no geometric slack)
-    size_t rb = (size_t)idx->dim * dtype_size(idx->dtype);
-    void* nb = nullptr;
-    float* na = nullptr;
-    cudaError_t e = cudaMalloc(&nb, (size_t)n_rows * rb);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(rows)");
-    e = cudaMalloc((void**)&na, ((size_t)n_rows + 256) * 4);  // +256: tile-tail reads
-    if (e != cudaSuccess) { cudaFree(nb); return fail_cuda(e, "cudaMalloc(aux)"); }
-    float* nn = nullptr;
-    if (idx->metric == METRIC_COSINE) {
-        e = cudaMalloc((void**)&nn, (size_t)n_rows * 4);
-        if (e != cudaSuccess) { cudaFree(nb); cudaFree(na); return fail_cuda(e, "cudaMalloc(nrm)"); }
-    }
-    CK(cudaDeviceSynchronize());
-    if (idx->size > 0) {
-        CK(cudaMemcpy(nb, idx->rows, (size_t)idx->size * rb, cudaMemcpyDeviceToDevice));
-        CK(cudaMemcpy(na, idx->aux, (size_t)idx->size * 4, cudaMemcpyDeviceToDevice));
-        if (nn) CK(cudaMemcpy(nn, idx->nrm, (size_t)idx->size * 4, cudaMemcpyDeviceToDevice));
-    }
-    if (idx->rows) cudaFree(idx->rows);
-    if (idx->aux) cudaFree(idx->aux);
-    if (idx->nrm) cudaFree(idx->nrm);
-    idx->rows = nb; idx->aux = na; idx->nrm = nn; idx->capacity = n_rows;
-    return LB_OK;
+    return index_ensure_rows(idx, n_rows);  // maps physical memory behind the reservation: no copy, no sync
 }
 
 static int index_add_common(lb_index* idx, const void* src, int64_t n, bool src_on_device, cudaStream_t st) {
@@ -383,8 +472,7 @@ static int index_add_common(lb_index* idx, const void* src, int64_t n, bool src_
     if (rc) return rc;
     if (idx->size + n > 0xfff00000ll) return fail(LB_ERR_INVALID, "more than 2^32 rows per device handle");
     size_t rb = (size_t)idx->dim * dtype_size(idx->dtype);
-    rc = grow(&idx->rows, &idx->capacity, idx->size + n, rb, idx->size, &idx->aux,
-              idx->metric == METRIC_COSINE ? &idx->nrm : nullptr);
+    rc = index_ensure_rows(idx, idx->size + n);
     if (rc) return rc;
     char* dst = (char*)idx->rows + (size_t)idx->size * rb;
     CK(cudaMemcpyAsync(dst, src, (size_t)n * rb, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
@@ -405,6 +493,63 @@ int lb_index_add(lb_index* idx, const void* rows, int64_t n) {
 int lb_index_add_device(lb_index* idx, const void* d_rows, int64_t n, void* stream) {
     return index_add_common(idx, d_rows, n, true, (cudaStream_t)stream);
 }
+// Arrow ingest (internal/store/arrow_utils.go:112-171): rows of a FixedSizeList<T, dim> column live in the child
+// values buffer, row r at element (list_offset + r) * dim -- unless the buffer was flattened by Arrow IPC and is
+// only long enough for the relative offset, in which case row 0 is the buffer's first element (the reference's
+// "truncated buffer heuristic", :146-160).  With pin != 0 the caller's buffer is page-locked for the duration of the
+// call (cudaHostRegister) and uploaded in chunks on two streams, so the DMA of chunk i+1 overlaps the row-statistics
+// kernels of chunk i and runs at full PCIe rate instead of the pageable-copy rate.
+int lb_index_add_arrow(lb_index* idx, const void* values, size_t values_len_bytes, int64_t list_offset, int64_t n_rows,
+                       int pin) {
+    if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
+    if (n_rows < 0 || list_offset < 0) return fail(LB_ERR_INVALID, "negative size");
+    if (n_rows == 0) return LB_OK;
+    if (!values) return fail(LB_ERR_INVALID, "record is nil");
+    const size_t rb = (size_t)idx->dim * dtype_size(idx->dtype);
+    size_t start = (size_t)list_offset * rb;
+    if (values_len_bytes < start + (size_t)n_rows * rb) {
+        if (values_len_bytes >= (size_t)n_rows * rb) start = 0;  // truncated buffer: index 0 is logical row list_offset
+        else return fail(LB_ERR_INVALID, "ExtractVector: buffer out of bounds (too small even for relative access)");
+    }
+    const char* src = (const char*)values + start;
+    if (!pin) return index_add_common(idx, src, n_rows, false, cudaStreamPerThread);
+    int rc = use_device(idx->device);
+    if (rc) return rc;
+    const size_t bytes = (size_t)n_rows * rb;
+    bool registered = cudaHostRegister((void*)src, bytes, cudaHostRegisterDefault) == cudaSuccess;
+    if (!registered) {
+        cudaGetLastError();
+        registered = cudaHostRegister((void*)src, bytes, cudaHostRegisterReadOnly) == cudaSuccess;  // mmap'ed IPC files
+        if (!registered) cudaGetLastError();
+    }
+    if (idx->size + n_rows > 0xfff00000ll) { if (registered) cudaHostUnregister((void*)src); return fail(LB_ERR_INVALID, "more than 2^32 rows per device handle"); }
+    rc = index_ensure_rows(idx, idx->size + n_rows);
+    if (rc) { if (registered) cudaHostUnregister((void*)src); return rc; }
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaError_t e = cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking);
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)((32u << 20) / rb));  // 32 MB per copy
+    int which = 0;
+    for (int64_t r0 = 0; r0 < n_rows && e == cudaSuccess; r0 += chunk_rows, which ^= 1) {
+        const int64_t cr = std::min(chunk_rows, n_rows - r0);
+        const int64_t row0 = idx->size + r0;
+        e = cudaMemcpyAsync((char*)idx->rows + (size_t)row0 * rb, src + (size_t)r0 * rb, (size_t)cr * rb,
+                            cudaMemcpyHostToDevice, st[which]);
+        if (e == cudaSuccess && idx->metric != METRIC_DOT)
+            e = launch_row_aux(idx->dtype, idx->rows, row0 + cr, idx->dim, idx->metric, idx->aux, row0, st[which]);
+        if (e == cudaSuccess && idx->metric == METRIC_COSINE)
+            e = launch_row_norm_exact(idx->dtype, idx->rows, row0 + cr, idx->dim, idx->nrm, row0, st[which]);
+        if (e == cudaSuccess && idx->max_norm2)
+            e = launch_row_maxnorm(idx->dtype, idx->rows, row0 + cr, idx->dim, row0, idx->max_norm2, st[which]);
+    }
+    for (int i = 0; i < 2; i++)
+        if (st[i]) { cudaError_t e2 = cudaStreamSynchronize(st[i]); if (e == cudaSuccess) e = e2; cudaStreamDestroy(st[i]); }
+    if (registered) cudaHostUnregister((void*)src);
+    if (e != cudaSuccess) return fail_cuda(e, "lb_index_add_arrow");
+    idx->size += n_rows;
+    return LB_OK;
+}
+
 int64_t lb_index_size(const lb_index* idx) { return idx ? idx->size : -1; }
 int lb_index_dim(const lb_index* idx) { return idx ? idx->dim : -1; }
 int lb_index_set_id_base(lb_index* idx, int64_t b) {
@@ -414,12 +559,25 @@ int lb_index_set_id_base(lb_index* idx, int64_t b) {
 }
 int64_t lb_index_last_uncertified(const lb_index* idx) { return idx ? idx->last_uncertified.load() : -1; }
 
+// Replaces a device bitmap without stalling the device: the new copy is uploaded on `st`, the old buffer is
+// RETIRED (searches enqueued earlier through the *_device entry points may still read it) and freed once more than
+// a few have piled up -- one device synchronisation per eight updates instead of two per update.
 static int set_bitmap(int device, uint32_t** dst, int64_t* dst_bits, const uint64_t* src, int64_t nbits,
-                      bool on_device, cudaStream_t st) {
+                      bool on_device, cudaStream_t st, std::vector<void*>* retired) {
     int rc = use_device(device);
     if (rc) return rc;
+    auto retire = [&](void* p) {
+        if (!p) return;
+        if (!retired) { cudaDeviceSynchronize(); cudaFree(p); return; }
+        retired->push_back(p);
+        if (retired->size() > 8) {
+            cudaDeviceSynchronize();
+            for (void* r : *retired) cudaFree(r);
+            retired->clear();
+        }
+    };
     if (!src || nbits <= 0) {
-        if (*dst) { CK(cudaDeviceSynchronize()); cudaFree(*dst); }
+        retire(*dst);
         *dst = nullptr; *dst_bits = 0;
         return LB_OK;
     }
@@ -427,19 +585,23 @@ static int set_bitmap(int device, uint32_t** dst, int64_t* dst_bits, const uint6
     uint32_t* nb = nullptr;
     CK(cudaMalloc((void**)&nb, words * 8));
     CK(cudaMemcpyAsync(nb, src, words * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-    if (*dst) { CK(cudaDeviceSynchronize()); cudaFree(*dst); }
+    if (!on_device) CK(cudaStreamSynchronize(st));  // the host buffer may move after return (cgo)
+    else {
+        // later searches run on other streams: make the upload visible to them by finishing it here (it is small)
+        CK(cudaStreamSynchronize(st));
+    }
+    retire(*dst);
     *dst = nb; *dst_bits = (int64_t)words * 64;
     return LB_OK;
 }
 
 int lb_index_set_tombstones(lb_index* idx, const uint64_t* bitmap, int64_t nbits) {
     if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
-    return set_bitmap(idx->device, &idx->tomb, &idx->tomb_bits, bitmap, nbits, false, cudaStreamPerThread);
+    return set_bitmap(idx->device, &idx->tomb, &idx->tomb_bits, bitmap, nbits, false, cudaStreamPerThread, &idx->retired);
 }
 int lb_index_set_tombstones_device(lb_index* idx, const uint64_t* d_bitmap, int64_t nbits, void* stream) {
     if (!idx) return fail(LB_ERR_INVALID, "index is NULL");
-    return set_bitmap(idx->device, &idx->tomb, &idx->tomb_bits, d_bitmap, nbits, true, (cudaStream_t)stream);
+    return set_bitmap(idx->device, &idx->tomb, &idx->tomb_bits, d_bitmap, nbits, true, (cudaStream_t)stream, &idx->retired);
 }
 
 // coarse candidates per query: margin over k absorbs coarse-key rounding; the re-score stage
@@ -457,16 +619,10 @@ static int coarse_k(int k) {
 static int ensure_lo(lb_index* idx, cudaStream_t st) {
     std::lock_guard<std::mutex> g(idx->lo_mu);
     if (idx->lo_rows == idx->size && idx->lo != nullptr) return LB_OK;
-    if (idx->lo_cap < idx->capacity || idx->lo == nullptr) {
-        float* nl = nullptr;
-        CK(cudaMalloc((void**)&nl, (size_t)idx->capacity * idx->dim * 4));
-        CK(cudaDeviceSynchronize());
-        if (idx->lo && idx->lo_rows > 0)
-            CK(cudaMemcpy(nl, idx->lo, (size_t)idx->lo_rows * idx->dim * 4, cudaMemcpyDeviceToDevice));
-        if (idx->lo) cudaFree(idx->lo);
-        idx->lo = nl;
-        idx->lo_cap = idx->capacity;
-    }
+    int rc = idx->v_lo.ensure((size_t)idx->size * idx->dim * 4);
+    if (rc) return rc;
+    idx->lo = reinterpret_cast<float*>(idx->v_lo.ptr());
+    idx->lo_cap = idx->size;
     const size_t off = (size_t)idx->lo_rows * idx->dim;
     CK(launch_split_lo((const float*)idx->rows + off, idx->lo + off, (size_t)(idx->size - idx->lo_rows) * idx->dim, st));
     CK(cudaStreamSynchronize(st));  // other threads' streams may use it as soon as the lock drops
@@ -1223,7 +1379,7 @@ int lb_pq_attach_raw(lb_pq* pq, lb_index* raw) {
 
 int lb_pq_set_tombstones(lb_pq* pq, const uint64_t* bitmap, int64_t nbits) {
     if (!pq) return fail(LB_ERR_INVALID, "pq is NULL");
-    return set_bitmap(pq->device, &pq->tomb, &pq->tomb_bits, bitmap, nbits, false, cudaStreamPerThread);
+    return set_bitmap(pq->device, &pq->tomb, &pq->tomb_bits, bitmap, nbits, false, cudaStreamPerThread, nullptr);
 }
 
 int lb_pq_build_adc_table(lb_pq* pq, const float* query, float* table) {

@@ -191,6 +191,12 @@ class DenseIndex:
             raise ValueError(f"vector data length {rows.size} not divisible by dimension {self.dim}")
         check(self._lib.lb_index_add(self._h, _ptr(rows), rows.size // self.dim))
 
+    def add_arrow(self, values: np.ndarray, list_offset: int, n_rows: int, pin: bool = True):
+        """Append rows straight from an Arrow FixedSizeList child values buffer (a flat NumPy view of it):
+        internal/store/arrow_utils.go:112-171, including the truncated-buffer rule."""
+        values = np.ascontiguousarray(values, dtype=self.np_dtype).reshape(-1)
+        check(self._lib.lb_index_add_arrow(self._h, _ptr(values), values.nbytes, int(list_offset), int(n_rows), int(pin)))
+
     def add_device(self, tensor, stream=None):
         """Append rows already resident on this device (a contiguous torch tensor)."""
         assert tensor.is_cuda and tensor.is_contiguous()

@@ -263,3 +263,26 @@ def CallFunction(name: str, *args, **kwargs):
     if name not in _ARROW_FUNCTIONS:
         raise KeyError(f"function not found: {name}")
     return _ARROW_FUNCTIONS[name](*args, **kwargs)
+
+
+def GenerateFilterBitsetBatches(batches, op: int, value, n_vector_ids: int, device: int = 0):
+    """Dataset.GenerateFilterBitset (internal/store/dataset.go:247-300) over several record batches, on the device:
+    ``batches`` = [(column (int64 / float32 array), vector_ids (uint32 array with 0xffffffff for rows the index
+    does not know) or an int VectorID base for contiguously indexed batches), ...].  Per batch the predicate
+    kernel builds the batch-local match bitmap and the scatter kernel sets the matching rows' VectorID bits in one
+    global allow-bitmap (packed uint64, n_vector_ids bits), which can be passed to the searches as ``allow``."""
+    import torch
+    lib = _lib.load()
+    dev = torch.device("cuda", device)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    glob = torch.zeros((n_vector_ids + 63) // 64, dtype=torch.int64, device=dev)
+    for column, ids in batches:
+        col = torch.from_numpy(np.ascontiguousarray(column)).to(dev)
+        n = col.numel()
+        bm = GenerateFilterBitsetDevice(col, op, value, device=device)
+        if isinstance(ids, (int, np.integer)):
+            check(lib.lb_filter_scatter_device(device, bm.data_ptr(), n, None, int(ids), n_vector_ids, glob.data_ptr(), st))
+        else:
+            idt = torch.from_numpy(np.ascontiguousarray(ids, np.uint32).view(np.int32)).to(dev)
+            check(lib.lb_filter_scatter_device(device, bm.data_ptr(), n, idt.data_ptr(), 0, n_vector_ids, glob.data_ptr(), st))
+    return glob.cpu().numpy().view(np.uint64)

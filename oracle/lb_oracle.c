@@ -748,3 +748,60 @@ LBO_API int lbo_hnsw_search_layer_batch(int metric, int dtype, const void *db, i
     }
     return bad ? -1 : 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * SQ8 scalar quantisation (internal/simd/sq8.go:70-104) and the inline de-quantising distance of the
+ * HNSW computer (internal/store/arrow_hnsw.go:1176-1186).
+ * -------------------------------------------------------------------------------------------- */
+LBO_API void lbo_quantize_sq8(const float *src, int64_t n, float minv, float maxv, uint8_t *dst) {
+    float scale = 255.0f / (maxv - minv);
+    if (maxv == minv) scale = 0;
+    for (int64_t i = 0; i < n; i++) {
+        float val = (src[i] - minv) * scale;
+        if (val < 0) val = 0;
+        if (val > 255) val = 255;
+        dst[i] = (uint8_t)val;
+    }
+}
+LBO_API void lbo_compute_bounds(const float *v, int64_t n, float *mn, float *mx) {
+    if (n == 0) { *mn = 0; *mx = 0; return; }
+    float a = v[0], b = v[0];
+    for (int64_t i = 1; i < n; i++) { if (v[i] < a) a = v[i]; if (v[i] > b) b = v[i]; }
+    *mn = a; *mx = b;
+}
+LBO_API void lbo_dequantize_sq8(const uint8_t *src, int64_t n, float minv, float maxv, float *dst) {
+    const float scale = (maxv - minv) / 255.0f;
+    for (int64_t i = 0; i < n; i++) dst[i] = minv + (float)src[i] * scale;
+}
+LBO_API void lbo_sq8_dequant_distance_batch(const float *q, const uint8_t *rows, int64_t n, int dim, float minv,
+                                            float maxv, float *out) {
+    const float scale = (maxv - minv) / 255.0f;
+    for (int64_t r = 0; r < n; r++) {
+        float sum = 0;
+        for (int i = 0; i < dim; i++) {
+            float deq = minv + (float)rows[r * dim + i] * scale;
+            float diff = q[i] - deq;
+            sum += diff * diff;
+        }
+        out[r] = (float)sqrt((double)sum);
+    }
+}
+/* simd.FindNearestCentroid (internal/simd/simd.go:278-326) */
+LBO_API int lbo_find_nearest_centroid(const float *query, const float *cent, int sub, int k, float *out_d) {
+    if (k <= 8) {
+        float best = FLT_MAX; int bi = 0;
+        for (int i = 0; i < k; i++) {
+            float d = lbo_l2sq_f32(query, cent + (size_t)i * sub, sub);
+            if (d < best) { best = d; bi = i; }
+        }
+        *out_d = best;
+        return bi;
+    }
+    float best = lbo_euclid_f32(query, cent, sub); int bi = 0;
+    for (int i = 1; i < k; i++) {
+        float d = lbo_euclid_f32(query, cent + (size_t)i * sub, sub);
+        if (d < best) { best = d; bi = i; }
+    }
+    *out_d = best;
+    return bi;
+}

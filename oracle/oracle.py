@@ -264,3 +264,40 @@ def fast_use_all_cores() -> int:
 
 def fast_isa() -> str:
     return {2: "avx512", 1: "avx2", 0: "scalar"}[int(fast().lbf_isa())]
+
+
+def quantize_sq8(src: np.ndarray, minv: float, maxv: float) -> np.ndarray:
+    src = _c(src, np.float32).reshape(-1)
+    dst = np.empty(src.size, np.uint8)
+    exact().lbo_quantize_sq8(_p(src), C.c_int64(src.size), C.c_float(minv), C.c_float(maxv), _p(dst))
+    return dst
+
+
+def dequantize_sq8(src: np.ndarray, minv: float, maxv: float) -> np.ndarray:
+    src = _c(src, np.uint8).reshape(-1)
+    dst = np.empty(src.size, np.float32)
+    exact().lbo_dequantize_sq8(_p(src), C.c_int64(src.size), C.c_float(minv), C.c_float(maxv), _p(dst))
+    return dst
+
+
+def compute_bounds(v: np.ndarray):
+    v = _c(v, np.float32).reshape(-1)
+    mn, mx = C.c_float(), C.c_float()
+    exact().lbo_compute_bounds(_p(v), C.c_int64(v.size), C.byref(mn), C.byref(mx))
+    return mn.value, mx.value
+
+
+def sq8_dequant_distance_batch(q: np.ndarray, rows: np.ndarray, minv: float, maxv: float) -> np.ndarray:
+    q, rows = _c(q, np.float32), _c(rows, np.uint8)
+    out = np.empty(rows.shape[0], np.float32)
+    exact().lbo_sq8_dequant_distance_batch(_p(q), _p(rows), C.c_int64(rows.shape[0]), rows.shape[1], C.c_float(minv),
+                                           C.c_float(maxv), _p(out))
+    return out
+
+
+def find_nearest_centroid(query: np.ndarray, centroids: np.ndarray):
+    query, centroids = _c(query, np.float32), _c(centroids, np.float32)
+    k, sub = centroids.shape
+    d = C.c_float()
+    i = exact().lbo_find_nearest_centroid(_p(query), _p(centroids), sub, k, C.byref(d))
+    return int(i), d.value

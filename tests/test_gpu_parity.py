@@ -686,3 +686,42 @@ def test_pq_train_reference_fuzz_shapes(oracle, dims, M, K, n):
     assert np.array_equal(iters, witers)
     assert np.array_equal(cb, wcb)
     assert cb.shape == (M, K, dims // M)
+
+
+# ------------------------------------------------------------------ Arrow ingest, growth, bitmap updates
+def test_add_arrow_offsets_pinned_and_growth(lbgpu, oracle):
+    """lb_index_add_arrow: list offset, the reference's truncated-buffer rule (arrow_utils.go:146-160), pinned chunked
+    upload; the mirror grows across many appends without copying (base pointer stable), results stay bit-exact."""
+    rng = np.random.default_rng(2024)
+    n, dim, k = 30000, 96, 10
+    db = make_db(rng, n, dim, np.float16)
+    idx = lbgpu.DenseIndex(dim, np.float16, COS)
+    pad = make_db(rng, 7, dim, np.float16)
+    buf = np.concatenate([pad, db[:10000]]).reshape(-1)          # list offset 7 inside a larger values buffer
+    idx.add_arrow(buf, 7, 10000, pin=True)
+    idx.add_arrow(db[10000:20000].reshape(-1), 123, 10000, pin=True)   # IPC-flattened: offset kept, buffer relative
+    idx.add_arrow(db[20000:].reshape(-1), 0, 10000, pin=False)
+    with pytest.raises(Exception):
+        idx.add_arrow(db[:10].reshape(-1), 0, 11)                  # too small even for relative access
+    assert len(idx) == n
+    q = make_db(rng, 20, dim, np.float16)
+    gd, gl = idx.search(q, k)
+    wd, wl = oracle.search(COS, db, q, k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "arrow ingest")
+    # many small appends: growth maps memory behind the mirror, earlier rows stay where they were
+    more = make_db(rng, 5000, dim, np.float16)
+    for lo in range(0, 5000, 500):
+        idx.add(more[lo:lo + 500])
+    full = np.concatenate([db, more])
+    gd, gl = idx.search(q, k)
+    wd, wl = oracle.search(COS, full, q, k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "after growth")
+    # tombstone updates in a loop (no device stall per update, old buffers retired)
+    for i in range(12):
+        tomb = np.zeros(len(idx), bool)
+        tomb[rng.integers(0, len(idx), 200)] = True
+        idx.set_tombstones(tomb)
+    gd, gl = idx.search(q, k)
+    wd, wl = oracle.search(COS, full, q, k, tomb=lbgpu.pack_bitmap(tomb))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "after tombstone updates")
+    idx.close()

@@ -12,8 +12,10 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(1)
-if cfg == "c2":
+if cfg.startswith("c2"):
     N, D, Q, K, metric, npdt = 1_000_000, 768, 1024, 100, _lib.METRIC_COSINE, np.float16
+    if ":" in cfg:
+        N = int(cfg.split(":")[1])  # c2:125000 = one rank's shard at 8 GPUs
     db = torch.randn((N, D), generator=g, device=dev)
     db = (db / db.norm(dim=1, keepdim=True)).half()
     qs = torch.randn((Q, D), generator=g, device=dev)
