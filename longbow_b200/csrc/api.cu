@@ -356,6 +356,10 @@ int lb_set_option(const char* name, int value) {
         g_rescore_legacy = value != 0;
         return LB_OK;
     }
+    if (strcmp(name, "rescore_block") == 0) {
+        g_rescore_block = value != 0;
+        return LB_OK;
+    }
     if (strcmp(name, "tc_debug") == 0) {
         g_opt_tc_debug.store(value);
         return LB_OK;

@@ -34,6 +34,7 @@ inline cudaError_t smem_optin(const void* func, std::atomic<uint64_t>& done) {
     } while (0)
 
 extern bool g_rescore_legacy;
+extern bool g_rescore_block;
 extern bool g_tc_pair;
 void count_launch();  // api.cu: process-wide launch counter (bench evidence)
 

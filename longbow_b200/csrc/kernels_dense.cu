@@ -13,7 +13,8 @@
 
 namespace lb {
 
-bool g_rescore_legacy = false;  // lb_set_option("rescore_legacy"): A/B the thread-per-candidate kernel
+bool g_rescore_legacy = false;
+bool g_rescore_block = false;   // lb_set_option("rescore_block"): A/B the block-per-query cooperative kernel  // lb_set_option("rescore_legacy"): A/B the thread-per-candidate kernel
 
 // ---------------------------------------------------------------------------------------------
 // Row auxiliaries used by coarse keys: aux[r] = |x_r|^2 (L2) or 1/|x_r| (cosine; 0 for a
@@ -617,6 +618,52 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// One trip of the cooperative gather: the warp's (up to ROWS) candidate rows are copied global -> shared in 128-byte
+// chunks with NBUF chunk buffers in flight, and lane l accumulates candidate l's chunk out of shared memory in the
+// reference order.  NBUF * ROWS == 96 (the staging space of one warp).
+template <typename T, int ACC, int NBUF, int ROWS>
+__device__ __forceinline__ void rc_gather(unsigned char* stage, const unsigned char* const (&src_row)[8],
+                                          const bool (&src_ok)[8], size_t row_bytes, int n_chunks, int dim,
+                                          const float* qf, bool ok, int lane, ExactAcc<ACC>& acc) {
+    constexpr int V = Elem<T>::kVec;
+    constexpr int PIECES = RC_CHUNK / 16;
+    auto issue = [&](int ch) {
+        unsigned char* dstb = stage + (size_t)(ch % NBUF) * ROWS * RC_PITCH + (lane & 7) * 16;
+        const size_t off = (size_t)ch * RC_CHUNK;
+        const bool in_row = off + (size_t)(lane & 7) * 16 < row_bytes;  // tail chunk: pieces past the row end
+#pragma unroll
+        for (int i = 0; i < ROWS / 4; i++) {
+            if (src_ok[i] && in_row) cp_async16(dstb + (size_t)(4 * i + (lane >> 3)) * RC_PITCH, src_row[i] + off);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int p = 0; p < NBUF - 1; p++) {
+        if (p < n_chunks) issue(p); else cp_async_commit();
+    }
+    for (int ch = 0; ch < n_chunks; ch++) {
+        if (ch + NBUF - 1 < n_chunks) issue(ch + NBUF - 1); else cp_async_commit();
+        cp_async_wait<NBUF - 1>();
+        __syncwarp();
+        if (ok) {
+            const uint4* rowp = reinterpret_cast<const uint4*>(stage + (size_t)(ch % NBUF) * ROWS * RC_PITCH +
+                                                               (size_t)lane * RC_PITCH);
+            const int e0 = ch * (RC_CHUNK / (int)sizeof(T));
+#pragma unroll
+            for (int p = 0; p < PIECES; p++) {
+                const int i0 = e0 + p * V;
+                if (i0 < dim) {  // dim % V == 0 on this path: a piece is inside the row entirely or not at all
+                    float x[V];
+                    unpack16<T>(rowp[p], x);
+#pragma unroll
+                    for (int e = 0; e < V; e++) acc.add(e & 3, qf[i0 + e], x[e]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(RC_WARPS * 32)
 rescore_coop_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T* __restrict__ queries, int nq,
@@ -625,8 +672,6 @@ rescore_coop_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T*
                     int64_t id_base, float* __restrict__ out_d, int64_t* __restrict__ out_l, int negate_dot,
                     const float* __restrict__ nrm, const CertArgs ca) {
     __shared__ float s_red32[32];
-    constexpr int V = Elem<T>::kVec;              // elements per 16-byte piece
-    constexpr int PIECES = RC_CHUNK / 16;         // pieces per row chunk
     constexpr int ACC = (METRIC == METRIC_COSINE) ? METRIC_DOT : METRIC;  // cosine: stored |x|^2, dot chain only
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                      // [n2]
@@ -681,12 +726,16 @@ rescore_coop_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T*
         n_cand = s_live;
     }
 
-    for (int base = warp * 32; base < n_cand; base += RC_WARPS * 32) {
+    // Candidates are dealt to the warps in equal contiguous shares (not 32 at a time): with bitmaps in force only
+    // ~36 of 128 ids survive, and dealing by 32 left three of the four warps idle through the whole gather.
+    const int per_warp = (n_cand + RC_WARPS - 1) / RC_WARPS;
+    const int w_begin = warp * per_warp, w_end = min(n_cand, w_begin + per_warp);
+    for (int base = w_begin; base < w_end; base += 32) {
         // candidate of this lane
         const int ci = base + lane;
         uint32_t id = 0xffffffffu;
         bool ok = false;
-        if (ci < n_cand) {
+        if (ci < w_end) {
             if (packed != nullptr) {
                 const uint64_t p = packed[(size_t)q * c + ci];
                 if (p != kInvalid) { id = id_of(p); ok = id < n_rows; }
@@ -705,41 +754,15 @@ rescore_coop_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T*
             src_ok[i] = __shfl_sync(0xffffffffu, ok ? 1 : 0, r) != 0;
             src_row[i] = reinterpret_cast<const unsigned char*>(db) + (size_t)rid * row_bytes + (lane & 7) * 16;
         }
-        auto issue = [&](int ch) {
-            unsigned char* dstb = stage + (size_t)(ch % RC_NBUF) * 32 * RC_PITCH + (lane & 7) * 16;
-            const size_t off = (size_t)ch * RC_CHUNK;
-            const bool in_row = off + (size_t)(lane & 7) * 16 < row_bytes;  // tail chunk: pieces past the row end
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (src_ok[i] && in_row) cp_async16(dstb + (size_t)(4 * i + (lane >> 3)) * RC_PITCH, src_row[i] + off);
-            }
-            cp_async_commit();
-        };
+        // The staging space holds 3 chunks of 32 rows.  A trip with <= 16 (<= 8) rows lays the same space out as
+        // 6 (12) chunk buffers of 16 (8) rows: a short candidate list (bitmaps in force) gets a deeper pipeline
+        // instead of idle buffer rows -- 12 buffers cover a whole 1.5 KB row, i.e. ONE memory round trip.
+        const int rows_here = min(32, w_end - base);
         ExactAcc<ACC> acc;
         acc.init();
-        issue(0);
-        if (n_chunks > 1) issue(1); else cp_async_commit();
-        for (int ch = 0; ch < n_chunks; ch++) {
-            if (ch + 2 < n_chunks) issue(ch + 2); else cp_async_commit();
-            cp_async_wait<2>();
-            __syncwarp();
-            if (ok) {
-                const uint4* rowp = reinterpret_cast<const uint4*>(stage + (size_t)(ch % RC_NBUF) * 32 * RC_PITCH +
-                                                                   (size_t)lane * RC_PITCH);
-                const int e0 = ch * (RC_CHUNK / (int)sizeof(T));
-#pragma unroll
-                for (int p = 0; p < PIECES; p++) {
-                    const int i0 = e0 + p * V;
-                    if (i0 < dim) {  // dim % V == 0 on this path: a piece is inside the row entirely or not at all
-                        float x[V];
-                        unpack16<T>(rowp[p], x);
-#pragma unroll
-                        for (int e = 0; e < V; e++) acc.add(e & 3, qf[i0 + e], x[e]);
-                    }
-                }
-            }
-            __syncwarp();
-        }
+        if (rows_here <= 8) rc_gather<T, ACC, 12, 8>(stage, src_row, src_ok, row_bytes, n_chunks, dim, qf, ok, lane, acc);
+        else if (rows_here <= 16) rc_gather<T, ACC, 6, 16>(stage, src_row, src_ok, row_bytes, n_chunks, dim, qf, ok, lane, acc);
+        else rc_gather<T, ACC, 3, 32>(stage, src_row, src_ok, row_bytes, n_chunks, dim, qf, ok, lane, acc);
         if (ok) {
             float d;
             if (METRIC == METRIC_COSINE) {
@@ -769,6 +792,124 @@ rescore_coop_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T*
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// S3, warp-per-query form.  Same gather and the same arithmetic as rescore_coop_kernel, but one WARP owns a query
+// end to end (ids -> bitmap tests -> gather -> exact distances -> sort -> certification -> output) and never
+// meets a block barrier: the four warps of a CTA are four independent queries.  The block form spent most of a
+// short-list call (bitmaps in force: ~36 live ids of 128) waiting on its own serial latency chain -- ids, bitmap
+// words, rows, sort, each behind a __syncthreads -- with three CTAs per SM; here twelve to twenty queries per SM
+// are in flight at different stages.  SR = staging row-buffers per warp (96: trips of 32 rows; 48: trips of 16,
+// half the shared memory, for lists that bitmaps are going to thin out).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int METRIC, int SR>
+__global__ void __launch_bounds__(RC_WARPS * 32)
+rescore_warp_kernel(const T* __restrict__ db, uint32_t n_rows, int dim, const T* __restrict__ queries, int nq,
+                    const uint64_t* __restrict__ packed, const uint32_t* __restrict__ ids32, int c, int k, int n2,
+                    const uint32_t* __restrict__ tomb, uint32_t tomb_bits, const uint32_t* __restrict__ allow,
+                    int64_t id_base, float* __restrict__ out_d, int64_t* __restrict__ out_l, int negate_dot,
+                    const float* __restrict__ nrm, const CertArgs ca) {
+    constexpr int ACC = (METRIC == METRIC_COSINE) ? METRIC_DOT : METRIC;  // cosine: stored |x|^2, dot chain only
+    constexpr int TRIP = (SR >= 96) ? 32 : 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * RC_WARPS + warp;
+    if (q >= nq) return;
+    const size_t per_warp = (size_t)n2 * 8 + (size_t)n2 * 4 + (size_t)((dim + 3) & ~3) * 4 + (size_t)SR * RC_PITCH;
+    unsigned char* base_p = smem_raw + (size_t)warp * per_warp;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(base_p);                 // [n2]
+    uint32_t* live = reinterpret_cast<uint32_t*>(keys + n2);              // [n2]
+    float* qf = reinterpret_cast<float*>(live + n2);                      // [dim]
+    unsigned char* stage = reinterpret_cast<unsigned char*>(qf + ((dim + 3) & ~3));
+    const T* qrow = queries + (size_t)q * dim;
+    for (int i = lane; i < dim; i += 32) qf[i] = Elem<T>::widen(qrow[i]);
+    for (int i = lane; i < n2; i += 32) keys[i] = kInvalid;
+    __syncwarp();
+    float qn_exact = 0.f;  // cosine: |q|^2 in the reference lane order (simd.go:399-450), lanes 0..3 hold the lanes
+    if (METRIC == METRIC_COSINE) {
+        float sacc = 0.f;
+        if (lane < 4) {
+            const int main_end = dim - (dim & 3);
+            for (int i = lane; i < main_end; i += 4) sacc = __fadd_rn(sacc, __fmul_rn(qf[i], qf[i]));
+            if (lane == 0) for (int i = main_end; i < dim; i++) sacc = __fadd_rn(sacc, __fmul_rn(qf[i], qf[i]));
+        }
+        const float s0 = __shfl_sync(0xffffffffu, sacc, 0), s1 = __shfl_sync(0xffffffffu, sacc, 1);
+        const float s2 = __shfl_sync(0xffffffffu, sacc, 2), s3 = __shfl_sync(0xffffffffu, sacc, 3);
+        qn_exact = __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
+    }
+    const size_t row_bytes = (size_t)dim * sizeof(T);
+    const int n_chunks = (int)((row_bytes + RC_CHUNK - 1) / RC_CHUNK);
+    // live candidate ids, compacted (order is irrelevant: the result is sorted by (distance, id))
+    int n_cand = 0;
+    for (int c0 = 0; c0 < c; c0 += 32) {
+        const int ci = c0 + lane;
+        uint32_t id = 0xffffffffu;
+        bool ok = false;
+        if (ci < c) {
+            if (packed != nullptr) {
+                const uint64_t p = packed[(size_t)q * c + ci];
+                if (p != kInvalid) { id = id_of(p); ok = id < n_rows; }
+            } else {
+                id = ids32[(size_t)q * c + ci];
+                ok = id < n_rows;
+                if (ok && allow != nullptr && !bit_set(allow, id)) ok = false;
+                if (ok && tomb != nullptr && id < tomb_bits && bit_set(tomb, id)) ok = false;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) live[n_cand + __popc(m & ((1u << lane) - 1u))] = id;
+        n_cand += __popc(m);
+    }
+    __syncwarp();
+    for (int base = 0; base < n_cand; base += TRIP) {
+        const int ci = base + lane;
+        const bool ok = lane < TRIP && ci < n_cand;
+        const uint32_t id = ok ? live[ci] : 0xffffffffu;
+        const unsigned char* src_row[8];
+        bool src_ok[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = 4 * i + (lane >> 3);
+            const uint32_t rid = __shfl_sync(0xffffffffu, id, r);
+            src_ok[i] = __shfl_sync(0xffffffffu, ok ? 1 : 0, r) != 0;
+            src_row[i] = reinterpret_cast<const unsigned char*>(db) + (size_t)rid * row_bytes + (lane & 7) * 16;
+        }
+        const int rows_here = min(TRIP, n_cand - base);
+        ExactAcc<ACC> acc;
+        acc.init();
+        if (rows_here <= 8) rc_gather<T, ACC, SR / 8, 8>(stage, src_row, src_ok, row_bytes, n_chunks, dim, qf, ok, lane, acc);
+        else if (rows_here <= 16 || SR < 96) rc_gather<T, ACC, SR / 16, 16>(stage, src_row, src_ok, row_bytes, n_chunks, dim, qf, ok, lane, acc);
+        else rc_gather<T, ACC, (SR >= 96 ? SR / 32 : 3), 32>(stage, src_row, src_ok, row_bytes, n_chunks, dim, qf, ok, lane, acc);
+        if (ok) {
+            float d;
+            if (METRIC == METRIC_COSINE) {
+                const float dot = acc.finish();
+                const float nb = __ldg(nrm + id);
+                if (qn_exact == 0.f || nb == 0.f) d = 1.0f;
+                else d = __fsub_rn(1.0f, __fdiv_rn(dot, (float)sqrt((double)qn_exact * (double)nb)));
+            } else {
+                d = acc.finish();
+            }
+            if (METRIC == METRIC_DOT && negate_dot) d = -d;
+            if (d < INFINITY) keys[ci] = pack_key(d, id);  // NaN / +Inf are never returned
+        }
+    }
+    __syncwarp();
+    warp_bitonic_sort(keys, next_pow2(max(n_cand, 2)), lane);
+    if (ca.flags != nullptr && packed != nullptr) {
+        float s = 0.f;
+        for (int i = lane; i < dim; i += 32) s = fmaf(qf[i], qf[i], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) certify<METRIC>(ca, q, packed + (size_t)q * c, c, keys, k, s);
+    }
+    for (int j = lane; j < k; j += 32) {
+        const uint64_t p = (j < n2) ? keys[j] : kInvalid;
+        const bool valid = p != kInvalid;
+        out_d[(size_t)q * k + j] = valid ? key_of(p) : 3.402823466e+38f;
+        out_l[(size_t)q * k + j] = valid ? (int64_t)id_of(p) + id_base : -1;
+    }
+}
+
 template <typename T>
 static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
     int n2 = next_pow2(max(a.c, 32));
@@ -778,6 +919,32 @@ static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
     const size_t row_bytes = (size_t)a.dim * sizeof(T);
     const bool coop = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.db) & 15) == 0) &&
                       !(a.metric == METRIC_COSINE && a.nrm == nullptr) && !g_rescore_legacy;
+    if (coop && !g_rescore_block) {
+        // warp-per-query kernel; lists that bitmaps will thin out get the half-size staging (more queries per SM)
+        const bool thin = a.packed == nullptr && (a.allow != nullptr || a.tomb != nullptr);
+        const int SRv = thin ? 48 : 96;
+        const size_t per_warp = (size_t)n2 * 12 + (size_t)((a.dim + 3) & ~3) * 4 + (size_t)SRv * RC_PITCH;
+        const size_t smem = per_warp * RC_WARPS;
+        if (smem <= 200 * 1024) {
+            const int grid = (a.nq + RC_WARPS - 1) / RC_WARPS;
+#define LB_RW(M, S)                                                                                         \
+    {                                                                                                       \
+        auto kern = rescore_warp_kernel<T, M, S>;                                                           \
+        LB_SMEM_OPTIN(kern);                                                                                \
+        kern<<<grid, RC_WARPS * 32, smem, st>>>((const T*)a.db, a.n_rows, a.dim, (const T*)a.queries, a.nq, \
+                                                a.packed, a.ids32, a.c, a.k, n2, a.tomb, a.tomb_bits, a.allow, \
+                                                a.id_base, a.out_d, a.out_l, a.negate_dot, a.nrm, ca);      \
+    }
+            switch (a.metric) {
+                case METRIC_L2: if (thin) LB_RW(METRIC_L2, 48) else LB_RW(METRIC_L2, 96) break;
+                case METRIC_COSINE: if (thin) LB_RW(METRIC_COSINE, 48) else LB_RW(METRIC_COSINE, 96) break;
+                default: if (thin) LB_RW(METRIC_DOT, 48) else LB_RW(METRIC_DOT, 96) break;
+            }
+#undef LB_RW
+            count_launch();
+            return cudaGetLastError();
+        }
+    }
     if (coop) {
         const size_t smem = (size_t)n2 * 8 + (size_t)((a.dim + 3) & ~3) * 4 + (size_t)RC_WARPS * RC_NBUF * 32 * RC_PITCH +
                             (size_t)n2 * 4;
