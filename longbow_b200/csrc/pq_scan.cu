@@ -39,6 +39,7 @@
 
 namespace lb {
 
+int g_pq_ahead = 2;  // lb_set_option("pq_ahead"): measured flat for 1..6 trips, worse at 12 (L2 thrash)
 constexpr int PQS_THREADS = 640;   // 20 warps, one CTA per SM, <= 102 registers: room for two tiles of codes per lane
 constexpr int PQS_WARPS = PQS_THREADS / 32;
 constexpr int PQS_GROUP_BYTES = 65536;  // one group's table: 256 codes x 256 B
@@ -222,6 +223,7 @@ struct PqCoarseArgs {
     // [nq], zeroed by the caller: set when a candidate had to be dropped because a CTA's list was full between two
     // overflow checks (only degenerate tables can do that); the exact stage then reports the query uncertified
     uint32_t* overflow;
+    int ahead;                // trips the L2 prefetch runs ahead of the register loads (single-query passes)
 };
 
 // kc-th smallest (rounded UP to a histogram bin edge: still a valid upper bound) of the set entries of v[0, n).
@@ -448,12 +450,26 @@ adc_coarse_kernel(const PqCoarseArgs a) {
 
     // two trips per loop iteration with ping-pong register buffers: the next tile's codes are in flight while the
     // current tile's look-ups run
+    // The register double buffer keeps one tile (3 KB) per warp in flight: 60 KB per SM, which at the loaded HBM
+    // latency (~2.5 us) sustains only ~3.7 TB/s.  The rest of the latency is taken off the critical path by an L2
+    // prefetch PQS_AHEAD trips ahead: one lane issues a bulk prefetch of the warp's future tile (no registers, no
+    // shared memory), so the later LDG hits L2.
+    auto l2_prefetch = [&](uint32_t tile) {
+        if (NQ == 1 && lane == 0 && tile < tile_end) {  // batched passes re-read the codes from L2 anyway
+            const void* p = a.tiles + (size_t)tile * CH * 32;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(CH * 32 * 16)) : "memory");
+        }
+    };
+    const uint32_t PQS_AHEAD = (uint32_t)a.ahead;
     uint4 buf0[CH], buf1[CH];
+    for (uint32_t p = 1; p < PQS_AHEAD; p++) l2_prefetch(tile_begin + p * PQS_WARPS + warp);
     prefetch(buf0, tile_begin + warp);
     uint32_t it = 0;
 #pragma unroll 1
     for (; it + 1 < iters; it += 2) {
         const uint32_t tile = tile_begin + it * PQS_WARPS + warp;
+        l2_prefetch(tile + PQS_AHEAD * PQS_WARPS);
+        l2_prefetch(tile + (PQS_AHEAD + 1) * PQS_WARPS);
         prefetch(buf1, tile + PQS_WARPS);
         consume(buf0, tile);
         housekeeping(it);
@@ -623,7 +639,7 @@ cudaError_t launch_adc_coarse(const uint8_t* tiled, uint32_t n_rows, int M, cons
     a.tiles = reinterpret_cast<const uint4*>(tiled); a.n_rows = n_rows; a.tiles_per_part = tiles_per_part;
     a.lutq = lutq; a.tomb = tomb; a.tomb_bits = tomb_bits; a.allow = allow;
     a.kc = kc; a.nq = nq; a.compact = compact; a.out_cnt = out_cnt; a.stride = stride; a.g_tau = g_tau;
-    a.g_min = g_min; a.nmin = parts * PQS_WARPS; a.overflow = overflow;
+    a.g_min = g_min; a.nmin = parts * PQS_WARPS; a.overflow = overflow; a.ahead = g_pq_ahead;
     a.cap = (nq_per_pass == 1) ? 2048 : 1024;
 #define LB_PQC(NQ_, G_) return launch_coarse_t<NQ_, G_>(a, qgroups, parts, st)
     if (nq_per_pass == 1) {
