@@ -441,6 +441,9 @@ def main():
             hbm_scan["frac"] = hbm_scan["achieved_gbs"] / hbm_peak
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": ("ncu --set full capture of this kernel on this workload (dram__bytes_read.sum + "
+                                   "dram__bytes_write.sum per launch), profiles/r1_roofline_traffic.json; a recorded "
+                                   "constant, not measured in this run") if traffic else None,
                 "frac_of_sustained_peak": (achieved / sustained) if (achieved and sustained) else None,
                 "algorithmic_bytes_per_launch": scan_units / max(scan_n, 1) / NQ * DIM * 2,
                 "algorithmic_flops_per_launch": flops_per_launch,

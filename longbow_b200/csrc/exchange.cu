@@ -8,8 +8,9 @@
 //   push   : the local [nq,k] (distance, label) record is written straight into slot[parity][rank] of EVERY
 //            peer with 16-byte stores over NVLink (all-gather semantics: every rank ends up with every record);
 //   signal : one release-store of the batch's sequence number into flags[rank] on every peer;
-//   merge  : the (distance, label) merge kernel spins (acquire loads, bounded by a timeout) until the flags of
-//            all sources reach the sequence number, then merges the world records of the batch.
+//   wait   : one warp polls the flags of all sources (acquire loads, bounded by a timeout) until they reach the
+//            sequence number;
+//   merge  : the (distance, label) merge kernel merges the world records of the batch.
 // No rank ever waits before pushing, so there is no cycle; a slot of parity p is only overwritten by batch
 // s+2 after the pusher has merged batch s+1, which needed the receiver's signal s+1, which the receiver issues
 // (stream order) after its own merge of batch s -- the last reader of that slot.
@@ -53,6 +54,26 @@ __global__ void exchange_signal_kernel(PeerPtrs pp, int rank, int world, uint32_
     // before the flag for any observer that acquires it at system scope
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.flags[p] + rank), "r"(seq) : "memory");
+}
+
+// One warp waits for the batch's records: lane p polls source p's flag (acquire at system scope) until it reaches
+// the sequence number, at most ~10 s.  The MERGE kernel must not do this waiting itself: a thousand resident merge
+// CTAs spinning on a slow peer hold every SM's shared memory and lock the next batch's persistent scan out, and the
+// ranks then convoy (measured: 8 GPUs slower than 4).  A single warp costs nothing while it waits.
+__global__ void exchange_wait_kernel(const uint32_t* flags, uint32_t seq, int world, uint32_t* err) {
+    const int p = threadIdx.x;
+    if (p >= world) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
+        if ((int32_t)(v - seq) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) { atomicExch(err, 1u); break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
 }
 
 }  // namespace lb
@@ -206,9 +227,12 @@ int lb_exchange_all_gather_merge(lb_exchange* ex, int64_t nq, int k_in, int k, f
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return api_fail_cuda(e, "exchange push");
     }
-    cudaError_t e = launch_merge_topk_wait(ex->recv + parity_off, ex->slot_bytes, ex->recv + parity_off + loff,
-                                           ex->slot_bytes, ex->world, (int)nq, k_in, k, d_out_d, d_out_l,
-                                           ex->world > 1 ? ex->flags : nullptr, ex->seq, ex->rank, ex->err, st);
+    if (ex->world > 1) {
+        exchange_wait_kernel<<<1, 32, 0, st>>>(ex->flags, ex->seq, ex->world, ex->err);
+        count_launch();
+    }
+    cudaError_t e = launch_merge_topk_strided(ex->recv + parity_off, ex->slot_bytes, ex->recv + parity_off + loff,
+                                              ex->slot_bytes, ex->world, (int)nq, k_in, k, d_out_d, d_out_l, st);
     if (e != cudaSuccess) return api_fail_cuda(e, "exchange merge");
     return LB_OK;
 }

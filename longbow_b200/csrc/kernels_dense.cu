@@ -919,7 +919,9 @@ static cudaError_t launch_rescore_t(const RescoreArgs& a, cudaStream_t st) {
     const size_t row_bytes = (size_t)a.dim * sizeof(T);
     const bool coop = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.db) & 15) == 0) &&
                       !(a.metric == METRIC_COSINE && a.nrm == nullptr) && !g_rescore_legacy;
-    if (coop && !g_rescore_block) {
+    // few queries: the block-per-query kernel spreads one query's candidates over four warps (latency); many
+    // queries: one warp per query keeps every SM full of independent queries (throughput)
+    if (coop && !g_rescore_block && a.nq >= 256) {
         // warp-per-query kernel; lists that bitmaps will thin out get the half-size staging (more queries per SM)
         const bool thin = a.packed == nullptr && (a.allow != nullptr || a.tomb != nullptr);
         const int SRv = thin ? 48 : 96;
