@@ -356,6 +356,10 @@ int lb_set_option(const char* name, int value) {
         g_rescore_legacy = value != 0;
         return LB_OK;
     }
+    if (strcmp(name, "pq_ring") == 0) {
+        g_pq_ring = value != 0;
+        return LB_OK;
+    }
     if (strcmp(name, "pq_ahead") == 0) {
         g_pq_ahead = value < 1 ? 1 : (value > 64 ? 64 : value);
         return LB_OK;

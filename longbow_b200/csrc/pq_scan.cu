@@ -39,6 +39,8 @@
 
 namespace lb {
 
+bool g_pq_ring = false;  // lb_set_option("pq_ring"): single-query passes through the bulk-copy ring kernel.
+                         // Measured 0.267 ms against 0.227 ms for the register kernel at C3: kept selectable, off by default
 int g_pq_ahead = 2;  // lb_set_option("pq_ahead"): measured flat for 1..6 trips, worse at 12 (L2 thrash)
 constexpr int PQS_THREADS = 640;   // 20 warps, one CTA per SM, <= 102 registers: room for two tiles of codes per lane
 constexpr int PQS_WARPS = PQS_THREADS / 32;
@@ -593,6 +595,345 @@ adc_exact_kernel(const uint8_t* __restrict__ tiled, int M, int Mp, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Single-query coarse scan with the code tiles staged through a shared-memory RING fed by bulk copies
+// (cp.async.bulk + mbarrier), warp-specialised: one producer warp keeps up to NSLOT tiles (3 KB each) in flight,
+// sixteen consumer warps take them round-robin.  The register double buffer of adc_coarse_kernel keeps one tile per
+// warp in flight -- 60 KB per SM, which the loaded HBM latency turns into ~3.8 TB/s; the ring decouples the bytes
+// in flight (~80 KB per SM, no registers) from the look-up work.  To make room the table is stored ONCE
+// (adc_coarse_kernel stores every line twice): lines of 256 bytes hold two groups of 32 sub-quantisers side by side,
+// and the slot (lane + step) mod 32 costs one extra integer instruction per look-up (there is issue headroom).
+// Per tile the shared-memory pipe moves 96 look-up wavefronts + 24 (codes out of the ring) + 24 (the bulk copy's
+// write) = 144, against 135 cycles of HBM time per tile and SM: the pass is balanced at ~0.16 ms.
+// ---------------------------------------------------------------------------------------------
+constexpr int RING_CONSUMERS = 16;
+constexpr int RING_PRODUCERS = 4;  // producer warps (one issuing lane each)
+constexpr int RING_THREADS = (RING_CONSUMERS + RING_PRODUCERS) * 32;
+constexpr int RING_CT = RING_CONSUMERS * 32;  // consumer threads (named barrier 1)
+
+__device__ __forceinline__ uint32_t ring_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_csync() { asm volatile("bar.sync 1, %0;" ::"n"(RING_CT) : "memory"); }
+__device__ __forceinline__ void ring_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ring_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ring_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a lost arrival traps after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void ring_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 0; !ok; spins++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
+        if (!ok && (spins & 63u) == 63u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void ring_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// consumer-only bitonic sort (named barrier, RING_CT threads)
+__device__ __forceinline__ void ring_bitonic_sort(uint64_t* a, int n, int tid) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (n >> 1); t += RING_CT) {
+                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const uint64_t x = a[lo], y = a[hi];
+                if ((x > y) == up) { a[lo] = y; a[hi] = x; }
+            }
+            ring_csync();
+        }
+    }
+}
+
+// kc-th smallest (rounded up to a histogram bin edge) of the set entries of v[0, n), consumer threads only
+__device__ __forceinline__ uint32_t ring_kth_upper_bound(const uint32_t* __restrict__ v, int n, int kc, int* s_hist,
+                                                         uint32_t* s_lo, uint32_t* s_hi, int* s_c, int tid) {
+    constexpr int E = (4096 + RING_CT - 1) / RING_CT;
+    uint32_t mine[E];
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int i = tid + e * RING_CT;
+        mine[e] = (i < n) ? __ldcg(v + i) : 0xffffffffu;
+        if (mine[e] != 0xffffffffu) { lo = min(lo, mine[e]); hi = max(hi, mine[e]); cnt++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (tid < 256) s_hist[tid] = 0;
+    if ((tid & 31) == 0) { s_lo[tid >> 5] = lo; s_hi[tid >> 5] = hi; s_c[tid >> 5] = cnt; }
+    ring_csync();
+    lo = 0xffffffffu; hi = 0u; cnt = 0;
+#pragma unroll
+    for (int w = 0; w < RING_CONSUMERS; w++) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); cnt += s_c[w]; }
+    uint32_t result = 0xffffffffu;
+    if (cnt >= kc) {  // uniform
+        int shift = 0;
+        while (((hi - lo) >> shift) >= 256u) shift++;
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            if (mine[e] != 0xffffffffu) atomicAdd(&s_hist[(mine[e] - lo) >> shift], 1);
+        ring_csync();
+        if (tid == 0) {
+            int cum = 0, b = 0;
+            for (; b < 256; b++) { cum += s_hist[b]; if (cum >= kc) break; }
+            const uint64_t edge = (uint64_t)lo + (((uint64_t)b + 1) << shift) - 1;
+            s_hist[256] = (int)(uint32_t)min(edge, (uint64_t)hi);
+        }
+        ring_csync();
+        result = (uint32_t)s_hist[256];
+    }
+    ring_csync();
+    return result;
+}
+
+template <int G>
+__global__ void __launch_bounds__(RING_THREADS, 1)
+adc_coarse_ring_kernel(const PqCoarseArgs a, int nslot) {
+    constexpr int CH = 2 * G;
+    constexpr int NT = (G + 1) / 2;                 // 64 KB tables of two groups each
+    constexpr uint32_t TILE_BYTES = CH * 32 * 16;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* lut = smem_raw;                                                   // NT * 64 KB
+    unsigned char* ring = smem_raw + NT * PQS_GROUP_BYTES;                           // nslot * TILE_BYTES
+    uint64_t* cand = reinterpret_cast<uint64_t*>(ring + (size_t)nslot * TILE_BYTES);  // [cap]
+    uint64_t* bars = cand + a.cap;                                                   // full[nslot], empty[nslot]
+    __shared__ int s_cnt;
+    __shared__ uint32_t s_tau;
+    __shared__ int s_hist[258];
+    __shared__ uint32_t s_lo[RING_CONSUMERS], s_hi[RING_CONSUMERS];
+    __shared__ int s_c[RING_CONSUMERS];
+    __shared__ uint32_t s_pos, s_keep, s_w, s_gt;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = blockIdx.x, part = blockIdx.y;
+    const uint32_t bar0 = ring_smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (nslot + s); };
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.lutq + (size_t)q * NT * PQS_GROUP_BYTES);
+        uint4* dst = reinterpret_cast<uint4*>(lut);
+        for (int i = tid; i < NT * (PQS_GROUP_BYTES / 16); i += RING_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        s_cnt = 0;
+        s_tau = __ldcg(a.g_tau + q);
+        for (int s = 0; s < nslot; s++) { ring_mbar_init(full_bar(s), 1); ring_mbar_init(empty_bar(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the only full-block barrier: producer and consumers part ways here
+
+    const uint32_t n_tiles = (a.n_rows + 31) >> 5;
+    const uint32_t tile_begin = (uint32_t)part * a.tiles_per_part;
+    const uint32_t tile_end = min(n_tiles, tile_begin + a.tiles_per_part);
+    const uint32_t n_my = tile_end > tile_begin ? tile_end - tile_begin : 0;
+
+    if (warp >= RING_CONSUMERS) {
+        // ================================ producers ================================
+        // Four producer warps, one issuing lane each, take the tiles seq = p, p + 4, ...: a single thread cannot
+        // issue a 3 KB copy every 70 ns (measured: one issuing lane halves the pass rate), and lanes of ONE warp
+        // waiting on different barriers stall each other.  Two tiles that share a slot are a whole round apart and
+        // ordered by the slot's empty barrier, whichever warp issues them.
+        if (lane == 0) {
+            for (uint32_t seq = warp - RING_CONSUMERS; seq < n_my; seq += RING_PRODUCERS) {
+                const int slot = (int)(seq % (uint32_t)nslot);
+                const uint32_t round = seq / (uint32_t)nslot;
+                ring_mbar_wait(empty_bar(slot), (round & 1u) ^ 1u);
+                ring_mbar_expect_tx(full_bar(slot), TILE_BYTES);
+                ring_bulk_load(ring_smem_u32(ring + (size_t)slot * TILE_BYTES),
+                               a.tiles + (size_t)(tile_begin + seq) * (CH * 32), TILE_BYTES, full_bar(slot));
+            }
+        }
+        return;
+    }
+    // ================================ consumers ================================
+    const uint32_t iters = (n_my + RING_CONSUMERS - 1) / RING_CONSUMERS;
+    uint32_t lmin = 0xffffffffu;  // smallest LIVE key this lane has seen
+
+    auto housekeeping = [&](uint32_t it) {
+        const bool pow2 = ((it + 1) & it) == 0;
+        const bool chk = ((it + 1) & 7) == 0;
+        if (!pow2 && !chk) return;
+        ring_csync();
+        {
+            const int c = min(s_cnt, a.cap);
+            if (pow2 ? (c > a.kc) : (c > a.cap / 2)) {
+                const int n2 = next_pow2(c);
+                for (int t = c + tid; t < n2; t += RING_CT) cand[t] = kInvalid;
+                ring_csync();
+                ring_bitonic_sort(cand, n2, tid);
+                if (tid == 0) {
+                    s_cnt = min(c, a.kc);
+                    if (c >= a.kc) {
+                        const uint32_t lt = (uint32_t)(cand[a.kc - 1] >> 32);
+                        atomicMin(a.g_tau + q, lt);
+                        s_tau = min(s_tau, lt);
+                    }
+                }
+                ring_csync();
+            }
+        }
+        if (pow2) {
+            uint32_t m = lmin;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0 && m != 0xffffffffu) atomicMin(a.g_min + (size_t)q * a.nmin + part * RING_CONSUMERS + warp, m);
+            __threadfence();
+            ring_csync();
+            const uint32_t b = ring_kth_upper_bound(a.g_min + (size_t)q * a.nmin, a.nmin, a.kc, s_hist, s_lo, s_hi, s_c, tid);
+            if (tid == 0) s_tau = min(min(s_tau, b), __ldcg(a.g_tau + q));
+        }
+        ring_csync();
+    };
+
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; it++) {
+        const uint32_t seq = it * RING_CONSUMERS + warp;
+        if (seq < n_my) {
+            const int slot = (int)(seq % (uint32_t)nslot);
+            const uint32_t round = seq / (uint32_t)nslot;
+            ring_mbar_wait(full_bar(slot), round & 1u);
+            const uint4* tp = reinterpret_cast<const uint4*>(ring + (size_t)slot * TILE_BYTES) + lane;
+            uint4 cur[CH];
+#pragma unroll
+            for (int i = 0; i < CH; i++) cur[i] = tp[i * 32];
+            __syncwarp();
+            if (lane == 0) ring_mbar_arrive(empty_bar(slot));  // the tile is in registers: the slot may be refilled
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int t = c * 16 + wi * 4 + b;
+                        const uint32_t off0 = (uint32_t)((lane + t) & 31) << 2;   // slot (lane + t) mod 32 of the line
+                        const uint32_t off1 = off0 | 128u;                          // ... of the line's second group
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            const uint4 v = cur[g * 2 + c];
+                            const uint32_t w = (wi == 0) ? v.x : (wi == 1) ? v.y : (wi == 2) ? v.z : v.w;
+                            const uint32_t addr = prmt(w, (g & 1) ? off1 : off0, 0x7704u | ((uint32_t)b << 4));
+                            acc += *reinterpret_cast<const uint32_t*>(lut + addr + (g >> 1) * PQS_GROUP_BYTES);
+                        }
+                    }
+            const uint32_t tile = tile_begin + seq;
+            const uint32_t row = (tile << 5) + lane;
+            if (row < a.n_rows && (acc <= s_tau || acc < lmin)) {
+                bool ok = true;
+                if (a.tomb != nullptr && row < a.tomb_bits && bit_set(a.tomb, row)) ok = false;
+                if (ok && a.allow != nullptr && !bit_set(a.allow, row)) ok = false;
+                if (ok) {
+                    lmin = min(lmin, acc);
+                    if (acc <= s_tau) {
+                        const int pos = atomicAdd(&s_cnt, 1);
+                        if (pos < a.cap) cand[pos] = ((uint64_t)acc << 32) | row;
+                        else a.overflow[q] = 1u;
+                    }
+                }
+            }
+        }
+        housekeeping(it);
+    }
+    ring_csync();
+    // emit (as adc_coarse_kernel)
+    {
+        int c = min(s_cnt, a.cap);
+        if (c > a.kc) {
+            const int n2 = next_pow2(c);
+            for (int t = c + tid; t < n2; t += RING_CT) cand[t] = kInvalid;
+            ring_csync();
+            ring_bitonic_sort(cand, n2, tid);
+            c = a.kc;
+            if (tid == 0) atomicMin(a.g_tau + q, (uint32_t)(cand[a.kc - 1] >> 32));
+        }
+        if (tid == 0) { s_keep = 0; s_w = 0; s_gt = min(s_tau, __ldcg(a.g_tau + q)); }
+        ring_csync();
+        const uint32_t gt = s_gt;
+        uint32_t keep = 0;
+        for (int t = tid; t < c; t += RING_CT) keep += ((uint32_t)(cand[t] >> 32) <= gt) ? 1u : 0u;
+        if (keep) atomicAdd(&s_keep, keep);
+        ring_csync();
+        if (tid == 0) s_pos = s_keep ? atomicAdd(a.out_cnt + q, s_keep) : 0u;
+        ring_csync();
+        uint64_t* out = a.compact + (size_t)q * a.stride + s_pos;
+        for (int t = tid; t < c; t += RING_CT) {
+            const uint64_t e = cand[t];
+            if ((uint32_t)(e >> 32) <= gt) out[atomicAdd(&s_w, 1u)] = e;
+        }
+    }
+}
+
+// table layout of adc_coarse_ring_kernel: [table = group / 2][code][(group & 1) * 32 + slot] u32
+__global__ void __launch_bounds__(256)
+adc_quantise_paired_kernel(const float* __restrict__ luts, int M, int G, int nq, uint8_t* __restrict__ lutq,
+                           PqQParams* __restrict__ params) {
+    __shared__ float s_min[96];
+    __shared__ double s_rng[96];
+    __shared__ double s_scale;
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int j = warp; j < M; j += 8) {
+        float mn = INFINITY, mx = -INFINITY;
+        const float* t = luts + ((size_t)q * M + j) * 256;
+#pragma unroll
+        for (int c = 0; c < 8; c++) { const float v = __ldg(t + c * 32 + lane); mn = fminf(mn, v); mx = fmaxf(mx, v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) { s_min[j] = mn; s_rng[j] = (double)mx - (double)mn; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double base = 0, R = 0, top = 0;
+        for (int j = 0; j < M; j++) { base += (double)s_min[j]; R = fmax(R, s_rng[j]); top += (double)s_min[j] + s_rng[j]; }
+        const double smax = floor(4294960000.0 / (double)M);
+        const double scale = (R > 0 && isfinite(R)) ? smax / R : 0.0;
+        s_scale = scale;
+        if (blockIdx.y == 0) {
+            params[q].base = base;
+            params[q].inv_scale = scale > 0 ? 1.0 / scale : 0.0;
+            params[q].smax_sum = top;
+        }
+    }
+    __syncthreads();
+    const int NT = (G + 1) / 2;
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(lutq + (size_t)q * NT * PQS_GROUP_BYTES);
+    const int total = NT * 256 * 64;
+    const double scale = s_scale;
+    for (int e = blockIdx.y * 256 + tid; e < total; e += gridDim.y * 256) {
+        const int slot = e & 63, c = (e >> 6) & 255, T = e >> 14;
+        const int g = 2 * T + (slot >> 5);
+        const int j = g * 32 + (slot & 31);
+        uint32_t v = 0;
+        if (g < G && j < M) {
+            const double x = ((double)__ldg(luts + ((size_t)q * M + j) * 256 + c) - (double)s_min[j]) * scale;
+            v = (uint32_t)llrint(x);
+        }
+        o32[e] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 bool adc_coarse_eligible(int M, int kc, int nq_per_pass) {
@@ -629,6 +970,38 @@ cudaError_t launch_adc_coarse(const uint8_t* tiled, uint32_t n_rows, int M, cons
     if (nq <= 0) return cudaSuccess;
     const int G = (M + 31) / 32;
     const int qgroups = (nq + nq_per_pass - 1) / nq_per_pass;
+    if (nq_per_pass == 1 && g_pq_ring) {
+        // ring kernel: paired table layout, sixteen consumer warps
+        const int NT = (G + 1) / 2;
+        const dim3 qg(nq, nq >= 64 ? 4 : PQS_QSPLIT);
+        adc_quantise_paired_kernel<<<qg, 256, 0, st>>>(luts, M, G, nq, lutq, (PqQParams*)params);
+        count_launch();
+        cudaError_t e0 = cudaGetLastError();
+        if (e0 != cudaSuccess) return e0;
+        PqCoarseArgs a;
+        a.tiles = reinterpret_cast<const uint4*>(tiled); a.n_rows = n_rows; a.tiles_per_part = tiles_per_part;
+        a.lutq = lutq; a.tomb = tomb; a.tomb_bits = tomb_bits; a.allow = allow;
+        a.kc = kc; a.nq = nq; a.compact = compact; a.out_cnt = out_cnt; a.stride = stride; a.g_tau = g_tau;
+        a.g_min = g_min; a.nmin = parts * RING_CONSUMERS; a.overflow = overflow; a.ahead = 0;
+        a.cap = 2048;
+        const size_t tile_bytes = (size_t)G * 1024;
+        const size_t fixed = (size_t)NT * PQS_GROUP_BYTES + (size_t)a.cap * 8;
+        int nslot = (int)((232448 - 4096 - fixed) / (tile_bytes + 16));
+        if (nslot > 48) nslot = 48;
+        if (nslot < 4) return cudaErrorInvalidValue;
+        const size_t smem = fixed + (size_t)nslot * (tile_bytes + 16);
+        dim3 grid(nq, parts);
+#define LB_RING(G_)                                                                   \
+        {                                                                             \
+            auto kern = adc_coarse_ring_kernel<G_>;                                   \
+            LB_SMEM_OPTIN(kern);                                                      \
+            kern<<<grid, RING_THREADS, smem, st>>>(a, nslot);                         \
+        }
+        if (G == 1) LB_RING(1) else if (G == 2) LB_RING(2) else LB_RING(3)
+#undef LB_RING
+        count_launch();
+        return cudaGetLastError();
+    }
     const dim3 qgrid(qgroups, qgroups >= 64 ? 4 : PQS_QSPLIT);
     if (nq_per_pass == 1) adc_quantise_kernel<1><<<qgrid, 256, 0, st>>>(luts, M, G, nq, lutq, (PqQParams*)params);
     else adc_quantise_kernel<4><<<qgrid, 256, 0, st>>>(luts, M, G, nq, lutq, (PqQParams*)params);
@@ -666,6 +1039,6 @@ cudaError_t launch_adc_exact(const uint8_t* tiled, int M, const float* luts, con
 }
 
 size_t adc_params_bytes(int nq) { return (size_t)nq * sizeof(PqQParams); }
-int adc_min_slots(int parts) { return parts * PQS_WARPS; }  // one published minimum per warp of every CTA
+int adc_min_slots(int parts) { return parts * (PQS_WARPS > 16 ? PQS_WARPS : 16); }  // one published minimum per warp of every CTA
 
 }  // namespace lb

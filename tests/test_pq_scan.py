@@ -101,6 +101,27 @@ def test_coarse_scan_certification_repairs(oracle, pq_mode, mode):
     enc.close()
 
 
+def test_coarse_scan_ring_kernel(oracle, pq_mode):
+    """The warp-specialised bulk-copy ring variant of the single-query pass (off by default): same answers."""
+    from longbow_b200 import _lib, pq
+    rng = np.random.default_rng(77)
+    M, sub, n = 96, 8, 90001
+    cb, codes = _setup(rng, n, M, sub)
+    q = rng.standard_normal((3, M * sub)).astype(np.float32)
+    enc = pq.PQEncoder(M * sub, M, 256, cb)
+    enc.add_codes(codes)
+    pq_mode(2)
+    _lib.set_option("pq_ring", 1)
+    try:
+        gd, gl = enc.search(q, 100)
+    finally:
+        _lib.set_option("pq_ring", 0)
+    wd, wl = oracle.pq_search(cb, codes, None, q, 100, 0)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "ring kernel")
+    assert enc.last_uncertified() == 0
+    enc.close()
+
+
 def test_coarse_scan_small_and_empty(oracle, pq_mode):
     from longbow_b200 import pq
     rng = np.random.default_rng(9)

@@ -25,7 +25,7 @@ HBM = PEAKS.get("hbm_gbs", 6650.0)
 TF = PEAKS.get("bf16_tflops", 1590.0)
 dev = torch.device("cuda", 0)
 STEPS = int(os.environ.get("STEPS", "10"))
-for _opt in ("tc_pair", "dense_scan", "tc_boot_tiles", "pq_scan", "pq_ahead"):
+for _opt in ("tc_pair", "dense_scan", "tc_boot_tiles", "pq_scan", "pq_ahead", "pq_ring"):
     if os.environ.get(_opt.upper()):
         _lib.set_option(_opt, int(os.environ[_opt.upper()]))
 
