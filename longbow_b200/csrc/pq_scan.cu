@@ -362,39 +362,53 @@ adc_coarse_kernel(const PqCoarseArgs a) {
 #pragma unroll
     for (int q = 0; q < NQ; q++) lmin[q] = 0xffffffffu;
 
+    // The hot loop is issue-bound (ncu: ~49 % issue-active at the pass's plateau, every other pipe lower), so
+    // everything outside the 2.5 instructions per look-up is kept off it: ONE compare per row and query against an
+    // exclusive bound thr1 = max(tau + 1, lmin) held in a register (key < thr1  <=>  key <= tau || key < lmin);
+    // row index, range checks, bitmaps, the shared-memory threshold and the list append live in the rare path.
+    uint32_t thr1[NQ];
+    auto refresh_thr = [&]() {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const uint32_t t = s_tau[q];
+            thr1[q] = (q < nvalid) ? max(t == 0xffffffffu ? t : t + 1u, lmin[q]) : 0u;
+        }
+    };
+    refresh_thr();
+    auto rare = [&](uint32_t tile, const uint32_t (&key)[NQ]) {
+        const uint32_t row = (tile << 5) + lane;
+        if (tile >= tile_end || row >= a.n_rows) return;
+        bool ok = true;
+        if (a.tomb != nullptr && row < a.tomb_bits && bit_set(a.tomb, row)) ok = false;
+        if (ok && a.allow != nullptr && !bit_set(a.allow, row)) ok = false;
+        if (!ok) return;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            if (q >= nvalid || key[q] >= thr1[q]) continue;
+            lmin[q] = min(lmin[q], key[q]);
+            if (key[q] <= s_tau[q]) {
+                const int pos = atomicAdd(&s_cnt[q], 1);
+                if (pos < a.cap) cand[(size_t)q * a.cap + pos] = ((uint64_t)key[q] << 32) | row;
+                else a.overflow[qg * NQ + q] = 1u;
+            }
+        }
+        refresh_thr();
+    };
     auto consume = [&](const uint4 (&cur)[CH], uint32_t tile) {
         uint32_t key[NQ];
         adc_tile_keys<NQ, G>(cur, lut, lane, cb, key);
-        const uint32_t row = (tile << 5) + lane;
-        if (tile < tile_end && row < a.n_rows) {
-            bool any = false;
+        bool any = false;
 #pragma unroll
-            for (int q = 0; q < NQ; q++) any = any || (q < nvalid && (key[q] <= s_tau[q] || key[q] < lmin[q]));
-            if (any) {  // rare once the threshold is tight: only now are the bitmaps consulted
-                bool ok = true;
-                if (a.tomb != nullptr && row < a.tomb_bits && bit_set(a.tomb, row)) ok = false;
-                if (ok && a.allow != nullptr && !bit_set(a.allow, row)) ok = false;
-                if (ok) {
-#pragma unroll
-                    for (int q = 0; q < NQ; q++) {
-                        if (q >= nvalid) continue;
-                        lmin[q] = min(lmin[q], key[q]);
-                        if (key[q] <= s_tau[q]) {
-                            const int pos = atomicAdd(&s_cnt[q], 1);
-                            if (pos < a.cap) cand[(size_t)q * a.cap + pos] = ((uint64_t)key[q] << 32) | row;
-                            else a.overflow[qg * NQ + q] = 1u;
-                        }
-                    }
-                }
-            }
-        }
+        for (int q = 0; q < NQ; q++) any = any || (key[q] < thr1[q]);
+        if (any) rare(tile, key);
     };
+    // tiles past the end are clamped to the last one (their keys never pass the range check in the rare path): no
+    // predicates, no zero fill
+    const uint32_t tile_last = tile_end - 1;  // only used when iters > 0
     auto prefetch = [&](uint4 (&dst)[CH], uint32_t tile) {
+        const uint4* p = a.tiles + (size_t)min(tile, tile_last) * (CH * 32) + lane;
 #pragma unroll
-        for (int i = 0; i < CH; i++) {
-            dst[i] = make_uint4(0, 0, 0, 0);
-            if (tile < tile_end) dst[i] = __ldcs(a.tiles + ((size_t)tile * CH + i) * 32 + lane);
-        }
+        for (int i = 0; i < CH; i++) dst[i] = __ldcs(p + i * 32);
     };
     auto housekeeping = [&](uint32_t it) {
         // Block barriers only on a doubling schedule (after trips 1, 2, 4, 8, ...): list compaction and threshold
@@ -448,6 +462,7 @@ adc_coarse_kernel(const PqCoarseArgs a) {
             }
         }
         __syncthreads();
+        refresh_thr();
     };
 
     // two trips per loop iteration with ping-pong register buffers: the next tile's codes are in flight while the
@@ -457,16 +472,26 @@ adc_coarse_kernel(const PqCoarseArgs a) {
     // prefetch PQS_AHEAD trips ahead: one lane issues a bulk prefetch of the warp's future tile (no registers, no
     // shared memory), so the later LDG hits L2.
     auto l2_prefetch = [&](uint32_t tile) {
-        if (NQ == 1 && lane == 0 && tile < tile_end) {  // batched passes re-read the codes from L2 anyway
-            const void* p = a.tiles + (size_t)tile * CH * 32;
+        if (NQ == 1 && lane == 0) {  // batched passes re-read the codes from L2 anyway
+            const void* p = a.tiles + (size_t)min(tile, tile_last) * (CH * 32);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(CH * 32 * 16)) : "memory");
         }
     };
     const uint32_t PQS_AHEAD = (uint32_t)a.ahead;
     uint4 buf0[CH], buf1[CH];
-    for (uint32_t p = 1; p < PQS_AHEAD; p++) l2_prefetch(tile_begin + p * PQS_WARPS + warp);
-    prefetch(buf0, tile_begin + warp);
     uint32_t it = 0;
+    if (iters > 0) {
+        for (uint32_t p = 1; p < PQS_AHEAD; p++) l2_prefetch(tile_begin + p * PQS_WARPS + warp);
+        prefetch(buf0, tile_begin + warp);
+    }
+    // housekeeping after trips 0, 1, 3, 7 and then every 8th (one compare per trip on the hot path)
+    uint32_t next_hk = 0;
+    auto maybe_hk = [&](uint32_t t) {
+        if (t == next_hk) {
+            housekeeping(t);
+            next_hk = (t < 7) ? 2 * t + 1 : t + 8;
+        }
+    };
 #pragma unroll 1
     for (; it + 1 < iters; it += 2) {
         const uint32_t tile = tile_begin + it * PQS_WARPS + warp;
@@ -474,10 +499,10 @@ adc_coarse_kernel(const PqCoarseArgs a) {
         l2_prefetch(tile + (PQS_AHEAD + 1) * PQS_WARPS);
         prefetch(buf1, tile + PQS_WARPS);
         consume(buf0, tile);
-        housekeeping(it);
+        maybe_hk(it);
         prefetch(buf0, tile + 2 * PQS_WARPS);
         consume(buf1, tile + PQS_WARPS);
-        housekeeping(it + 1);
+        maybe_hk(it + 1);
     }
     if (it < iters) consume(buf0, tile_begin + it * PQS_WARPS + warp);
     __syncthreads();
