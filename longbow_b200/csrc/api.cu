@@ -356,6 +356,10 @@ int lb_set_option(const char* name, int value) {
         g_rescore_legacy = value != 0;
         return LB_OK;
     }
+    if (strcmp(name, "hnsw_coop") == 0) {
+        g_hnsw_coop = value != 0;
+        return LB_OK;
+    }
     if (strcmp(name, "pq_ring") == 0) {
         g_pq_ring = value != 0;
         return LB_OK;

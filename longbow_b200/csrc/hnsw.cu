@@ -33,8 +33,10 @@ int api_index_view(const lb_index* idx, IndexView* out);  // api.cu
 int api_rerank_device(lb_index* idx, const void* d_q, int64_t nq, const uint32_t* d_ids, int c, int k,
                       const uint64_t* d_allow, float* d_dist, int64_t* d_lab, cudaStream_t st);
 
+bool g_hnsw_coop = true;  // lb_set_option("hnsw_coop")
 constexpr int HN_WARPS = 4;            // queries per CTA
 constexpr uint32_t HN_EMPTY = 0xffffffffu;
+constexpr int HN_SR = 48;              // staging row-buffers per warp (trips of 16 rows, 3 chunks in flight)
 
 struct HnswArgs {
     const void* db;
@@ -54,6 +56,7 @@ struct HnswArgs {
     uint32_t* out_visited;      // [nq] or null
     uint32_t* fail_count;       // [1]: queries that hit a table / heap limit (results invalid for those)
     uint32_t* fail_flags;       // [nq] or null
+    int coop;                   // rows are 16-byte aligned multiples of 16 bytes: cooperative gather
 };
 
 // ---- binary heaps of packed u64 in shared memory, lane 0 only
@@ -96,8 +99,10 @@ hnsw_search_layer_kernel(const HnswArgs a) {
     const int q = blockIdx.x * HN_WARPS + warp;
     // per-warp regions: query (fp32) | result heap [ef + 1] | candidate heap [cand_cap]
     const size_t q_bytes = ((size_t)a.dim * 4 + 15) & ~(size_t)15;
-    const size_t per_warp = q_bytes + (size_t)(a.ef + 1 + a.cand_cap) * 8;
+    const size_t heap_bytes = (((size_t)(a.ef + 1 + a.cand_cap) * 8) + 15) & ~(size_t)15;  // cp.async needs 16-byte slots
+    const size_t per_warp = q_bytes + heap_bytes + (a.coop ? (size_t)HN_SR * RC_PITCH : 0);
     unsigned char* base = smem_raw + (size_t)warp * per_warp;
+    unsigned char* stage = base + q_bytes + heap_bytes;  // [HN_SR][RC_PITCH] when coop
     float* qf = reinterpret_cast<float*>(base);
     uint64_t* res = reinterpret_cast<uint64_t*>(base + q_bytes);
     uint64_t* cand = res + (a.ef + 1);
@@ -171,17 +176,58 @@ hnsw_search_layer_kernel(const HnswArgs a) {
             int fresh = 0;
             if (nb < a.n_rows && !dup) fresh = visit(nb);
             if (fresh < 0) { failed = true; fresh = 0; }
-            float d = 0.f;
-            if (fresh) d = dist_of(nb);
             const unsigned fm = __ballot_sync(0xffffffffu, fresh != 0);
-            n_vis += __popc(fm);
+            const int nfresh = __popc(fm);
+            n_vis += nfresh;
+            // Distances of the new nodes.  Aligned rows: the new ids are compacted to lanes 0..nfresh-1 (list order
+            // kept) and the warp gathers their rows together through shared memory -- 128-byte chunks copied with
+            // cp.async, several chunks in flight, lane i accumulating node i in the reference order (common.cuh
+            // rc_gather, the re-rank's gather): 3-5 memory round trips per expansion instead of the 12 a lane needs
+            // to stream a 1.5 KB row with eight 16-byte loads in flight.  Other rows: one lane per node.
+            float d = 0.f;
+            uint32_t cnb = nb;  // node held by this lane in the order the replay walks
+            if (a.coop) {
+                const unsigned src = __fns(fm, 0, lane + 1);      // lane of the (lane + 1)-th new node
+                cnb = __shfl_sync(0xffffffffu, nb, src < 32 ? src : 0);
+                const size_t row_bytes = (size_t)a.dim * sizeof(T);
+                const int n_chunks = (int)((row_bytes + RC_CHUNK - 1) / RC_CHUNK);
+                for (int base_i = 0; base_i < nfresh; base_i += 16) {   // trips of 16 rows (HN_SR = 48 row buffers)
+                    const int mine_i = lane - base_i;                   // row slot of this lane in the trip
+                    const bool okc = lane >= base_i && lane < nfresh && mine_i < 16;
+                    const unsigned char* src_row[8];
+                    bool src_ok[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int r = 4 * i + (lane >> 3);              // trip row copied by copy instruction i
+                        const int sl = base_i + r;                      // lane that owns it
+                        const uint32_t rid = __shfl_sync(0xffffffffu, cnb, sl < 32 ? sl : 0);
+                        src_ok[i] = r < 16 && sl < nfresh;
+                        src_row[i] = reinterpret_cast<const unsigned char*>(db) + (size_t)rid * row_bytes + (lane & 7) * 16;
+                    }
+                    // lane (base_i + j) must accumulate trip row j: rc_gather reads row `lane` of the staging space,
+                    // so the trip is issued from a rotated view: lanes base_i.. act as rows 0..
+                    const int rows_here = min(16, nfresh - base_i);
+                    ExactAcc<METRIC> acc;
+                    acc.init();
+                    const int vlane = okc ? mine_i : 31;                // staging row this lane reads (31: unused)
+                    if (rows_here <= 8) rc_gather<T, METRIC, HN_SR / 8, 8>(stage, src_row, src_ok, row_bytes, n_chunks, a.dim, qf, okc, lane, acc, vlane);
+                    else rc_gather<T, METRIC, HN_SR / 16, 16>(stage, src_row, src_ok, row_bytes, n_chunks, a.dim, qf, okc, lane, acc, vlane);
+                    if (okc) {
+                        float dd = acc.finish();
+                        if (METRIC == METRIC_DOT) dd = -dd;
+                        d = __fadd_rn(dd, 0.f);
+                    }
+                }
+            } else if (fresh) {
+                d = dist_of(nb);
+            }
             // replay in list order through the acceptance test (arrow_hnsw.go:1349-1370)
-            unsigned m = fm;
+            unsigned m = a.coop ? (nfresh >= 32 ? 0xffffffffu : ((1u << nfresh) - 1u)) : fm;
             while (m) {
                 const int l = __ffs(m) - 1;
                 m &= m - 1;
                 const float dl = __shfl_sync(0xffffffffu, d, l);
-                const uint32_t nl = __shfl_sync(0xffffffffu, nb, l);
+                const uint32_t nl = __shfl_sync(0xffffffffu, cnb, l);
                 int accept = 0;
                 if (lane == 0) accept = (nr < a.ef || dl < key_of(res[0])) ? 1 : 0;
                 accept = __shfl_sync(0xffffffffu, accept, 0);
@@ -254,7 +300,8 @@ hnsw_search_layer_kernel(const HnswArgs a) {
 template <typename T>
 static cudaError_t launch_hnsw_t(const HnswArgs& a, int metric, cudaStream_t st) {
     const size_t q_bytes = ((size_t)a.dim * 4 + 15) & ~(size_t)15;
-    const size_t smem = (size_t)HN_WARPS * (q_bytes + (size_t)(a.ef + 1 + a.cand_cap) * 8);
+    const size_t heap_bytes = (((size_t)(a.ef + 1 + a.cand_cap) * 8) + 15) & ~(size_t)15;
+    const size_t smem = (size_t)HN_WARPS * (q_bytes + heap_bytes + (a.coop ? (size_t)HN_SR * RC_PITCH : 0));
     const int grid = (a.nq + HN_WARPS - 1) / HN_WARPS;
 #define LB_HN(M)                                                              \
     {                                                                         \
@@ -369,6 +416,10 @@ static int graph_walk(lb_graph* g, const void* d_q, int64_t nq, const uint32_t* 
     ht <<= ht_scale;
     a.ht_mask = ht - 1;
     a.out_ids = d_ids; a.out_d = d_dist; a.out_visited = d_visited; a.fail_count = d_fail_count; a.fail_flags = nullptr;
+    {
+        const size_t rb = (size_t)v.dim * (v.dtype == DT_F32 ? 4 : v.dtype == DT_F16 ? 2 : 1);
+        a.coop = (rb % 16 == 0) && ((reinterpret_cast<uintptr_t>(v.rows) & 15) == 0) && g_hnsw_coop ? 1 : 0;
+    }
     // visited tables are allocated per chunk of queries so that scratch stays bounded (<= ~1 GB)
     const int64_t chunk_max = std::max<int64_t>(64, (int64_t)(1ull << 30) / ((int64_t)ht * 4));
     for (int64_t qo = 0; qo < nq; qo += chunk_max) {

@@ -37,6 +37,7 @@ extern bool g_rescore_legacy;
 extern bool g_rescore_block;
 extern int g_pq_ahead;
 extern bool g_pq_ring;
+extern bool g_hnsw_coop;
 extern bool g_tc_pair;
 void count_launch();  // api.cu: process-wide launch counter (bench evidence)
 

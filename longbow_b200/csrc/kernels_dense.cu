@@ -604,65 +604,7 @@ __global__ void rescore_kernel(const T* __restrict__ db, uint32_t n_rows, int di
 // reference-order accumulation of candidate l out of shared memory (row pitch 144 B: conflict free).
 // Arithmetic and order are identical to exact_pair(), so results are bit-identical to the kernel above.
 // ---------------------------------------------------------------------------------------------
-constexpr int RC_WARPS = 4;
-constexpr int RC_CHUNK = 128;            // bytes of a row per stage
-constexpr int RC_PITCH = RC_CHUNK + 16;  // shared-memory row pitch
-constexpr int RC_NBUF = 3;
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// One trip of the cooperative gather: the warp's (up to ROWS) candidate rows are copied global -> shared in 128-byte
-// chunks with NBUF chunk buffers in flight, and lane l accumulates candidate l's chunk out of shared memory in the
-// reference order.  NBUF * ROWS == 96 (the staging space of one warp).
-template <typename T, int ACC, int NBUF, int ROWS>
-__device__ __forceinline__ void rc_gather(unsigned char* stage, const unsigned char* const (&src_row)[8],
-                                          const bool (&src_ok)[8], size_t row_bytes, int n_chunks, int dim,
-                                          const float* qf, bool ok, int lane, ExactAcc<ACC>& acc) {
-    constexpr int V = Elem<T>::kVec;
-    constexpr int PIECES = RC_CHUNK / 16;
-    auto issue = [&](int ch) {
-        unsigned char* dstb = stage + (size_t)(ch % NBUF) * ROWS * RC_PITCH + (lane & 7) * 16;
-        const size_t off = (size_t)ch * RC_CHUNK;
-        const bool in_row = off + (size_t)(lane & 7) * 16 < row_bytes;  // tail chunk: pieces past the row end
-#pragma unroll
-        for (int i = 0; i < ROWS / 4; i++) {
-            if (src_ok[i] && in_row) cp_async16(dstb + (size_t)(4 * i + (lane >> 3)) * RC_PITCH, src_row[i] + off);
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int p = 0; p < NBUF - 1; p++) {
-        if (p < n_chunks) issue(p); else cp_async_commit();
-    }
-    for (int ch = 0; ch < n_chunks; ch++) {
-        if (ch + NBUF - 1 < n_chunks) issue(ch + NBUF - 1); else cp_async_commit();
-        cp_async_wait<NBUF - 1>();
-        __syncwarp();
-        if (ok) {
-            const uint4* rowp = reinterpret_cast<const uint4*>(stage + (size_t)(ch % NBUF) * ROWS * RC_PITCH +
-                                                               (size_t)lane * RC_PITCH);
-            const int e0 = ch * (RC_CHUNK / (int)sizeof(T));
-#pragma unroll
-            for (int p = 0; p < PIECES; p++) {
-                const int i0 = e0 + p * V;
-                if (i0 < dim) {  // dim % V == 0 on this path: a piece is inside the row entirely or not at all
-                    float x[V];
-                    unpack16<T>(rowp[p], x);
-#pragma unroll
-                    for (int e = 0; e < V; e++) acc.add(e & 3, qf[i0 + e], x[e]);
-                }
-            }
-        }
-        __syncwarp();
-    }
-}
+// (RC_* constants, cp.async helpers and rc_gather live in common.cuh: the graph walk uses the same gather)
 
 template <typename T, int METRIC>
 __global__ void __launch_bounds__(RC_WARPS * 32)
