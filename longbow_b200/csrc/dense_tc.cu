@@ -110,8 +110,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  No cluster-scope release: the barriers signalled this way only
+// order tensor-memory reads against the next MMA (tcgen05.fence::before_thread_sync does that), never generic-proxy
+// data.  The .release.cluster form compiles to ERRBAR + CGAERRBAR, which waits for every outstanding global store
+// and RED of the warp (the candidate appends) -- round 2's ncu source view had 20 % of the epilogue's stall samples
+// on that fence, on the critical path of handing the accumulator stage back to the MMA issuer.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; the transaction bytes are credited to `bar` (a shared::cluster
 // address, here always the leader CTA's barrier)
@@ -178,6 +183,28 @@ __device__ __forceinline__ void tmem_wait_ld4(uint32_t& a, uint32_t& b, uint32_t
     asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d)::"memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld1(uint32_t& a) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a)::"memory");
+}
+// v[j] for a run-time j: registers cannot be indexed, a select tree can (16 + 8 + 4 + 2 + 1 SEL)
+__device__ __forceinline__ uint32_t sel32(const uint32_t (&v)[32], int j) {
+    uint32_t t[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) t[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = (j & 2) ? t[2 * i + 1] : t[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) t[i] = (j & 4) ? t[2 * i + 1] : t[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) t[i] = (j & 8) ? t[2 * i + 1] : t[2 * i];
+    return (j & 16) ? t[1] : t[0];
+}
+// 3-input maximum (FMNMX3 on sm_100); a NaN input is ignored like fmaxf does
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
 // Same wait, but naming the 32 destination registers of the load it completes as read-write operands:
 // no use of v[] can be scheduled above the wait even when a second tcgen05.ld is already in flight.
 __device__ __forceinline__ void tmem_wait_ld32(uint32_t* v) {
@@ -357,6 +384,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     constexpr int STAGE_BYTES = PARTS * (TC_A_BYTES + B_BYTES);
     constexpr int STAGES = (TC_STAGES * TC_STAGE_BYTES) / STAGE_BYTES;   // 4 / 6 (pair); fp32: 2 / 3
     constexpr int B_OFF = PARTS * TC_A_BYTES;         // stage layout: A_hi [A_lo] B_hi [B_lo]
+    constexpr int NBAR = STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -366,10 +394,10 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t bar_base = base + bar_off;
     // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (2 * STAGES + 4));
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NBAR + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * NBAR + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NBAR + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (2 * NBAR + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -379,8 +407,9 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
     if (threadIdx.x == 0) {
         // full: one arrive.expect_tx (the leader's producer); tmem_empty: 8 epilogue warps of every CTA of the pair
-        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < NBAR; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8 * CG); }
+
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -521,6 +550,9 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         int as = 0;
         uint32_t aphase = 0;
         int abuf = 0;
+        // the leader issues the MMAs: both CTAs of a pair hand their accumulator stages back to ITS barriers
+        const uint32_t tempty_remote[2] = {CG == 2 ? map_to_cta(tempty_bar(0), 0) : tempty_bar(0),
+                                           CG == 2 ? map_to_cta(tempty_bar(1), 0) : tempty_bar(1)};
         int rt = a.tile_begin + g;
         uint32_t tile_no = 0;
         // Row auxiliaries (|x|^2 or 1/|x|) of a tile are staged in shared memory one tile ahead: the
@@ -554,117 +586,138 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             tc_fence_after();
 
             // one 32-column chunk of this thread's query: keys, filter, rare appends
+            // one 32-column chunk of this thread's query.  Survivors are sparse (a fraction of a percent once the
+            // threshold is tight), so the common path only answers "does any of my 32 keys pass?": the keys are
+            // folded, negated, into four running maxima of eight columns each (one multiply / FMA and half a
+            // 3-input max per key) and the maxima are tested against -tau.  Only column groups in which SOME lane
+            // saw a survivor are looked at key by key.
             auto process = [&](uint32_t (&v)[32], const int c0) {
-                float ax[32];
-                if constexpr (METRIC != METRIC_DOT) {
-                    const float4* ap = reinterpret_cast<const float4*>(axs + c0);  // warp-uniform: broadcast
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 t = ap[j];
-                        ax[4 * j] = t.x; ax[4 * j + 1] = t.y; ax[4 * j + 2] = t.z; ax[4 * j + 3] = t.w;
-                    }
-                }
-                uint32_t hits = 0;
-                if constexpr (KIND == KIND_I8 && METRIC == METRIC_DOT) {
-                    // integer dot, key = -dot: filter in the integer domain (key < tau <=> dot > floor(-tau)),
-                    // no int->float conversion per key (the conversion pipe is a quarter-rate unit)
-                    const int ti = __float2int_rd(-tau);  // saturates: tau = +inf admits every row, -inf none
-                    // First the chunk maximum (3-input integer max, four independent chains: ~0.5 instruction
-                    // per key); the per-key mask is built only when some lane of the warp has a survivor.
-                    // (v[0..3] seed the chains; trips j = 4, 12, 20 add eight values each, j = 28 the last four)
-                    int m0 = (int32_t)v[0], m1 = (int32_t)v[1], m2 = (int32_t)v[2], m3 = (int32_t)v[3];
-#pragma unroll
-                    for (int j = 4; j < 32; j += 8) {
-                        m0 = __vimax3_s32(m0, (int32_t)v[j], (int32_t)v[j + 1]);
-                        m1 = __vimax3_s32(m1, (int32_t)v[j + 2], (int32_t)v[j + 3]);
-                        if (j + 4 < 32) {
-                            m2 = __vimax3_s32(m2, (int32_t)v[j + 4], (int32_t)v[j + 5]);
-                            m3 = __vimax3_s32(m3, (int32_t)v[j + 6], (int32_t)v[j + 7]);
-                        }
-                    }
-                    const int mx = max(__vimax3_s32(m0, m1, m2), m3);
-                    if (__any_sync(0xffffffffu, mx > ti) || dump) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if ((int32_t)v[j] > ti) hits |= 1u << j;
-                    }
-                    if (dump) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] = __float_as_uint(-(float)(int32_t)v[j]);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        float dot;
-                        if constexpr (KIND == KIND_I8) dot = (float)(int32_t)v[j];
-                        else dot = __uint_as_float(v[j]);
-                        float key;
-                        if constexpr (METRIC == METRIC_L2) key = fmaf(-2.f, dot, ax[j]);
-                        else if constexpr (METRIC == METRIC_COSINE) key = -dot * ax[j];
-                        else key = -dot;
-                        v[j] = __float_as_uint(key);
-                        if (key < tau) hits |= 1u << j;
-                    }
-                }
+                // val = -key, bit for bit: cosine -(-dot * ax) = dot * ax, L2 -(ax - 2 dot) = fma(2, dot, -ax)
+                auto val_of = [&](uint32_t raw, float axj) {
+                    float dot;
+                    if constexpr (KIND == KIND_I8) dot = (float)(int32_t)raw;
+                    else dot = __uint_as_float(raw);
+                    if constexpr (METRIC == METRIC_L2) return fmaf(2.f, dot, -axj);
+                    else if constexpr (METRIC == METRIC_COSINE) return dot * axj;
+                    else return dot;
+                };
                 if (dump) {
                     // bootstrap sample: write the keys of this chunk (row-major per query)
                     if (q < a.nq) {
                         float4* dst = reinterpret_cast<float4*>(a.keys_out + (size_t)q * a.keys_ld +
                                                                 (row0 - (uint32_t)a.tile_begin * TC_N) + c0);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            dst[j >> 2] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 ax4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if constexpr (METRIC != METRIC_DOT) ax4 = *reinterpret_cast<const float4*>(axs + c0 + j);
+                            dst[j >> 2] = make_float4(-val_of(v[j], ax4.x), -val_of(v[j + 1], ax4.y),
+                                                      -val_of(v[j + 2], ax4.z), -val_of(v[j + 3], ax4.w));
+                        }
                     }
                     return;
                 }
-                // Survivors are sparse (a fraction of a percent once the threshold is tight) but a warp
-                // filters 1024 keys per chunk, so most chunks have a few.  Walk the columns that hold a
-                // survivor of ANY lane, four per trip (warp-uniform loop, compact code): re-read those
-                // accumulator columns from TMEM with the loads in flight together, and let the lanes that
-                // own a survivor append it.  Columns ascend, so every list stays in increasing row order.
-                uint32_t cols = __reduce_or_sync(0xffffffffu, hits);
-                if (a.debug & 32) cols = 0;  // probe: filter only, survivors ignored
-                while (cols) {
-                    int jj[4];
-                    uint32_t dv[4];
+                constexpr bool INT_KEYS = (KIND == KIND_I8 && METRIC == METRIC_DOT);
+                // integer dot, key = -dot: filter in the integer domain (key < tau <=> dot > floor(-tau)), no
+                // int->float conversion per key (the conversion pipe is a quarter-rate unit)
+                const int ti = __float2int_rd(-tau);  // saturates: tau = +inf admits every row, -inf none
+                const float thr = -tau;
+                uint32_t gm = 0;  // bit c: some column of [8c, 8c + 8) passes for this lane
+                if constexpr (INT_KEYS) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        jj[u] = cols ? (__ffs(cols) - 1) : -1;
-                        cols &= cols - 1;  // 0 stays 0
-                        dv[u] = tmem_ld1(taddr + c0 + (jj[u] < 0 ? 0 : jj[u]));
+                    for (int c = 0; c < 4; c++) {
+                        int m = __vimax3_s32((int32_t)v[8 * c], (int32_t)v[8 * c + 1], (int32_t)v[8 * c + 2]);
+                        m = __vimax3_s32(m, (int32_t)v[8 * c + 3], (int32_t)v[8 * c + 4]);
+                        m = __vimax3_s32(m, (int32_t)v[8 * c + 5], (int32_t)v[8 * c + 6]);
+                        m = max(m, (int32_t)v[8 * c + 7]);
+                        gm |= (m > ti ? 1u : 0u) << c;
                     }
-                    tmem_wait_ld4(dv[0], dv[1], dv[2], dv[3]);
+                } else {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (jj[u] >= 0 && (hits & (1u << jj[u]))) {
-                            float dot;
-                            if constexpr (KIND == KIND_I8) dot = (float)(int32_t)dv[u];
-                            else dot = __uint_as_float(dv[u]);
-                            float key;
-                            if constexpr (METRIC == METRIC_L2) key = fmaf(-2.f, dot, axs[c0 + jj[u]]);
-                            else if constexpr (METRIC == METRIC_COSINE) key = -dot * axs[c0 + jj[u]];
-                            else key = -dot;
-                            const uint32_t row = row0 + c0 + jj[u];
-                            bool ok = row < n_rows;
-                            if (filt && ok) {
-                                if (tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) ok = false;
-                                if (ok && allow != nullptr && !bit_set(allow, row)) ok = false;
+                    for (int c = 0; c < 4; c++) {
+                        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                        if constexpr (METRIC != METRIC_DOT) {  // warp-uniform address: broadcast
+                            a0 = *reinterpret_cast<const float4*>(axs + c0 + 8 * c);
+                            a1 = *reinterpret_cast<const float4*>(axs + c0 + 8 * c + 4);
+                        }
+                        float m = fmax3(val_of(v[8 * c], a0.x), val_of(v[8 * c + 1], a0.y), val_of(v[8 * c + 2], a0.z));
+                        m = fmax3(m, val_of(v[8 * c + 3], a0.w), val_of(v[8 * c + 4], a1.x));
+                        m = fmax3(m, val_of(v[8 * c + 5], a1.y), val_of(v[8 * c + 6], a1.z));
+                        m = fmaxf(m, val_of(v[8 * c + 7], a1.w));
+                        gm |= (m > thr ? 1u : 0u) << c;   // NaN never passes (max ignores it, the compare is false)
+                    }
+                }
+                uint32_t groups = __reduce_or_sync(0xffffffffu, gm);
+                if (a.debug & 32) groups = 0;  // probe: filter only, survivors ignored
+                if (groups == 0) return;
+                // per-key mask, only for the flagged groups (warp-uniform branches, static register indices)
+                uint32_t hits = 0;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (groups & (1u << c)) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int j = 8 * c + u;
+                            bool pass;
+                            if constexpr (INT_KEYS) pass = (int32_t)v[j] > ti;
+                            else {
+                                float axj = 0.f;
+                                if constexpr (METRIC != METRIC_DOT) axj = axs[c0 + j];
+                                pass = val_of(v[j], axj) > thr;
                             }
-                            if (ok) {
-                                mybuf[cnt++] = pack_key(key, row);
-                                if (shared_tau) {
-                                    int b = 0;
+                            if (pass) hits |= 1u << j;
+                        }
+                    }
+                }
+                // Every lane walks its OWN survivors, ascending columns (so every list stays in increasing row order);
+                // the loop runs while some lane has one left, i.e. max-over-lanes survivors per chunk: one trip in
+                // the steady state, two or three right after the bootstrap when the threshold is still loose.  The
+                // key of a run-time column comes out of the registers through a five-level select tree (31 SEL).
+                // (Rounds 1-2 walked the columns holding a survivor of ANY lane and re-read each from TMEM: one
+                // serial tcgen05.ld round trip per column, ~60 trips per tile and warp during the first tile steps --
+                // that, not the filter, was what stalled the MMA issuer: filter-only ran at the no-epilogue time.)
+#pragma unroll 1
+                while (__any_sync(0xffffffffu, hits != 0)) {
+                    const bool mine = hits != 0;
+                    const int j = mine ? (__ffs(hits) - 1) : 0;
+                    hits &= hits - 1;  // 0 stays 0
+                    const uint32_t raw = sel32(v, j);
+                    if (mine) {
+                        float axj = 0.f;
+                        if constexpr (METRIC != METRIC_DOT) axj = axs[c0 + j];
+                        const float key = -val_of(raw, axj);
+                        const uint32_t row = row0 + c0 + j;
+                        bool ok = row < n_rows;
+                        if (filt && ok) {
+                            if (tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) ok = false;
+                            if (ok && allow != nullptr && !bit_set(allow, row)) ok = false;
+                        }
+                        if (ok) {
+                            mybuf[cnt++] = pack_key(key, row);
+                            if (shared_tau) {
+                                int b = 0;
 #pragma unroll
-                                    for (int i = 0; i < LB_NEDGE; i++) b += (ed[i] <= key) ? 1 : 0;
-                                    if (b < LB_NEDGE) atomicAdd(gcnt + b, 1u);
-                                }
+                                for (int i = 0; i < LB_NEDGE; i++) b += (ed[i] <= key) ? 1 : 0;
+                                if (b < LB_NEDGE) atomicAdd(gcnt + b, 1u);
                             }
                         }
                     }
                 }
             };
 
+            // hand the accumulator stage back to the MMA issuer: called once this warp's last TMEM read has landed
+            // (the survivor path works from registers, so the rest of the drain needs no tensor memory)
+            auto release = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 2) {
+                        if (a.debug & 128)  // probe: the round-1 form (cluster-scope release)
+                            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+                                         ::"r"(as ? tempty_remote[1] : tempty_remote[0]) : "memory");
+                        else mbar_arrive_cluster(as ? tempty_remote[1] : tempty_remote[0]);
+                    } else mbar_arrive(tempty_bar(as));
+                }
+            };
             if (!(a.debug & 1)) {
                 // TMEM -> registers, double buffered: the load of chunk c+1 is in flight while chunk c is filtered
                 uint32_t va[32], vb[32];
@@ -676,15 +729,11 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     process(va, c0);
                     tmem_wait_ld32(vb);
                     if (c0 + 64 < HALF) tmem_ld32(taddr + c0 + 64, va);
+                    else release();
                     process(vb, c0 + 32);
                 }
-            }
-            // release the accumulator stage (the survivor path re-reads TMEM, so only now)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(tempty_bar(as), 0));  // the leader issues the MMAs
-                else mbar_arrive(tempty_bar(as));
+            } else {
+                release();
             }
             if (++as == 2) { as = 0; aphase ^= 1u; }
 
@@ -1032,7 +1081,7 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     {                                                                                                          \
         auto kern = dense_scan_tc<KIND_, METRIC_, CAP_, CG_>;                                                  \
         LB_SMEM_OPTIN(kern);                                                                                   \
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mdb, mqlo, mdblo, a);                                                        \
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mdb, mqlo, mdblo, a);                               \
         if (e != cudaSuccess) return e;                                                                        \
     }
 #define LB_TC1(KIND_, METRIC_, CAP_)                                                                           \
