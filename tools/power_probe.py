@@ -8,11 +8,19 @@ import pynvml as nv
 from longbow_b200 import _lib, gpu
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(1)
-N, D, NQ, K = 1_000_000, 768, 1024, 100
 SECS = float(os.environ.get("SECS", "2.5"))
-db = torch.randn((N, D), generator=g, device=dev); db = (db / db.norm(dim=1, keepdim=True)).half()
-qs = torch.randn((NQ, D), generator=g, device=dev); qs = (qs / qs.norm(dim=1, keepdim=True)).half()
-idx = gpu.DenseIndex(D, np.float16, _lib.METRIC_COSINE); idx.reserve(N); idx.add_device(db)
+WORK = os.environ.get("WORK", "c2")
+if WORK == "c2":
+    N, D, NQ, K = 1_000_000, 768, 1024, 100
+    db = torch.randn((N, D), generator=g, device=dev); db = (db / db.norm(dim=1, keepdim=True)).half()
+    qs = torch.randn((NQ, D), generator=g, device=dev); qs = (qs / qs.norm(dim=1, keepdim=True)).half()
+    idx = gpu.DenseIndex(D, np.float16, _lib.METRIC_COSINE)
+else:  # c4: one rank's shard of the int8 dot-product config
+    N, D, NQ, K = 12_500_000, 128, 1024, 10
+    db = torch.randint(-128, 128, (N, D), generator=g, device=dev, dtype=torch.int8)
+    qs = torch.randint(-128, 128, (NQ, D), generator=g, device=dev, dtype=torch.int8)
+    idx = gpu.DenseIndex(D, np.int8, _lib.METRIC_DOT)
+idx.reserve(N); idx.add_device(db)
 od = torch.empty((NQ, K), dtype=torch.float32, device=dev); ol = torch.empty((NQ, K), dtype=torch.int64, device=dev)
 nv.nvmlInit(); h = nv.nvmlDeviceGetHandleByIndex(0)
 class S(threading.Thread):
