@@ -368,7 +368,9 @@ __device__ __forceinline__ float select_compact(const uint64_t* buf, uint64_t* d
 // the operand reads from 12 KiB to 8 KiB per instruction -- the CG = 1 kernel is bound by exactly that
 // shared-memory bandwidth.  The leader CTA (cluster rank 0) issues every MMA; accumulators
 // land in each CTA's own TMEM, so the epilogue is identical.
-template <int KIND, int METRIC, int CAP, int CG>
+// DUMP: the bootstrap-sample launch (raw keys written to keys_out, no selection) -- a template parameter so that
+// the selecting kernels carry no per-chunk test for it.
+template <int KIND, int METRIC, int CAP, int CG, bool DUMP = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
               const __grid_constant__ CUtensorMap map_qlo, const __grid_constant__ CUtensorMap map_dblo, const TcArgs a) {
@@ -546,7 +548,13 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const uint32_t* __restrict__ tomb = a.tomb;
         const uint32_t* __restrict__ allow = a.allow;
         const bool filt = (tomb != nullptr) || (allow != nullptr);
-        const bool dump = a.keys_out != nullptr;
+        constexpr bool dump = DUMP;
+        // timing probes (lb_set_option "tc_debug"), parked in registers the compiler cannot re-derive from the
+        // parameter bank: re-reading a.debug per chunk cost the short-row epilogue 15 % of its issue slots
+        uint32_t surv_mask = (a.debug & 32) ? 0u : 0xffffffffu;   // 32: filter only, survivors ignored
+        uint32_t probe_bits = (uint32_t)a.debug & (1u | 128u);    // 1: no epilogue work, 128: round-1 release form
+        asm volatile("mov.b32 %0, %0;" : "+r"(surv_mask));
+        asm volatile("mov.b32 %0, %0;" : "+r"(probe_bits));
         int as = 0;
         uint32_t aphase = 0;
         int abuf = 0;
@@ -601,7 +609,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                     else if constexpr (METRIC == METRIC_COSINE) return dot * axj;
                     else return dot;
                 };
-                if (dump) {
+                if constexpr (dump) {
                     // bootstrap sample: write the keys of this chunk (row-major per query)
                     if (q < a.nq) {
                         float4* dst = reinterpret_cast<float4*>(a.keys_out + (size_t)q * a.keys_ld +
@@ -646,8 +654,7 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                         gm |= (m > thr ? 1u : 0u) << c;   // NaN never passes (max ignores it, the compare is false)
                     }
                 }
-                uint32_t groups = __reduce_or_sync(0xffffffffu, gm);
-                if (a.debug & 32) groups = 0;  // probe: filter only, survivors ignored
+                const uint32_t groups = __reduce_or_sync(0xffffffffu, gm) & surv_mask;
                 if (groups == 0) return;
                 // per-key mask, only for the flagged groups (warp-uniform branches, static register indices)
                 uint32_t hits = 0;
@@ -711,14 +718,14 @@ dense_scan_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 __syncwarp();
                 if (lane == 0) {
                     if constexpr (CG == 2) {
-                        if (a.debug & 128)  // probe: the round-1 form (cluster-scope release)
+                        if (probe_bits & 128u)  // probe: the round-1 form (cluster-scope release)
                             asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
                                          ::"r"(as ? tempty_remote[1] : tempty_remote[0]) : "memory");
                         else mbar_arrive_cluster(as ? tempty_remote[1] : tempty_remote[0]);
                     } else mbar_arrive(tempty_bar(as));
                 }
             };
-            if (!(a.debug & 1)) {
+            if (!(probe_bits & 1u)) {
                 // TMEM -> registers, double buffered: the load of chunk c+1 is in flight while chunk c is filtered
                 uint32_t va[32], vb[32];
                 tmem_ld32(taddr, va);
@@ -1099,8 +1106,10 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
     cfg.attrs = attr;
     cfg.numAttrs = 1;
 #define LB_TC2(KIND_, METRIC_, CAP_, CG_)                                                                      \
+    if (s.keys_out != nullptr) LB_TC3(KIND_, METRIC_, 512, CG_, true) else LB_TC3(KIND_, METRIC_, CAP_, CG_, false)
+#define LB_TC3(KIND_, METRIC_, CAP_, CG_, DUMP_)                                                               \
     {                                                                                                          \
-        auto kern = dense_scan_tc<KIND_, METRIC_, CAP_, CG_>;                                                  \
+        auto kern = dense_scan_tc<KIND_, METRIC_, CAP_, CG_, DUMP_>;                                           \
         LB_SMEM_OPTIN(kern);                                                                                   \
         cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mdb, mqlo, mdblo, a);                               \
         if (e != cudaSuccess) return e;                                                                        \
@@ -1123,6 +1132,7 @@ cudaError_t launch_dense_scan_tc(const ScanArgs& s, int sm_count, uint64_t* cand
 #undef LB_TC
 #undef LB_TC1
 #undef LB_TC2
+#undef LB_TC3
     count_launch();
     return cudaGetLastError();
 }
