@@ -261,6 +261,11 @@ def main():
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mine = torch.tensor([ms, scan_ms / max(scan_n, 1)], device=dev)  # this rank's own region / scan-kernel time
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"region_ms": [round(float(x[0]), 3) for x in allr],
+                    "scan_kernel_ms": [round(float(x[1]), 4) for x in allr]}
         ms = float(t.item())
     check_l = outs[(warm + steps - 1) % 2][1].cpu().numpy()  # the last timed batch
     check_d = outs[(warm + steps - 1) % 2][0].cpu().numpy()
@@ -468,6 +473,8 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "clocks": main_clocks, "roofline": roof,
             "checks": checks, "uncertified": uncertified, "configs": extra,
         }
+        if world > 1:
+            out["per_rank"] = per_rank
         failed = [name for name, ok in checks.items() if ok is False]
         for name in failed:
             print(f"[bench] CHECK FAILED: {name}", file=sys.stderr, flush=True)

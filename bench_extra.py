@@ -27,13 +27,15 @@ class Timer:
     def __init__(self, torch, _lib, sampler, adaptive=True):
         self.torch, self._lib, self.sampler, self.adaptive = torch, _lib, sampler, adaptive
 
-    def run(self, fn, steps, warm=3, min_ms=300.0):
+    def run(self, fn, steps, warm=3, min_ms=300.0, fin=None):
         """Timed region of at least `min_ms` (so the 10 ms NVML clock sampler sees it) when adaptive: the step count
         is raised after a calibration pass.  Multi-rank runs keep the given count (every rank must issue the same
         number of exchanges)."""
         torch, _lib = self.torch, self._lib
         for _ in range(warm):
             fn()
+        if fin is not None:
+            fin()
         torch.cuda.synchronize()
         if self.adaptive:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -51,6 +53,8 @@ class Timer:
         e0.record()
         for _ in range(steps):
             fn()
+        if fin is not None:
+            fin()   # e.g. make the timing stream wait for work issued on side streams
         e1.record()
         torch.cuda.synchronize()
         t1 = time.time()
@@ -216,7 +220,7 @@ def config_c4(ctx):
     sidx = ShardedIndex(D, np.int8, _lib.METRIC_DOT, ROWS * world, rank, world, ctx["local"])
     sidx.index.reserve(ROWS)
     sidx.add_local_device(_c4_shard(torch, dev, rank, ROWS))
-    g = torch.Generator(device=dev).manual_seed(4002)
+    g = torch.Generator(device=dev).manual_seed(4999)   # (not 4001 + rank: the queries must not be rows of a shard)
     nb = 4
     qs = torch.randint(-128, 128, (nb, Q, D), generator=g, device=dev, dtype=torch.int8)
     od = torch.empty((Q, K), dtype=torch.float32, device=dev)
@@ -224,18 +228,27 @@ def config_c4(ctx):
     steps = max(4, ctx["steps"] // 2) if world == 1 else 80  # 80 x ~4 ms: long enough for the clock sampler
     it = [0]
 
+    # N > 1: the exchange (peer-memory push + signal + wait + merge) of batch s runs on the side stream under the
+    # scan of batch s + 1, as in the C2 arm; every batch is still one complete sharded search
     def step():
-        sidx.search_device(qs[it[0] % nb], K, od, ol)
+        sidx.search_device(qs[it[0] % nb], K, od, ol, overlap=world > 1)
         it[0] += 1
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
-    t = ctx["timer"].run(step, steps)
+    t = ctx["timer"].run(step, steps, fin=sidx.wait if world > 1 else None)
     ms = t["ms"]
+    per_rank = None
     if world > 1:
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+        # every rank's own step and scan-kernel time (a slow GPU of the box paces all of them through the exchange)
+        mine = torch.tensor([t["ms"], t["kernel_ms"] or 0.0, float((t["clocks"] or {}).get("sm_mhz") or 0)], device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"step_ms": [round(float(x[0]), 4) for x in allr], "scan_kernel_ms": [round(float(x[1]), 4) for x in allr],
+                    "sm_mhz": [int(x[2]) for x in allr]}
     last_q = qs[(it[0] - 1) % nb]
     got_d, got_l = od.cpu().numpy(), ol.cpu().numpy()
     out = {"name": "C4", "workload": f"int8 dot-product k=10 over {ROWS * world} x 128 int8 "
@@ -248,6 +261,7 @@ def config_c4(ctx):
            "gpu_launches": t["launches"], "clocks": t["clocks"], "checks": {}, "uncertified": sidx.uncertified()}
     if world > 1:
         sidx.check_exchange()
+        out["per_rank"] = per_rank
     if world == 1:
         hq = last_q.cpu().numpy()
         hd, hl = np.empty((Q, K), np.float32), np.empty((Q, K), np.int64)

@@ -865,26 +865,41 @@ sample_select_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_r
     __syncthreads();
     block_bitonic_sort(s_coll, n2);
     for (int t = tid; t < kc; t += nt) out[(size_t)q * kc + t] = s_coll[t];
-    // threshold ladder: the sample keys at the ranks in `ranks` (ascending), bumped one ulp so that the
-    // scan's strict '<' admits ties, and how many sample rows fall into each ladder bucket
-    if (tid < LB_NEDGE) {
-        const int r1 = ranks.r[tid], r0 = tid > ranks.n_spare ? ranks.r[tid - 1] : 0;
-        float e = nextafterf(key_of(s_coll[r1 - 1]), INFINITY);
-        uint32_t cnt = (uint32_t)(r1 - r0);
-        if (tid < ranks.n_spare) {
-            // Extrapolated edge below the sample's best key.  Key units per halving of the tail probability are
-            // read off the ladder's own span (rank kc down to its lowest rank); the edge is clamped to the
-            // sample's smallest key so that no sample row lies below it (count 0).
+    // Threshold ladder: the sample keys at the ranks in `ranks`, bumped one ulp so that the scan's strict '<' admits
+    // ties, plus -- in the slots the rank ladder left over -- edges extrapolated below the sample: the model
+    // key(r) = key(kc) - kpd * log2(kc / r) continued to fractional ranks, with kpd (key units per halving of the
+    // tail probability) read between ranks kc and ~kc/4, NOT off the lowest keys: a query that is itself a row of
+    // the index (self-match, common in practice) puts an outlier at rank 1.  The 16 values are then sorted and every
+    // bucket is seeded with the sample rows that actually fall into it, so any mix of values is a valid ladder.
+    __shared__ float s_edge[LB_NEDGE];
+    __shared__ int s_below[LB_NEDGE];
+    if (tid < LB_NEDGE) {   // one warp
+        const float ktop = key_of(s_coll[kc - 1]);
+        float e;
+        if (tid >= ranks.n_spare) {
+            e = nextafterf(key_of(s_coll[ranks.r[tid] - 1]), INFINITY);
+        } else {
             const int rl = ranks.r[ranks.n_spare];
-            const float klow = key_of(s_coll[rl - 1]), ktop = key_of(s_coll[kc - 1]), kmin = key_of(s_coll[0]);
-            const float halvings = (kc > rl) ? log2f((float)kc / (float)rl) : 1.f;
-            const float step = (ktop - klow) / halvings * ranks.doublings / (float)ranks.n_spare;
-            e = fminf(klow - (float)(ranks.n_spare - tid) * step, kmin);
-            if (!(e == e)) e = kmin;  // inf - inf
-            cnt = 0;
+            int rm = kc / 4;
+            if (rm <= rl) rm = rl + 1;
+            const float kpd = (rm < kc) ? (ktop - key_of(s_coll[rm - 1])) / log2f((float)kc / (float)rm) : 0.f;
+            const float below = (float)(ranks.n_spare - tid) * ranks.doublings / (float)ranks.n_spare;
+            e = ktop - kpd * (log2f((float)kc / (float)rl) + below);
+            if (!(e == e)) e = ktop;  // inf - inf
         }
-        edges[(size_t)q * LB_NEDGE + tid] = e;
-        edge_cnt[(size_t)q * LB_NEDGE + tid] = cnt;
+        s_edge[tid] = e;
+        __syncwarp(0xffffu);
+        int pos = 0;
+        for (int u = 0; u < LB_NEDGE; u++) pos += (s_edge[u] < e || (s_edge[u] == e && u < tid)) ? 1 : 0;
+        int lo = 0, hi = c;  // sample rows with key < e: all of them are among the c collected (e <= the kc-th key, bumped)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (key_of(s_coll[mid]) < e) lo = mid + 1; else hi = mid;
+        }
+        s_below[pos] = lo;
+        edges[(size_t)q * LB_NEDGE + pos] = e;
+        __syncwarp(0xffffu);
+        edge_cnt[(size_t)q * LB_NEDGE + tid] = (uint32_t)(s_below[tid] - (tid ? s_below[tid - 1] : 0));
     }
     if (tid == 0) { tau[q] = nextafterf(key_of(s_coll[kc - 1]), INFINITY); done[q] = 1; }
 }
@@ -958,7 +973,7 @@ cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_ro
         // without them the threshold stops at the sample's minimum and ~n_rows / S rows per query get through
         // (12.5 M x 128 int8, kc = 26: 1785 appended rows per query instead of ~250).
         er.n_spare = (lad[n - 1] == 1) ? LB_NEDGE - n : 0;
-        const float need = 0.9f * log2f(fmaxf(1.f, (float)n_rows / ((float)S * (float)kc)));
+        const float need = 0.8f * log2f(fmaxf(1.f, (float)n_rows / ((float)S * (float)kc)));
         er.doublings = fmaxf(need, 0.5f * (float)er.n_spare);
     }
 #define LB_SSEL(E_)                                                                                             \

@@ -75,9 +75,9 @@ struct ScanArgs {
 };
 
 // Ascending 1-based sample ranks of the threshold ladder.  The first n_spare slots have no rank of their own (the
-// ladder reached rank 1 before it ran out of slots): their edges are extrapolated BELOW the sample's best key,
-// `doublings` halvings of the tail probability spread evenly over them (any value is a valid edge -- an edge only
-// becomes the threshold once kc live rows were counted below it).
+// ladder reached rank 1 before it ran out of slots): their edges are extrapolated below the sample, `doublings`
+// halvings of the tail probability past the lowest rank spread evenly over them (any value is a valid edge -- an
+// edge only becomes the threshold once kc live rows were counted below it).
 struct EdgeRanks { int r[LB_NEDGE]; int n_spare; float doublings; };
 
 struct RescoreArgs {

@@ -725,3 +725,30 @@ def test_add_arrow_offsets_pinned_and_growth(lbgpu, oracle):
     wd, wl = oracle.search(COS, full, q, k, tomb=lbgpu.pack_bitmap(tomb))
     assert_topk_equal(gd, gl, wd, wl, 0.0, "after tombstone updates")
     idx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,metric,n,dim,k", [(np.int8, DOT, 300000, 128, 10), (np.float16, COS, 120000, 256, 100),
+                                                  (np.float32, L2, 150000, 64, 10)])
+def test_self_match_queries_and_duplicates(lbgpu, oracle, scan_mode, dtype, metric, n, dim, k):
+    """Queries that ARE rows of the index (some of them inside the bootstrap sample, some stored several times): the
+    sample then holds an outlier far below the rest of its keys.  The threshold ladder reads its extrapolation slope
+    off mid ranks, sorts its 16 edges and seeds every bucket with the sample rows that fall into it, so the answers
+    stay the oracle's -- tensor-core scan (batch) and streaming scan (one query)."""
+    rng = np.random.default_rng(77 + dim)
+    db = make_db(rng, n, dim, dtype)
+    rows = np.concatenate([np.arange(0, 40), rng.integers(0, n, 88)])   # first 40: inside the sample
+    q = db[rows].copy()
+    db[n // 2: n // 2 + 5] = db[7]       # a query stored six times
+    db[100:103] = db[n - 1]              # duplicates of a far row inside the sample
+    idx = lbgpu.DenseIndex(dim, dtype, metric)
+    idx.add(db)
+    wd, wl = oracle.search(metric, db, q, k)
+    scan_mode(2)
+    gd, gl = idx.search(q, k)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "self-match batch")
+    scan_mode(0)
+    for i in (0, 7, 50):
+        gd1, gl1 = idx.search(q[i:i + 1], k)
+        assert_topk_equal(gd1, gl1, wd[i:i + 1], wl[i:i + 1], 0.0, f"self-match single query {i}")
+    idx.close()
