@@ -434,7 +434,7 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")))
             for kname, rec in tj.items():
                 if kname.startswith("dense_scan_tc") and world == 1 and n_rows == N_ROWS:
                     traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
@@ -447,7 +447,7 @@ def main():
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "traffic_source": ("ncu --set full capture of this kernel on this workload (dram__bytes_read.sum + "
-                                   "dram__bytes_write.sum per launch), profiles/r1_roofline_traffic.json; a recorded "
+                                   "dram__bytes_write.sum per launch), profiles/r2_roofline_traffic.json; a recorded "
                                    "constant, not measured in this run") if traffic else None,
                 "frac_of_sustained_peak": (achieved / sustained) if (achieved and sustained) else None,
                 "algorithmic_bytes_per_launch": scan_units / max(scan_n, 1) / NQ * DIM * 2,
