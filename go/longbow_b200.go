@@ -11,7 +11,7 @@ package gpu
 
 /*
 #cgo CFLAGS: -I${SRCDIR}/../../third_party/longbow_b200/include
-#cgo LDFLAGS: -L${SRCDIR}/../../third_party/longbow_b200/lib -llongbow_b200 -lcuda
+#cgo LDFLAGS: -L${SRCDIR}/../../third_party/longbow_b200/lib -llongbow_b200
 #include <stdlib.h>
 #include "longbow_b200.h"
 */

@@ -140,6 +140,39 @@ using namespace lb;
 // allocated 1.5x, device-synchronised and copied: 2.5x transient HBM on a 100 M-row mirror), the base pointer never
 // changes, and a 180 GB part can be filled to the brim.
 // ---------------------------------------------------------------------------------------------
+// The driver API is reached through cudaGetDriverEntryPoint, not by linking libcuda: the library must load (and export
+// its symbols) on a machine without a driver, and fail loudly only when a GPU call is made.
+namespace drv {
+struct Api {
+    CUresult (*GetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    bool ok = false;
+};
+static const Api& api() {
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult qr;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &qr) == cudaSuccess &&
+                   qr == cudaDriverEntryPointSuccess && *fn != nullptr;
+        };
+        a.ok = get("cuMemGetAllocationGranularity", (void**)&a.GetAllocationGranularity) &&
+               get("cuMemAddressReserve", (void**)&a.AddressReserve) && get("cuMemAddressFree", (void**)&a.AddressFree) &&
+               get("cuMemCreate", (void**)&a.Create) && get("cuMemRelease", (void**)&a.Release) &&
+               get("cuMemMap", (void**)&a.Map) && get("cuMemUnmap", (void**)&a.Unmap) &&
+               get("cuMemSetAccess", (void**)&a.SetAccess);
+    });
+    return a;
+}
+}  // namespace drv
+
 struct VBuf {
     CUdeviceptr base = 0;
     size_t reserved = 0, mapped = 0, gran = 0;
@@ -153,10 +186,12 @@ struct VBuf {
         prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
         prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
         prop.location.id = dev;
-        if (cuMemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0)
+        const drv::Api& d = drv::api();
+        if (!d.ok) return fail(LB_ERR_CUDA, "CUDA driver virtual-memory entry points unavailable");
+        if (d.GetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0)
             return fail(LB_ERR_CUDA, "cuMemGetAllocationGranularity failed");
         reserved = ((max_bytes + gran - 1) / gran) * gran;
-        if (cuMemAddressReserve(&base, reserved, 0, 0, 0) != CUDA_SUCCESS) {
+        if (d.AddressReserve(&base, reserved, 0, 0, 0) != CUDA_SUCCESS) {
             base = 0; reserved = 0;
             return fail(LB_ERR_OOM, "cuMemAddressReserve failed");
         }
@@ -176,20 +211,21 @@ struct VBuf {
         prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
         prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
         prop.location.id = device;
+        const drv::Api& d = drv::api();
         CUmemGenericAllocationHandle h;
-        CUresult r = cuMemCreate(&h, want, &prop, 0);
+        CUresult r = d.Create(&h, want, &prop, 0);
         if (r != CUDA_SUCCESS && want > ((bytes - mapped + gran - 1) / gran) * gran) {  // retry with the exact need
             want = ((bytes - mapped + gran - 1) / gran) * gran;
-            r = cuMemCreate(&h, want, &prop, 0);
+            r = d.Create(&h, want, &prop, 0);
         }
         if (r != CUDA_SUCCESS) return fail(LB_ERR_OOM, "cuMemCreate failed (device memory exhausted)");
-        if (cuMemMap(base + mapped, want, 0, h, 0) != CUDA_SUCCESS) { cuMemRelease(h); return fail(LB_ERR_CUDA, "cuMemMap failed"); }
+        if (d.Map(base + mapped, want, 0, h, 0) != CUDA_SUCCESS) { d.Release(h); return fail(LB_ERR_CUDA, "cuMemMap failed"); }
         CUmemAccessDesc acc = {};
         acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
         acc.location.id = device;
         acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-        if (cuMemSetAccess(base + mapped, want, &acc, 1) != CUDA_SUCCESS) {
-            cuMemUnmap(base + mapped, want); cuMemRelease(h);
+        if (d.SetAccess(base + mapped, want, &acc, 1) != CUDA_SUCCESS) {
+            d.Unmap(base + mapped, want); d.Release(h);
             return fail(LB_ERR_CUDA, "cuMemSetAccess failed");
         }
         chunks.emplace_back(h, want);
@@ -199,8 +235,9 @@ struct VBuf {
     void release() {
         if (base) {
             size_t off = 0;
-            for (auto& c : chunks) { cuMemUnmap(base + off, c.second); cuMemRelease(c.first); off += c.second; }
-            cuMemAddressFree(base, reserved);
+            const drv::Api& d = drv::api();
+            for (auto& c : chunks) { d.Unmap(base + off, c.second); d.Release(c.first); off += c.second; }
+            d.AddressFree(base, reserved);
         }
         chunks.clear();
         base = 0; reserved = mapped = 0;
