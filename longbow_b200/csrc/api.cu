@@ -101,7 +101,7 @@ static std::atomic<int> g_opt_dense_scan{0};
 static std::atomic<int> g_opt_tc_debug{0};
 static std::atomic<int> g_opt_tc_boot_tiles{0};  // 0 = auto
 static std::atomic<int> g_opt_f32_tc{1};         // fp32 indexes: 3xTF32 tensor-core scan (0: SIMT scan)
-static std::atomic<int> g_opt_pq_scan{0};  // 0 auto, 1 exhaustive fp32 kernel, 2 coarse (1 query / pass), 3 coarse (4 / pass)
+static std::atomic<int> g_opt_pq_scan{0};  // 0 auto, 1 exhaustive fp32 kernel, 2 coarse (1 query / pass), 3 coarse (4 / pass), 4 decode + tensor-core scan
 static std::atomic<int> g_opt_certify{1};        // host searches: certify the coarse stage, redo flagged queries exactly
 static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off (A/B timing)    // timing probes of the tensor-core scan (results invalid when != 0)  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
 
@@ -289,6 +289,11 @@ static int index_ensure_rows(lb_index* idx, int64_t need) {
 struct lb_pq {
     int device, dims, M, K, sub;
     float* codebooks = nullptr;  // [M][K][sub]
+    void* codebook16 = nullptr;  // the same, fp16: decode source of the batched tensor-core coarse stage (pq_gemm.cu)
+    float* cnorm2 = nullptr;     // [M][256] |fp16 centroid|^2
+    float* xn2 = nullptr;        // [xn2_cap + 256] per row: |decoded fp16 vector|^2 (the dense scan's L2 auxiliary)
+    int64_t xn2_cap = 0;
+    uint32_t* xmax2 = nullptr;   // device word: largest xn2 so far (float bits)
     uint8_t* codes = nullptr;    // [capacity][M] row-major (flatCodes, adc_table.go:57): exhaustive fp32 scan, fallback
     uint8_t* tiled = nullptr;    // the same codes as 32-row tiles of rotated 16-byte chunks (pq_scan.cu): coarse scan
     int64_t tiled_cap = 0;       // rows (multiple of 32)
@@ -414,7 +419,8 @@ int lb_set_option(const char* name, int value) {
         return LB_OK;
     }
     if (strcmp(name, "pq_scan") == 0) {
-        if (value < 0 || value > 3) return fail(LB_ERR_INVALID, "pq_scan: 0 auto, 1 exhaustive fp32, 2 coarse x1, 3 coarse x4");
+        if (value < 0 || value > 4)
+            return fail(LB_ERR_INVALID, "pq_scan: 0 auto, 1 exhaustive fp32, 2 coarse x1, 3 coarse x4, 4 decode + tensor cores");
         g_opt_pq_scan.store(value);
         return LB_OK;
     }
@@ -1355,6 +1361,16 @@ int lb_pq_create(int device, const void* blob, size_t blob_len, lb_pq** out) {
     if (e != cudaSuccess) { delete pq; return fail_cuda(e, "cudaMalloc(codebooks)"); }
     e = cudaMemcpy(pq->codebooks, (const char*)blob + 12, (size_t)M * K * sub * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(pq->codebooks); delete pq; return fail_cuda(e, "cudaMemcpy(codebooks)"); }
+    if (pq_gemm_eligible(dims, M, sub)) {
+        e = cudaMalloc(&pq->codebook16, (size_t)M * K * sub * 2);
+        if (e == cudaSuccess) e = launch_pq_codebook16(pq->codebooks, pq->codebook16, (size_t)M * K * sub, cudaStreamPerThread);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&pq->cnorm2, (size_t)M * 256 * 4);
+        if (e == cudaSuccess) e = launch_pq_centroid_norms(pq->codebook16, M, sub, pq->cnorm2, cudaStreamPerThread);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&pq->xmax2, 4);
+        if (e == cudaSuccess) e = cudaMemsetAsync(pq->xmax2, 0, 4, cudaStreamPerThread);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+        if (e != cudaSuccess) { lb_pq_free(pq); return fail_cuda(e, "fp16 codebooks"); }
+    }
     *out = pq;
     return LB_OK;
 }
@@ -1364,6 +1380,10 @@ void lb_pq_free(lb_pq* pq) {
     if (cudaSetDevice(pq->device) == cudaSuccess) {
         cudaDeviceSynchronize();
         if (pq->codebooks) cudaFree(pq->codebooks);
+        if (pq->codebook16) cudaFree(pq->codebook16);
+        if (pq->cnorm2) cudaFree(pq->cnorm2);
+        if (pq->xn2) cudaFree(pq->xn2);
+        if (pq->xmax2) cudaFree(pq->xmax2);
         if (pq->codes) cudaFree(pq->codes);
         if (pq->tiled) cudaFree(pq->tiled);
         if (pq->tomb) cudaFree(pq->tomb);
@@ -1407,6 +1427,19 @@ static int pq_add_common(lb_pq* pq, const uint8_t* src, int64_t n, bool on_devic
             pq->tiled_cap = need;
         }
         CK(launch_pq_tile_codes(pq->codes + (size_t)pq->size * pq->M, n, pq->M, Mp, pq->size, pq->tiled, st));
+    }
+    if (pq->codebook16 != nullptr) {  // row norms of the decoded vectors (pq_gemm.cu)
+        if (pq->capacity > pq->xn2_cap) {
+            float* nx = nullptr;
+            CK(cudaMalloc((void**)&nx, (size_t)(pq->capacity + 256) * 4));
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemset(nx, 0, (size_t)(pq->capacity + 256) * 4));
+            if (pq->xn2 && pq->size > 0) CK(cudaMemcpy(nx, pq->xn2, (size_t)pq->size * 4, cudaMemcpyDeviceToDevice));
+            if (pq->xn2) cudaFree(pq->xn2);
+            pq->xn2 = nx;
+            pq->xn2_cap = pq->capacity;
+        }
+        CK(launch_pq_row_norms(pq->codes, pq->cnorm2, pq->M, pq->size, n, pq->xn2, pq->xmax2, st));
     }
     pq->size += n;
     if (!on_device) CK(cudaStreamSynchronize(st));
@@ -1569,6 +1602,68 @@ static int pq_search_exhaustive(lb_pq* pq, const float* q, int cq, const float* 
 }
 
 // d_flags [nq] / d_count [1] (device, optional): certification of the coarse pass (pq_scan.cu)
+
+// Coarse candidates of a dense fp16 / L2 view through the tensor-core scan: bootstrap sample -> shared-threshold
+// scan -> merge-select.  `a` names the view (db, aux, n_rows, dim), the queries and the bitmaps; *merged_out receives
+// [nq][kc] packed (key, row), the kc smallest by (key, row) in no particular order.  The same chain search_core runs
+// for a dense index (kept separate: that one also handles the streaming / SIMT / 3xTF32 cases).
+static int tc_coarse_candidates(ScanArgs a, int kc, int sm_count, Scratch& scr, cudaStream_t st, uint64_t** merged_out) {
+    const int cq = a.nq;
+    const int n_tiles = (int)(((int64_t)a.n_rows + 255) / 256);
+    a.kc = kc; a.tq = 128; a.cap = 0; a.rows_per_part = 0;
+    a.debug = g_opt_tc_debug.load(std::memory_order_relaxed);
+    int boot_tiles = 0, gm;
+    size_t cand_bytes;
+    if (g_opt_tc_boot.load(std::memory_order_relaxed)) {
+        int bt = g_opt_tc_boot_tiles.load(std::memory_order_relaxed);
+        if (bt <= 0) {
+            bt = n_tiles / 128;
+            if (bt < 8) bt = 8;
+            if (bt > 32) bt = 32;
+        }
+        if (bt > 128) bt = 128;
+        if (bt * 4 <= n_tiles) boot_tiles = bt;
+    }
+    dense_scan_tc_plan(cq, n_tiles - boot_tiles, sm_count, kc, &gm, &cand_bytes);
+    uint64_t *cand, *partial, *merged;
+    CK(scr.get((void**)&cand, cand_bytes));
+    const int extra = boot_tiles ? 1 : 0;
+    const int parts = 2 * gm + extra;
+    CK(scr.get((void**)&partial, (size_t)parts * cq * kc * 8));
+    a.partial = partial;
+    if (boot_tiles) {
+        const int S = boot_tiles * 256;
+        float *keys, *tau, *edges;
+        uint32_t* edge_cnt;
+        int* sel_done;
+        CK(scr.get((void**)&sel_done, (size_t)cq * 4));
+        CK(scr.get((void**)&keys, (size_t)cq * S * 4));
+        CK(scr.get((void**)&tau, (size_t)cq * 4));
+        CK(scr.get((void**)&edges, (size_t)cq * LB_NEDGE * 4));
+        CK(scr.get((void**)&edge_cnt, (size_t)cq * LB_NEDGE * 4));
+        ScanArgs b = a;
+        b.parts = 0; b.partial = nullptr; b.tile_begin = 0; b.tile_end = boot_tiles; b.part_offset = 0;
+        b.keys_out = keys; b.keys_ld = S;
+        CK(launch_dense_scan_tc(b, sm_count, cand, st));
+        CK(launch_sample_select(keys, S, S, a.n_rows, a.tomb, a.tomb_bits, a.allow, cq, kc, partial, tau, edges, edge_cnt,
+                                sel_done, st));
+        a.edges = edges; a.edge_cnt = edge_cnt; a.tau_init = tau;
+    }
+    a.parts = 2 * gm; a.tile_begin = boot_tiles; a.tile_end = n_tiles; a.part_offset = extra;
+    {
+        ProfScope prof(st, (double)cq * (double)((int64_t)a.n_rows - (int64_t)boot_tiles * 256));
+        CK(launch_dense_scan_tc(a, sm_count, cand, st));
+    }
+    if (parts > 1) {
+        CK(scr.get((void**)&merged, (size_t)cq * kc * 8));
+        CK(launch_merge_select(partial, parts, cq, kc, merged, nullptr, a.edges, a.edge_cnt, st));
+    } else {
+        merged = partial;
+    }
+    *merged_out = merged;
+    return LB_OK;
+}
+
 static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kprime, const uint64_t* d_allow,
                           float* d_dist, int64_t* d_lab, cudaStream_t st, uint32_t* d_flags = nullptr,
                           uint32_t* d_count = nullptr) {
@@ -1587,13 +1682,81 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
     }
     const int mode = g_opt_pq_scan.load(std::memory_order_relaxed);
     const int kc = coarse_k(kout);  // coarse candidates: margin over kout absorbs the quantisation step
-    const int64_t qchunk = 512;
+    // (the tensor-core path decodes the codes once per query chunk: larger chunks amortise it)
+    const int64_t qchunk = (mode == 4 || (mode == 0 && nq >= 64 && pq->codebook16 != nullptr)) ? 1024 : 512;
     for (int64_t qo = 0; qo < nq; qo += qchunk) {
         const int cq = (int)((nq - qo) < qchunk ? (nq - qo) : qchunk);
         const float* q = d_q + (size_t)qo * pq->dims;
         float* luts;
         CK(scr.get((void**)&luts, (size_t)cq * pq->M * 1024));
         CK(launch_adc_lut(pq->codebooks, pq->M, pq->K, pq->sub, q, cq, luts, st));
+        // Batches: coarse stage on the tensor cores over a decoded fp16 slab (pq_gemm.cu).  From ~64 queries up the
+        // look-up scan is bound by the shared-memory pipe (N*M look-ups per query) while the decode is paid once per
+        // slab and the dense scan runs at its tensor rate.
+        const bool gemm_ok = pq->codebook16 != nullptr && pq->xn2 != nullptr && pq->tiled != nullptr && pq->M <= 96 && pq->size >= 4096 &&
+                             dense_tc_eligible(DT_F16, pq->dims, pq->codebook16, pq->codebook16, 2 * kout + 64);
+        if (mode == 4 && !gemm_ok) return fail(LB_ERR_UNSUPPORTED, "decode + tensor-core PQ scan not eligible");
+        if (mode == 4 || (mode == 0 && gemm_ok && cq >= 64)) {
+            int kg = 2 * kout;  // wider candidate margin than the look-up path: the fp16 rounding bound is looser
+            if (kg < kc) kg = kc;
+            if (kg > 704) kg = 704;
+            if (kg < kout) return fail(LB_ERR_UNSUPPORTED, "k' too large for the tensor-core PQ scan");
+            void* q16; float* qn; void* slab; uint64_t *all, *merged, *exact;
+            const int64_t slab_rows_max = 4 << 20;   // 4 Mi rows per slab (6 GiB at 768 dims)
+            const int64_t slab_rows = pq->size < slab_rows_max ? ((pq->size + 255) / 256) * 256 : slab_rows_max;
+            const int n_slabs = (int)((pq->size + slab_rows - 1) / slab_rows);
+            CK(scr.get(&q16, (size_t)cq * pq->dims * 2));
+            CK(scr.get((void**)&qn, (size_t)cq * 8));
+            CK(scr.get(&slab, (size_t)slab_rows * pq->dims * 2));
+            CK(scr.get((void**)&all, (size_t)n_slabs * cq * kg * 8));
+            CK(scr.get((void**)&exact, (size_t)cq * kout * 8));
+            CK(launch_pq_q16(q, cq, pq->dims, q16, qn, st));
+            const int64_t tomb_bits = pq->tomb ? pq->tomb_bits : 0;
+            for (int sl = 0; sl < n_slabs; sl++) {
+                const int64_t r0 = (int64_t)sl * slab_rows;
+                const int64_t rn = (pq->size - r0) < slab_rows ? (pq->size - r0) : slab_rows;
+                CK(launch_pq_decode(pq->codes, pq->codebook16, pq->M, pq->sub, (uint32_t)r0, (uint32_t)rn, slab, pq->sm_count,
+                                    st));
+                ScanArgs a;
+                a.dtype = DT_F16; a.metric = METRIC_L2; a.db = slab; a.aux = pq->xn2 + r0; a.n_rows = (uint32_t)rn;
+                a.dim = pq->dims; a.queries = q16; a.nq = cq;
+                // bitmaps are indexed by global row: r0 is a multiple of 256, so the slab's view is a word offset
+                const int64_t tb = tomb_bits - r0;
+                a.tomb = (pq->tomb && tb > 0) ? pq->tomb + r0 / 32 : nullptr;
+                a.tomb_bits = (uint32_t)(tb > 0 ? (tb > 0xffffffffll ? 0xffffffffll : tb) : 0);
+                a.allow = d_allow ? (const uint32_t*)d_allow + r0 / 32 : nullptr;
+                uint64_t* mg;
+                int rc = tc_coarse_candidates(a, kg, pq->sm_count, scr, st, &mg);
+                if (rc) return rc;
+                uint64_t* dst = all + (size_t)sl * cq * kg;
+                CK(cudaMemcpyAsync(dst, mg, (size_t)cq * kg * 8, cudaMemcpyDeviceToDevice, st));
+                CK(launch_pq_offset_rows(dst, (size_t)cq * kg, (uint32_t)r0, st));
+            }
+            if (n_slabs > 1) {
+                CK(scr.get((void**)&merged, (size_t)cq * kg * 8));
+                CK(launch_merge_select(all, n_slabs, cq, kg, merged, nullptr, nullptr, nullptr, st));
+            } else {
+                merged = all;
+            }
+            uint32_t* flags = d_flags ? d_flags + qo : nullptr;
+            if (!flags && d_count) CK(scr.get((void**)&flags, (size_t)cq * 4));
+            PqGemmCert gc;
+            gc.qn = (const float2*)qn; gc.xmax2 = pq->xmax2; gc.dims = pq->dims;
+            gc.beta = (float)pq->dims * 1.2e-7f;
+            if (gc.beta < 8e-6f) gc.beta = 8e-6f;
+            CK(launch_adc_exact(pq->tiled, pq->M, luts, merged, cq, kg, kout, nullptr, nullptr, exact, flags, d_count, st, &gc));
+            if (rerank) {
+                RescoreArgs r;
+                r.dtype = DT_F32; r.metric = METRIC_L2; r.db = pq->raw->rows; r.n_rows = (uint32_t)pq->raw->size;
+                r.dim = pq->dims; r.queries = q; r.nq = cq; r.packed = exact; r.ids32 = nullptr; r.c = kout; r.k = k;
+                r.tomb = nullptr; r.tomb_bits = 0; r.allow = nullptr; r.id_base = 0;
+                r.out_d = d_dist + (size_t)qo * k; r.out_l = d_lab + (size_t)qo * k; r.negate_dot = 1;
+                CK(launch_rescore(r, st));
+            } else {
+                CK(launch_unpack_topk(exact, cq, kout, k, 0, d_dist + (size_t)qo * k, d_lab + (size_t)qo * k, st));
+            }
+            continue;
+        }
         int nqpp = (mode == 2) ? 1 : (mode == 3) ? 4 : (cq >= 2 ? 4 : 1);
         if (nqpp == 4 && !adc_coarse_eligible(pq->M, kc, 4)) nqpp = 1;
         const bool coarse = mode != 1 && pq->tiled != nullptr && adc_coarse_eligible(pq->M, kc, nqpp) &&

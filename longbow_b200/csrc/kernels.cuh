@@ -202,9 +202,27 @@ cudaError_t launch_adc_coarse(const uint8_t* tiled, uint32_t n_rows, int M, cons
                               uint32_t tiles_per_part, uint8_t* lutq, void* params, uint64_t* compact,
                               uint32_t* out_cnt, size_t stride, uint32_t* g_tau, uint32_t* g_min, uint32_t* overflow,
                               cudaStream_t st);
+// certification inputs when the coarse candidates come from the tensor-core scan over decoded rows (pq_gemm.cu)
+struct PqGemmCert {
+    const float2* qn;        // per query { |q_h|^2, |q| }; null = look-up path (integer keys, `params`)
+    const uint32_t* xmax2;   // largest |x_h|^2 over the decoded rows (bits of a non-negative float)
+    float beta;              // dot-product error bound of the scan, relative to |q_h||x_h|
+    int dims;
+};
 cudaError_t launch_adc_exact(const uint8_t* tiled, int M, const float* luts, const uint64_t* coarse, int nq, int kc,
                              int k_out, const void* params, const uint32_t* overflow, uint64_t* out,
-                             uint32_t* cert_flags, uint32_t* cert_count, cudaStream_t st);
+                             uint32_t* cert_flags, uint32_t* cert_count, cudaStream_t st,
+                             const PqGemmCert* gemm = nullptr);
+// pq_gemm.cu: batched PQ coarse stage through the dense tensor-core scan
+bool pq_gemm_eligible(int dims, int M, int sub);
+cudaError_t launch_pq_codebook16(const float* cb, void* out, size_t n, cudaStream_t st);
+cudaError_t launch_pq_q16(const float* q, int nq, int dims, void* q16, float* qn, cudaStream_t st);
+cudaError_t launch_pq_centroid_norms(const void* cb16, int M, int sub, float* n2, cudaStream_t st);
+cudaError_t launch_pq_row_norms(const uint8_t* codes, const float* n2, int M, int64_t r0, int64_t n, float* xn2,
+                                uint32_t* xmax2, cudaStream_t st);
+cudaError_t launch_pq_decode(const uint8_t* codes, const void* cb16, int M, int sub, uint32_t r0, uint32_t n, void* x,
+                             int sm_count, cudaStream_t st);
+cudaError_t launch_pq_offset_rows(uint64_t* p, size_t n, uint32_t r0, cudaStream_t st);
 cudaError_t launch_unpack_topk(const uint64_t* merged, int nq, int kc, int k, int64_t id_base, float* out_d,
                                int64_t* out_l, cudaStream_t st);
 

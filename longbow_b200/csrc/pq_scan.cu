@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(256)
 adc_exact_kernel(const uint8_t* __restrict__ tiled, int M, int Mp, const float* __restrict__ luts,
                  const uint64_t* __restrict__ coarse, int kc, int k_out, const PqQParams* __restrict__ params,
                  const uint32_t* __restrict__ overflow, uint64_t* __restrict__ out, uint32_t* __restrict__ cert_flags,
-                 uint32_t* __restrict__ cert_count) {
+                 uint32_t* __restrict__ cert_count, const PqGemmCert g) {
     __shared__ uint64_t keys[1024];
     __shared__ float vals[PQX_CHUNK * 97];
     const int q = blockIdx.x, tid = threadIdx.x;
@@ -596,6 +596,28 @@ adc_exact_kernel(const uint8_t* __restrict__ tiled, int M, int Mp, const float* 
         bool cert = true;
         const uint64_t last = coarse[(size_t)q * kc + kc - 1];  // merge output is sorted: the largest key, if full
         const uint64_t kth = (k_out - 1 < n2) ? keys[k_out - 1] : kInvalid;
+        if (g.qn != nullptr) {
+            // Coarse stage = tensor-core L2 keys over fp16-decoded rows (pq_gemm.cu).  The candidate list is the kc
+            // smallest (key, row) in no particular order; if it is full, every other live row has a key >= its
+            // largest one.  For such a row: |q_h - x_h|^2 >= |q_h|^2 + key - 2 beta |q_h||x_h| (truncating fp32
+            // accumulation of the dot product), the unrounded distance is at least the rounded one minus
+            // 2^-11 (|q| + |x|) + sqrt(dims) 2^-24, and the reference's fp32 table sum is within 1e-5 of it.
+            uint32_t kmax = 0;
+            bool full = true;
+            for (int i = 0; i < kc; i++) {
+                const uint64_t p = coarse[(size_t)q * kc + i];
+                if (p == kInvalid) full = false;
+                else kmax = max(kmax, (uint32_t)(p >> 32));
+            }
+            if (full && kth != kInvalid) {
+                const float2 qq = g.qn[q];
+                const double X = sqrt((double)__uint_as_float(*g.xmax2)) * 1.001;
+                const double d2 = (double)qq.x + (double)ordered_to_float(kmax) - 2.0 * g.beta * sqrt((double)qq.x) * X;
+                double lb = d2 > 0.0 ? sqrt(d2) : 0.0;
+                lb -= 4.8828125e-4 * ((double)qq.y + X) + sqrt((double)g.dims) * 1.2e-7;
+                cert = lb > 0.0 && lb * (1.0 - 1.0e-5) > (double)key_of(kth);
+            }
+        } else
         if (last != kInvalid && kth != kInvalid) {
             const PqQParams pr = params[q];
             const double klast = (double)(uint32_t)(last >> 32);
@@ -1053,12 +1075,14 @@ cudaError_t launch_adc_coarse(const uint8_t* tiled, uint32_t n_rows, int M, cons
 
 cudaError_t launch_adc_exact(const uint8_t* tiled, int M, const float* luts, const uint64_t* coarse, int nq, int kc,
                              int k_out, const void* params, const uint32_t* overflow, uint64_t* out,
-                             uint32_t* cert_flags, uint32_t* cert_count, cudaStream_t st) {
+                             uint32_t* cert_flags, uint32_t* cert_count, cudaStream_t st, const PqGemmCert* gemm) {
     if (nq <= 0) return cudaSuccess;
     if (kc > 1024 || M > 96) return cudaErrorInvalidValue;
     const int Mp = ((M + 31) / 32) * 32;
+    PqGemmCert g = {};
+    if (gemm) g = *gemm;
     adc_exact_kernel<<<nq, 256, 0, st>>>(tiled, M, Mp, luts, coarse, kc, k_out, (const PqQParams*)params, overflow, out,
-                                         cert_flags, cert_count);
+                                         cert_flags, cert_count, g);
     count_launch();
     return cudaGetLastError();
 }

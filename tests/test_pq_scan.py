@@ -136,3 +136,73 @@ def test_coarse_scan_small_and_empty(oracle, pq_mode):
     wd, wl = oracle.pq_search(cb, codes, None, q, 200, 0)
     assert_topk_equal(gd, gl, wd, wl, 0.0, "tiny")
     enc.close()
+
+
+@pytest.mark.parametrize("M,sub,n,nq", [(96, 8, 70001, 130), (16, 4, 20000, 70), (64, 4, 9000, 64), (32, 16, 30000, 96),
+                                        (40, 2, 33333, 65)])
+def test_gemm_coarse_bit_exact(oracle, pq_mode, M, sub, n, nq):
+    """Batches (>= 64 queries): coarse stage = decode to fp16 + dense tensor-core scan (csrc/pq_gemm.cu), then the same
+    exact fp32 table sums + certification.  Forced (mode 4) and by the automatic policy; bitmaps + re-rank too."""
+    from longbow_b200 import gpu, pq
+    rng = np.random.default_rng(9100 + M)
+    cb, codes = _setup(rng, n, M, sub)
+    dim = M * sub
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    q[:5] = oracle.pq_decode(codes[[0, 5, 4000, n - 1, n // 2]], cb)   # queries that are (decoded) rows: distance 0
+    enc = pq.PQEncoder(dim, M, 256, cb)
+    cuts = [0, 17, 1000, n // 2 + 5, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        enc.add_codes(codes[a:b])
+    for mode in (4, 0):
+        pq_mode(mode)
+        gd, gl = enc.search(q, 10)
+        wd, wl = oracle.pq_search(cb, codes, None, q, 10, 0)
+        assert_topk_equal(gd, gl, wd, wl, 0.0, f"gemm adc top-10 mode {mode}")
+    pq_mode(4)
+    gd, gl = enc.search(q, 100)
+    wd, wl = oracle.pq_search(cb, codes, None, q, 100, 0)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "gemm adc top-100")
+    raw = oracle.pq_decode(codes, cb) + rng.normal(0, 0.05, (n, dim)).astype(np.float32)
+    rawidx = gpu.DenseIndex(dim, np.float32, L2)
+    rawidx.add(raw)
+    enc.attach_raw(rawidx)
+    tomb, allow = random_bitmap(rng, n, 0.05), random_bitmap(rng, n, 0.3)
+    enc.set_tombstones(tomb)
+    gd, gl = enc.search(q, 10, 100, allow=allow)
+    wd, wl = oracle.pq_search(cb, codes, raw, q, 10, 100, tomb=gpu.pack_bitmap(tomb), allow=gpu.pack_bitmap(allow))
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "gemm adc + rerank + bitmaps")
+    enc.close(); rawidx.close()
+
+
+def test_gemm_coarse_ties_and_certification(oracle, pq_mode):
+    """Duplicate rows (equal distances: lower id wins) and a codebook whose centroids differ by ~1e-6: fp16 decoding
+    cannot separate them, the query must be flagged and the host call must return the exhaustive answer."""
+    from longbow_b200 import pq
+    rng = np.random.default_rng(43)
+    M, sub, n = 32, 4, 50000
+    cb, codes = _setup(rng, n, M, sub)
+    codes[40000:40040] = codes[123]
+    codes[777] = codes[123]
+    q = rng.standard_normal((70, M * sub)).astype(np.float32)
+    q[0] = oracle.pq_decode(codes[123:124], cb)[0] + 0.01
+    enc = pq.PQEncoder(M * sub, M, 256, cb)
+    enc.add_codes(codes)
+    pq_mode(4)
+    gd, gl = enc.search(q, 20)
+    wd, wl = oracle.pq_search(cb, codes, None, q, 20, 0)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "gemm duplicate rows")
+    enc.close()
+    M, sub, n = 16, 4, 30000
+    base = rng.standard_normal((M, 1, sub)).astype(np.float32)
+    cb = np.repeat(base, 256, axis=1)
+    cb += (rng.standard_normal(cb.shape) * 1e-6).astype(np.float32)
+    cb[:, 0] += 5.0
+    codes = rng.integers(1, 256, (n, M), dtype=np.uint8)
+    q = rng.standard_normal((66, M * sub)).astype(np.float32)
+    enc = pq.PQEncoder(M * sub, M, 256, cb)
+    enc.add_codes(codes)
+    gd, gl = enc.search(q, 10)
+    wd, wl = oracle.pq_search(cb, codes, None, q, 10, 0)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "gemm near-equal sums")
+    assert enc.last_uncertified() >= 1
+    enc.close()
