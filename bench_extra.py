@@ -46,6 +46,7 @@ class Timer:
             one = max(e0.elapsed_time(e1), 1e-3)
             steps = int(min(5000, max(steps, min_ms / one)))
         _lib.prof_read(reset=True)
+        _lib.prof_read_aux(reset=True)
         _lib.prof_enable(True)
         l0 = _lib.launch_count()
         t0 = time.time()
@@ -60,8 +61,10 @@ class Timer:
         t1 = time.time()
         _lib.prof_enable(False)
         k_ms, k_n, k_units = _lib.prof_read(reset=True)
+        a_ms, a_n, a_units = _lib.prof_read_aux(reset=True)
         return {"ms": e0.elapsed_time(e1) / steps, "steps": steps, "kernel_ms": (k_ms / k_n) if k_n else None,
-                "kernel_launches": k_n, "launches": _lib.launch_count() - l0,
+                "kernel_launches": k_n, "kernel_ms_per_step": k_ms / steps, "aux_ms_per_step": a_ms / steps,
+                "aux_bytes_per_step": a_units / steps, "launches": _lib.launch_count() - l0,
                 "clocks": self.sampler.window(t0, t1) if self.sampler else None}
 
 
@@ -173,16 +176,19 @@ def config_c3(ctx):
     e2e_ms = _host_timer(lambda: enc.search_into(hq, K, KP, hd, hl), 2, warm=1)
     lookups = float(Q) * N * M
     out = {"name": "C3", "workload": f"PQ ADC scan M=96 nbits=8 over {N} x 768 codes + fp32 re-rank k'=100 -> k=10, 256 queries",
-           "value": Q / (t["ms"] * 1e-3), "unit": "queries/s", "ms_per_step": t["ms"], "steps": t["steps"], "dtype": "u8 codes, u16/u32 coarse sums, f32 exact",
+           "value": Q / (t["ms"] * 1e-3), "unit": "queries/s", "ms_per_step": t["ms"], "steps": t["steps"], "dtype": "u8 codes; coarse f16 x f16 -> f32 (batch) or u16/u32 table sums (one query); exact stage f32",
            "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 12, "uncertified": enc.last_uncertified()},
-           "roofline": _roof_hbm(float(N) * M, t1["kernel_ms"], ctx["peaks"],
-                                 "adc_coarse_kernel<1,3> (one query per pass: N*M code bytes)"),
-           "batch_scan": {"queries_per_pass": 4, "passes": Q // 4, "kernel_ms": t["kernel_ms"],
-                          "lookups_per_s": lookups / (t["kernel_ms"] * 1e-3) if t["kernel_ms"] else None,
-                          "bound": "shared-memory look-up rate: 8 B per (row, sub-quantiser) for 4 queries, "
-                                   "128 B/clk/SM (tools/micro/lds_rate.cu)",
-                          "smem_bytes_per_s": lookups * 2 / (t["kernel_ms"] * 1e-3) if t["kernel_ms"] else None},
+           # dominant kernel of the batch: the dense tensor-core scan over the decoded fp16 slabs (2 Q N D flop per step);
+           # the decode that feeds it is HBM-bound and reported beside it, as is the one-query look-up pass
+           "roofline": _roof_tensor(2.0 * Q * N * D, t["kernel_ms_per_step"], ctx["peaks"],
+                                    "dense_scan_tc<f16,L2> over decoded slabs (3 launches per step; time = their sum)",
+                                    "batched PQ coarse stage: decode to fp16 (pq_decode_kernel) + tensor-core scan + exact fp32 "
+                                    "table sums of the candidates + certification (csrc/pq_gemm.cu)"),
+           "decode": _roof_hbm(t["aux_bytes_per_step"], t["aux_ms_per_step"], ctx["peaks"],
+                               "pq_decode_kernel<8> (per step: N*M code bytes in, N*D*2 bytes out)"),
+           "single_query_roofline": _roof_hbm(float(N) * M, t1["kernel_ms"], ctx["peaks"],
+                                              "adc_coarse_kernel<1,3> (one query per pass: N*M code bytes)"),
            "single_query": {"ms_per_call": t1["ms"], "scan_kernel_ms": t1["kernel_ms"]},
            "gpu_launches": t["launches"], "clocks": t["clocks"], "checks": {}}
     if ctx["cpu"]:
@@ -198,9 +204,13 @@ def config_c3(ctx):
                                          f"(raw vectors stay on the GPU), {oracle.fast_isa()} gather + OpenMP, {dt:.2f} s"}
         # checker: O-exact (sequential fp32 sum in j, simd.go:345-355) on 8 queries, bit-equal ids and distances
         enc.attach_raw(None)
-        gd, gl = enc.search(hq[:8], K)
+        gd, gl = enc.search(hq[:8], K)          # 8 queries: the look-up path
         ed, el = oracle.pq_search(cbh, ch, None, hq[:8], K, 0)
         out["checks"]["adc_topk_equals_exact_oracle_8q"] = bool(np.array_equal(gl, el) and np.array_equal(gd, ed))
+        gdb, glb = enc.search(hq, K)            # the whole batch: decode + tensor-core coarse stage
+        out["checks"]["adc_topk_batch_path_equals_exact_oracle_8q"] = bool(np.array_equal(glb[:8], el) and
+                                                                           np.array_equal(gdb[:8], ed))
+        out["batch_path_uncertified"] = enc.last_uncertified()
     enc.close()
     raw.close()
     return out

@@ -375,6 +375,9 @@ int lb_set_option(const char *name, int value);
  * (queries x rows) pairs those launches scanned, and (reset != 0) clears them. */
 int lb_prof_enable(int on);
 int lb_prof_read(double *total_ms, int64_t *launches, double *units, int reset);
+/* Second channel: auxiliary streaming kernels with a roofline of their own (the batched PQ path's decode; units =
+ * bytes moved).  Same semantics. */
+int lb_prof_read_aux(double *total_ms, int64_t *launches, double *units, int reset);
 
 #ifdef __cplusplus
 }

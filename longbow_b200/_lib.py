@@ -111,6 +111,7 @@ SIGNATURES = {
     "lb_set_option": (i32, [C.c_char_p, i32]),
     "lb_prof_enable": (i32, [i32]),
     "lb_prof_read": (i32, [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double), i32]),
+    "lb_prof_read_aux": (i32, [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double), i32]),
 }
 
 _lib = None
@@ -160,4 +161,11 @@ def prof_read(reset: bool = True):
     """(total_ms, launches, query-row pairs scanned) of the dominant scan kernel since the last reset."""
     ms, n, u = C.c_double(), i64(), C.c_double()
     load().lb_prof_read(C.byref(ms), C.byref(n), C.byref(u), int(reset))
+    return ms.value, n.value, u.value
+
+
+def prof_read_aux(reset: bool = True):
+    """(total_ms, launches, bytes moved) of the auxiliary streaming kernels (the batched PQ path's decode)."""
+    ms, n, u = C.c_double(), i64(), C.c_double()
+    load().lb_prof_read_aux(C.byref(ms), C.byref(n), C.byref(u), int(reset))
     return ms.value, n.value, u.value

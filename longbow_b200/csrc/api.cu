@@ -108,13 +108,16 @@ static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off
 // ---- dominant-kernel timing (lb_prof_*)
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
-static double g_prof_units = 0;  // sum over bracketed launches of (queries x rows) scanned
+// channel 0: the dominant scan kernel (units = queries x rows); channel 1: auxiliary streaming kernels worth their own
+// roofline line (the PQ decode: units = bytes moved)
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events[2];
+static double g_prof_units[2] = {0, 0};
 struct ProfScope {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaStream_t st;
     double units;
-    ProfScope(cudaStream_t s, double u) : st(s), units(u) {
+    int ch;
+    ProfScope(cudaStream_t s, double u, int channel = 0) : st(s), units(u), ch(channel) {
         if (g_prof_on.load(std::memory_order_relaxed)) {
             if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, st);
             else e0 = e1 = nullptr;
@@ -124,8 +127,8 @@ struct ProfScope {
         if (e0 && e1) {
             cudaEventRecord(e1, st);
             std::lock_guard<std::mutex> g(g_prof_mu);
-            g_prof_events.emplace_back(e0, e1);
-            g_prof_units += units;
+            g_prof_events[ch].emplace_back(e0, e1);
+            g_prof_units[ch] += units;
         }
     }
 };
@@ -431,11 +434,11 @@ int lb_prof_enable(int on) {
     g_prof_on.store(on ? 1 : 0);
     return LB_OK;
 }
-int lb_prof_read(double* total_ms, int64_t* launches, double* units, int reset) {
+static int prof_read_channel(int ch, double* total_ms, int64_t* launches, double* units, int reset) {
     std::lock_guard<std::mutex> g(g_prof_mu);
     double tot = 0;
     int64_t n = 0;
-    for (auto& pr : g_prof_events) {
+    for (auto& pr : g_prof_events[ch]) {
         float ms = 0;
         if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
             tot += ms;
@@ -443,15 +446,21 @@ int lb_prof_read(double* total_ms, int64_t* launches, double* units, int reset) 
         }
     }
     cudaGetLastError();
-    if (units) *units = g_prof_units;
+    if (units) *units = g_prof_units[ch];
     if (reset) {
-        for (auto& pr : g_prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-        g_prof_events.clear();
-        g_prof_units = 0;
+        for (auto& pr : g_prof_events[ch]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        g_prof_events[ch].clear();
+        g_prof_units[ch] = 0;
     }
     if (total_ms) *total_ms = tot;
     if (launches) *launches = n;
     return LB_OK;
+}
+int lb_prof_read(double* total_ms, int64_t* launches, double* units, int reset) {
+    return prof_read_channel(0, total_ms, launches, units, reset);
+}
+int lb_prof_read_aux(double* total_ms, int64_t* launches, double* units, int reset) {
+    return prof_read_channel(1, total_ms, launches, units, reset);
 }
 int64_t lb_kernel_launch_count(void) { return g_launches.load(); }
 
@@ -1715,8 +1724,11 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
             for (int sl = 0; sl < n_slabs; sl++) {
                 const int64_t r0 = (int64_t)sl * slab_rows;
                 const int64_t rn = (pq->size - r0) < slab_rows ? (pq->size - r0) : slab_rows;
-                CK(launch_pq_decode(pq->codes, pq->codebook16, pq->M, pq->sub, (uint32_t)r0, (uint32_t)rn, slab, pq->sm_count,
-                                    st));
+                {
+                    ProfScope prof(st, (double)rn * ((double)pq->dims * 2 + pq->M), 1);  // bytes written + code bytes read
+                    CK(launch_pq_decode(pq->codes, pq->codebook16, pq->M, pq->sub, (uint32_t)r0, (uint32_t)rn, slab,
+                                        pq->sm_count, st));
+                }
                 ScanArgs a;
                 a.dtype = DT_F16; a.metric = METRIC_L2; a.db = slab; a.aux = pq->xn2 + r0; a.n_rows = (uint32_t)rn;
                 a.dim = pq->dims; a.queries = q16; a.nq = cq;
