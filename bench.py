@@ -377,14 +377,14 @@ def main():
         q1 = d_qs[0, :1].contiguous()
         o1d = torch.empty((1, K), dtype=torch.float32, device=dev)
         o1l = torch.empty((1, K), dtype=torch.int64, device=dev)
-        for _ in range(5):
+        for _ in range(40):   # the e2e arm before this leaves the GPU half idle: let the clocks settle under this load
             sidx.search_device(q1, K, o1d, o1l)
         torch.cuda.synchronize()
         _lib.prof_read(reset=True)
         _lib.prof_enable(True)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        n1 = 20
+        n1 = 200
         for i in range(n1):
             sidx.search_device(d_qs[(i % (warm + steps)), :1], K, o1d, o1l)
         s1.record()

@@ -1370,7 +1370,19 @@ int lb_pq_create(int device, const void* blob, size_t blob_len, lb_pq** out) {
     if (e != cudaSuccess) { delete pq; return fail_cuda(e, "cudaMalloc(codebooks)"); }
     e = cudaMemcpy(pq->codebooks, (const char*)blob + 12, (size_t)M * K * sub * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(pq->codebooks); delete pq; return fail_cuda(e, "cudaMemcpy(codebooks)"); }
-    if (pq_gemm_eligible(dims, M, sub)) {
+    // fp16 copy for the batched tensor-core coarse stage -- only when every centroid component survives the trip
+    // (finite and far from the fp16 range limit; the certification bound assumes relative 2^-11 rounding)
+    bool fp16_ok = pq_gemm_eligible(dims, M, sub);
+    if (fp16_ok) {
+        const float* cbh = reinterpret_cast<const float*>((const char*)blob + 12);
+        for (size_t i = 0; i < (size_t)M * K * sub; i++) {
+            float v;
+            memcpy(&v, cbh + i, 4);
+            v = v < 0 ? -v : v;
+            if (!(v <= 1.0e4f)) { fp16_ok = false; break; }   // also catches NaN / inf
+        }
+    }
+    if (fp16_ok) {
         e = cudaMalloc(&pq->codebook16, (size_t)M * K * sub * 2);
         if (e == cudaSuccess) e = launch_pq_codebook16(pq->codebooks, pq->codebook16, (size_t)M * K * sub, cudaStreamPerThread);
         if (e == cudaSuccess) e = cudaMalloc((void**)&pq->cnorm2, (size_t)M * 256 * 4);

@@ -11,7 +11,7 @@ g = torch.Generator(device=dev).manual_seed(1)
 SECS = float(os.environ.get("SECS", "2.5"))
 WORK = os.environ.get("WORK", "c2")
 if WORK == "c2":
-    N, D, NQ, K = 1_000_000, 768, 1024, 100
+    N, D, NQ, K = int(os.environ.get("ROWS", "1000000")), 768, 1024, 100
     db = torch.randn((N, D), generator=g, device=dev); db = (db / db.norm(dim=1, keepdim=True)).half()
     qs = torch.randn((NQ, D), generator=g, device=dev); qs = (qs / qs.norm(dim=1, keepdim=True)).half()
     idx = gpu.DenseIndex(D, np.float16, _lib.METRIC_COSINE)
@@ -34,7 +34,9 @@ cases = (sys.argv[1] if len(sys.argv) > 1 else "0,1,32,128,mm,0").split(",")
 a = torch.randn((8192, 8192), device=dev, dtype=torch.bfloat16); b = torch.randn((8192, 8192), device=dev, dtype=torch.bfloat16)
 for dbg in cases:
     mm = dbg == "mm"
-    if not mm:
+    if dbg.startswith("boot"):      # "boot8": tc_boot_tiles = 8 (0 = automatic)
+        _lib.set_option("tc_debug", 0); _lib.set_option("tc_boot_tiles", int(dbg[4:]))
+    elif not mm:
         _lib.set_option("tc_debug", int(dbg))
     run = (lambda: torch.matmul(a, b)) if mm else (lambda: idx.search_device(qs, K, od, ol))
     for _ in range(5): run()
@@ -55,4 +57,4 @@ for dbg in cases:
     extra = f"TF/s {2 * 8192**3 / per / 1e9:.0f}" if mm else f"scan_ms {ms / max(cnt, 1):.4f}"
     print(f"case {dbg} ms/iter {per:.4f} {extra} sm_mhz {statistics.median(s.mhz[half:])} "
           f"power_w {statistics.median(s.w[half:]):.0f} max_w {max(s.w):.0f}", flush=True)
-_lib.set_option("tc_debug", 0)
+_lib.set_option("tc_debug", 0); _lib.set_option("tc_boot_tiles", 0)
