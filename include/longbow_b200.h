@@ -367,7 +367,10 @@ int64_t lb_kernel_launch_count(void);
  * "f32_tc": 3xTF32 tensor-core scan for fp32 indexes on/off.  "tc_boot_tiles": bootstrap sample size.
  * "tc_boot": 1 (default) = bootstrap-threshold pre-scan for the tensor-core path, 0 = off.
  * "tc_debug": timing probes of the tensor-core scan; results are INVALID when non-zero.
- * "pq_scan": 0 = auto, 1 = exhaustive fp32 ADC kernel, 2 = coarse scan one query per pass, 3 = four per pass. */
+ * "pq_scan": 0 = auto (look-up passes below 64 queries per call, decode + tensor-core coarse stage from 64 up),
+ *            1 = exhaustive fp32 ADC kernel, 2 = coarse look-up scan one query per pass, 3 = four per pass,
+ *            4 = decode the codes to fp16 slabs and run the dense tensor-core scan (csrc/pq_gemm.cu).
+ * Every mode returns the same (id, distance) pairs: the coarse stages only pick candidates for the exact stage. */
 int lb_set_option(const char *name, int value);
 /* Profiling hook for bench.py's roofline: when enabled, every search brackets its dominant
  * kernel (the coarse distance scan: dense or ADC) with CUDA events on the launching stream.

@@ -206,3 +206,23 @@ def test_gemm_coarse_ties_and_certification(oracle, pq_mode):
     assert_topk_equal(gd, gl, wd, wl, 0.0, "gemm near-equal sums")
     assert enc.last_uncertified() >= 1
     enc.close()
+
+
+def test_gemm_path_declines_out_of_range_codebooks(oracle, pq_mode):
+    """Centroid components beyond the fp16 comfort zone: no fp16 codebook is built, a 70-query batch takes the look-up
+    passes (forcing mode 4 is refused) and the answers are the oracle's."""
+    from longbow_b200 import _lib, pq
+    rng = np.random.default_rng(11)
+    M, sub, n = 16, 4, 20000
+    cb, codes = _setup(rng, n, M, sub)
+    cb = (cb * 3.0e4).astype(np.float32)
+    q = (rng.standard_normal((70, M * sub)) * 3.0e4).astype(np.float32)
+    enc = pq.PQEncoder(M * sub, M, 256, cb)
+    enc.add_codes(codes)
+    gd, gl = enc.search(q, 10)
+    wd, wl = oracle.pq_search(cb, codes, None, q, 10, 0)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "large centroids")
+    pq_mode(4)
+    with pytest.raises(_lib.LongbowError):
+        enc.search(q, 10)
+    enc.close()
