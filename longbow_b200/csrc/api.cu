@@ -1716,12 +1716,12 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
         // slab and the dense scan runs at its tensor rate.
         const bool gemm_ok = pq->codebook16 != nullptr && pq->xn2 != nullptr && pq->tiled != nullptr && pq->M <= 96 && pq->size >= 4096 &&
                              dense_tc_eligible(DT_F16, pq->dims, pq->codebook16, pq->codebook16, 2 * kout + 64);
-        if (mode == 4 && !gemm_ok) return fail(LB_ERR_UNSUPPORTED, "decode + tensor-core PQ scan not eligible");
-        if (mode == 4 || (mode == 0 && gemm_ok && cq >= 64)) {
+        if (mode == 4 && (!gemm_ok || kout > 704))
+            return fail(LB_ERR_UNSUPPORTED, "decode + tensor-core PQ scan not eligible");
+        if (mode == 4 || (mode == 0 && gemm_ok && cq >= 64 && kout <= 704)) {
             int kg = 2 * kout;  // wider candidate margin than the look-up path: the fp16 rounding bound is looser
             if (kg < kc) kg = kc;
             if (kg > 704) kg = 704;
-            if (kg < kout) return fail(LB_ERR_UNSUPPORTED, "k' too large for the tensor-core PQ scan");
             void* q16; float* qn; void* slab; uint64_t *all, *merged, *exact;
             const int64_t slab_rows_max = 4 << 20;   // 4 Mi rows per slab (6 GiB at 768 dims)
             const int64_t slab_rows = pq->size < slab_rows_max ? ((pq->size + 255) / 256) * 256 : slab_rows_max;
