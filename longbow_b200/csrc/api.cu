@@ -1718,7 +1718,7 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
                              dense_tc_eligible(DT_F16, pq->dims, pq->codebook16, pq->codebook16, 2 * kout + 64);
         if (mode == 4 && (!gemm_ok || kout > 704))
             return fail(LB_ERR_UNSUPPORTED, "decode + tensor-core PQ scan not eligible");
-        if (mode == 4 || (mode == 0 && gemm_ok && cq >= 64 && kout <= 704)) {
+        if (mode == 4 || (mode == 0 && gemm_ok && cq >= 64 && kout <= 352)) {  // auto: only with the full 2 k' margin
             int kg = 2 * kout;  // wider candidate margin than the look-up path: the fp16 rounding bound is looser
             if (kg < kc) kg = kc;
             if (kg > 704) kg = 704;
