@@ -451,6 +451,91 @@ __device__ __forceinline__ void rc_gather(unsigned char* stage, const unsigned c
     }
 }
 
+// One of the four interleaved partial sums of ExactAcc (elements i = 4m + t, increasing m): what ONE lane of a quad
+// accumulates when four lanes share a (query, row) pair.
+template <int METRIC> struct QuadPart;
+template <> struct QuadPart<METRIC_L2> {
+    float s;
+    __device__ __forceinline__ void init() { s = 0.f; }
+    __device__ __forceinline__ void add(float a, float b) {
+        const float d = __fsub_rn(a, b);
+        s = __fadd_rn(s, __fmul_rn(d, d));
+    }
+    // gather the quad's four partial sums (lanes 4c .. 4c+3) into the reference accumulator
+    __device__ __forceinline__ void collect(ExactAcc<METRIC_L2>& acc, int lane) const {
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc.s[j] = __shfl_sync(0xffffffffu, s, (lane & ~3) + j);
+    }
+};
+template <> struct QuadPart<METRIC_DOT> {
+    float s;
+    __device__ __forceinline__ void init() { s = 0.f; }
+    __device__ __forceinline__ void add(float a, float b) { s = __fadd_rn(s, __fmul_rn(a, b)); }
+    __device__ __forceinline__ void collect(ExactAcc<METRIC_DOT>& acc, int lane) const {
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc.s[j] = __shfl_sync(0xffffffffu, s, (lane & ~3) + j);
+    }
+};
+template <> struct QuadPart<METRIC_COSINE> {
+    float d, na, nb;
+    __device__ __forceinline__ void init() { d = na = nb = 0.f; }
+    __device__ __forceinline__ void add(float a, float b) {
+        d = __fadd_rn(d, __fmul_rn(a, b));
+        na = __fadd_rn(na, __fmul_rn(a, a));
+        nb = __fadd_rn(nb, __fmul_rn(b, b));
+    }
+    __device__ __forceinline__ void collect(ExactAcc<METRIC_COSINE>& acc, int lane) const {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            acc.d[j] = __shfl_sync(0xffffffffu, d, (lane & ~3) + j);
+            acc.na[j] = __shfl_sync(0xffffffffu, na, (lane & ~3) + j);
+            acc.nb[j] = __shfl_sync(0xffffffffu, nb, (lane & ~3) + j);
+        }
+    }
+};
+
+// Cooperative gather, QUAD form (fp32 rows): up to 8 rows per trip, lane 4c + t accumulates partial sum t of row c --
+// the reference's four interleaved sums, one per lane, so all 32 lanes work when a trip holds few rows (a graph
+// expansion brings ~7 new nodes on average: one lane per row left 24 lanes idle for 384 dependent steps).  Same
+// staging and cp.async pipeline as rc_gather<.., 8>; `part` ends up with this lane's partial sum.
+template <int ACC, int NBUF>
+__device__ __forceinline__ void rc_gather_quad(unsigned char* stage, const unsigned char* const (&src_row)[8],
+                                               const bool (&src_ok)[8], size_t row_bytes, int n_chunks, int dim,
+                                               const float* qf, bool ok, int lane, QuadPart<ACC>& part) {
+    constexpr int ROWS = 8;
+    constexpr int PIECES = RC_CHUNK / 16;
+    const int c = lane >> 2, t = lane & 3;
+    auto issue = [&](int ch) {
+        unsigned char* dstb = stage + (size_t)(ch % NBUF) * ROWS * RC_PITCH + (lane & 7) * 16;
+        const size_t off = (size_t)ch * RC_CHUNK;
+        const bool in_row = off + (size_t)(lane & 7) * 16 < row_bytes;
+#pragma unroll
+        for (int i = 0; i < ROWS / 4; i++) {
+            if (src_ok[i] && in_row) cp_async16(dstb + (size_t)(4 * i + (lane >> 3)) * RC_PITCH, src_row[i] + off);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int p = 0; p < NBUF - 1; p++) {
+        if (p < n_chunks) issue(p); else cp_async_commit();
+    }
+    for (int ch = 0; ch < n_chunks; ch++) {
+        if (ch + NBUF - 1 < n_chunks) issue(ch + NBUF - 1); else cp_async_commit();
+        cp_async_wait<NBUF - 1>();
+        __syncwarp();
+        if (ok) {
+            const float* rowp = reinterpret_cast<const float*>(stage + (size_t)(ch % NBUF) * ROWS * RC_PITCH +
+                                                               (size_t)c * RC_PITCH) + t;
+            const int e0 = ch * (RC_CHUNK / 4) + t;
+#pragma unroll
+            for (int p = 0; p < PIECES; p++) {
+                if (e0 + 4 * p < dim) part.add(qf[e0 + 4 * p], rowp[4 * p]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __host__ __device__ __forceinline__ int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;

@@ -34,9 +34,11 @@ int api_rerank_device(lb_index* idx, const void* d_q, int64_t nq, const uint32_t
                       const uint64_t* d_allow, float* d_dist, int64_t* d_lab, cudaStream_t st);
 
 bool g_hnsw_coop = true;  // lb_set_option("hnsw_coop")
-constexpr int HN_WARPS = 4;            // queries per CTA
+constexpr int HN_WARPS_MAX = 8;        // queries (warps) per CTA: 4..8, chosen at launch for the most resident warps
 constexpr uint32_t HN_EMPTY = 0xffffffffu;
 constexpr int HN_SR = 48;              // staging row-buffers per warp (trips of 16 rows, 3 chunks in flight)
+constexpr int HN_SR_QUAD = 24;         // fp32 rows, quad form: trips of 8 rows, 3 chunks in flight
+template <typename T> __host__ __device__ constexpr int hn_stage_rows() { return sizeof(T) == 4 ? HN_SR_QUAD : HN_SR; }
 
 struct HnswArgs {
     const void* db;
@@ -92,17 +94,17 @@ __device__ __forceinline__ uint64_t heap_pop(uint64_t* h, int& n, bool maxheap) 
 }
 
 template <typename T, int METRIC>
-__global__ void __launch_bounds__(HN_WARPS * 32)
+__global__ void __launch_bounds__(HN_WARPS_MAX * 32)
 hnsw_search_layer_kernel(const HnswArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * HN_WARPS + warp;
+    const int q = blockIdx.x * (int)(blockDim.x >> 5) + warp;
     // per-warp regions: query (fp32) | result heap [ef + 1] | candidate heap [cand_cap]
     const size_t q_bytes = ((size_t)a.dim * 4 + 15) & ~(size_t)15;
     const size_t heap_bytes = (((size_t)(a.ef + 1 + a.cand_cap) * 8) + 15) & ~(size_t)15;  // cp.async needs 16-byte slots
-    const size_t per_warp = q_bytes + heap_bytes + (a.coop ? (size_t)HN_SR * RC_PITCH : 0);
+    const size_t per_warp = q_bytes + heap_bytes + (a.coop ? (size_t)hn_stage_rows<T>() * RC_PITCH : 0);
     unsigned char* base = smem_raw + (size_t)warp * per_warp;
-    unsigned char* stage = base + q_bytes + heap_bytes;  // [HN_SR][RC_PITCH] when coop
+    unsigned char* stage = base + q_bytes + heap_bytes;  // [hn_stage_rows][RC_PITCH] when coop
     float* qf = reinterpret_cast<float*>(base);
     uint64_t* res = reinterpret_cast<uint64_t*>(base + q_bytes);
     uint64_t* cand = res + (a.ef + 1);
@@ -191,6 +193,36 @@ hnsw_search_layer_kernel(const HnswArgs a) {
                 cnb = __shfl_sync(0xffffffffu, nb, src < 32 ? src : 0);
                 const size_t row_bytes = (size_t)a.dim * sizeof(T);
                 const int n_chunks = (int)((row_bytes + RC_CHUNK - 1) / RC_CHUNK);
+                if constexpr (sizeof(T) == 4) {
+                    // fp32 rows: trips of 8, four lanes per row (rc_gather_quad)
+                    for (int base_i = 0; base_i < nfresh; base_i += 8) {
+                        const unsigned char* src_row[8];
+                        bool src_ok[8];
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const int r = 4 * i + (lane >> 3);
+                            const int sl = base_i + r;
+                            const uint32_t rid = __shfl_sync(0xffffffffu, cnb, sl < 32 ? sl : 0);
+                            src_ok[i] = sl < nfresh;
+                            src_row[i] = reinterpret_cast<const unsigned char*>(db) + (size_t)rid * row_bytes + (lane & 7) * 16;
+                        }
+#pragma unroll
+                        for (int i = 2; i < 8; i++) { src_ok[i] = false; src_row[i] = nullptr; }
+                        QuadPart<METRIC> part;
+                        part.init();
+                        const bool okq = base_i + (lane >> 2) < nfresh;   // this lane's quad holds a row
+                        rc_gather_quad<METRIC, HN_SR_QUAD / 8>(stage, src_row, src_ok, row_bytes, n_chunks, a.dim, qf, okq, lane, part);
+                        ExactAcc<METRIC> acc;
+                        part.collect(acc, lane);
+                        float dd = acc.finish();
+                        if (METRIC == METRIC_DOT) dd = -dd;
+                        dd = __fadd_rn(dd, 0.f);
+                        // the replay wants row j of the trip in lane base_i + j
+                        const int from = 4 * (lane - base_i);
+                        const float got = __shfl_sync(0xffffffffu, dd, (from >= 0 && from < 32) ? from : 0);
+                        if (lane >= base_i && lane < base_i + 8 && lane < nfresh) d = got;
+                    }
+                } else
                 for (int base_i = 0; base_i < nfresh; base_i += 16) {   // trips of 16 rows (HN_SR = 48 row buffers)
                     const int mine_i = lane - base_i;                   // row slot of this lane in the trip
                     const bool okc = lane >= base_i && lane < nfresh && mine_i < 16;
@@ -301,13 +333,27 @@ template <typename T>
 static cudaError_t launch_hnsw_t(const HnswArgs& a, int metric, cudaStream_t st) {
     const size_t q_bytes = ((size_t)a.dim * 4 + 15) & ~(size_t)15;
     const size_t heap_bytes = (((size_t)(a.ef + 1 + a.cand_cap) * 8) + 15) & ~(size_t)15;
-    const size_t smem = (size_t)HN_WARPS * (q_bytes + heap_bytes + (a.coop ? (size_t)HN_SR * RC_PITCH : 0));
-    const int grid = (a.nq + HN_WARPS - 1) / HN_WARPS;
+    const size_t per_warp = q_bytes + heap_bytes + (a.coop ? (size_t)hn_stage_rows<T>() * RC_PITCH : 0);
+    // Warps per CTA: the walk is a chain of dependent memory round trips, so what matters is how many queries are
+    // resident.  Pick the CTA size that packs the most warps into an SM's shared memory (1 KiB reserved per CTA,
+    // 64 registers per thread): 4096 queries of C5w fit one wave of 148 x 28.
+    int wpc = 4, best = 0;
+    for (int w = 4; w <= HN_WARPS_MAX; w++) {
+        const size_t cta = (size_t)w * per_warp + 1024;
+        int ctas = (int)(233472 / cta);
+        if (ctas > 32 / w) ctas = 32 / w;          // register file: 64 regs x 32 lanes x w warps per CTA
+        if (ctas * w > best) { best = ctas * w; wpc = w; }
+    }
+    const size_t smem = (size_t)wpc * per_warp;
+    const int grid = (a.nq + wpc - 1) / wpc;
 #define LB_HN(M)                                                              \
     {                                                                         \
         auto kern = hnsw_search_layer_kernel<T, M>;                           \
         LB_SMEM_OPTIN(kern);                                                  \
-        kern<<<grid, HN_WARPS * 32, smem, st>>>(a);                           \
+        static std::atomic<int> carve_{0};                                    \
+        if (!carve_.exchange(1))                                              \
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+        kern<<<grid, wpc * 32, smem, st>>>(a);                                \
     }
     switch (metric) {
         case METRIC_L2: LB_HN(METRIC_L2) break;
@@ -409,7 +455,9 @@ static int graph_walk(lb_graph* g, const void* d_q, int64_t nq, const uint32_t* 
     a.neighbors = g->neighbors; a.counts = g->counts; a.max_degree = g->max_degree;
     a.queries = d_q; a.entries = d_entries; a.ef = ef;
     const int n2 = next_pow2(ef + 1 > 2 ? ef + 1 : 2);
-    a.cand_cap = next_pow2(2 * ef + 64);  // power of two: the prune step sorts it in place
+    // power of two (the prune step sorts it in place).  2 ef is enough: a prune keeps only candidates not worse than
+    // the worst result, and every such candidate is itself in the result set -- at most ef of them (plus exact ties)
+    a.cand_cap = next_pow2(2 * ef);
     if (a.cand_cap < n2) a.cand_cap = n2;
     uint32_t ht = 4096;
     while (ht < (uint32_t)ef * 96u) ht <<= 1;

@@ -10,7 +10,7 @@ import torch
 from longbow_b200 import _lib, gpu, store
 
 dev = torch.device("cuda", 0)
-N, D, Q, EF, K, DEG, KNN = 200_000, 384, 2048, 128, 10, 32, 24
+N, D, Q, EF, K, DEG, KNN = 200_000, 384, int(os.environ.get("Q", "2048")), 128, 10, 32, 24
 g = torch.Generator(device=dev).manual_seed(5101)
 db = torch.randn((N, D), generator=g, device=dev)
 idx = gpu.DenseIndex(D, np.float32, _lib.METRIC_L2)
