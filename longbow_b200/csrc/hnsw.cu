@@ -169,12 +169,7 @@ hnsw_search_layer_kernel(const HnswArgs a) {
             if (i < cnt) nb = __ldg(a.neighbors + (size_t)cid * a.max_degree + i);
             // a duplicate inside one list is "already visited" for every occurrence but the first (the reference
             // marks sequentially): a lane defers to any lower lane holding the same id
-            bool dup = false;
-#pragma unroll 4
-            for (int l = 0; l < 31; l++) {
-                const uint32_t o = __shfl_sync(0xffffffffu, nb, l);
-                if (l < lane && o == nb) dup = true;
-            }
+            const bool dup = (__match_any_sync(0xffffffffu, nb) & ((1u << lane) - 1u)) != 0u;
             int fresh = 0;
             if (nb < a.n_rows && !dup) fresh = visit(nb);
             if (fresh < 0) { failed = true; fresh = 0; }
@@ -255,6 +250,16 @@ hnsw_search_layer_kernel(const HnswArgs a) {
             }
             // replay in list order through the acceptance test (arrow_hnsw.go:1349-1370)
             unsigned m = a.coop ? (nfresh >= 32 ? 0xffffffffu : ((1u << nfresh) - 1u)) : fm;
+            {
+                // Once the result set is full, a node at or beyond the CURRENT worst result can never be accepted by
+                // the replay (the worst only improves while the list is walked): drop those lanes up front.
+                float worst0 = 3.402823466e+38f;
+                int full0 = 0;
+                if (lane == 0 && nr >= a.ef) { worst0 = key_of(res[0]); full0 = 1; }
+                worst0 = __shfl_sync(0xffffffffu, worst0, 0);
+                full0 = __shfl_sync(0xffffffffu, full0, 0);
+                if (full0) m &= __ballot_sync(0xffffffffu, d < worst0);
+            }
             while (m) {
                 const int l = __ffs(m) - 1;
                 m &= m - 1;
