@@ -527,9 +527,15 @@ __device__ __forceinline__ void rc_gather_quad(unsigned char* stage, const unsig
             const float* rowp = reinterpret_cast<const float*>(stage + (size_t)(ch % NBUF) * ROWS * RC_PITCH +
                                                                (size_t)c * RC_PITCH) + t;
             const int e0 = ch * (RC_CHUNK / 4) + t;
+            const float* qp = qf + e0;
+            if ((ch + 1) * (RC_CHUNK / 4) <= dim) {   // chunk entirely inside the row: no per-piece test
 #pragma unroll
-            for (int p = 0; p < PIECES; p++) {
-                if (e0 + 4 * p < dim) part.add(qf[e0 + 4 * p], rowp[4 * p]);
+                for (int p = 0; p < PIECES; p++) part.add(qp[4 * p], rowp[4 * p]);
+            } else {
+#pragma unroll
+                for (int p = 0; p < PIECES; p++) {
+                    if (e0 + 4 * p < dim) part.add(qp[4 * p], rowp[4 * p]);
+                }
             }
         }
         __syncwarp();
