@@ -220,15 +220,16 @@ def main():
     log("index resident")
     # N > 1: the exchange (peer-memory push + signal + merge, csrc/exchange.cu) of batch s runs on ONE side stream,
     # in batch order on every rank, under the scan of batch s + 1.
-    n_streams = 2
+    n_streams = int(os.environ.get("LB_BENCH_STREAMS", "2"))
     overlap = world > 1
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
-    outs = [(out_d, out_l), (torch.empty_like(out_d), torch.empty_like(out_l))]
+    outs = [(out_d, out_l)] + [(torch.empty_like(out_d), torch.empty_like(out_l)) for _ in range(n_streams - 1)]
 
     def run_steps(first, count):
         for s in range(first, first + count):
             with torch.cuda.stream(streams[s % n_streams]):
-                sidx.search_device(d_qs[s % d_qs.shape[0]], K, outs[s % 2][0], outs[s % 2][1], overlap=overlap)
+                sidx.search_device(d_qs[s % d_qs.shape[0]], K, outs[s % n_streams][0], outs[s % n_streams][1],
+                                   overlap=overlap)
 
     def join_streams():
         cur = torch.cuda.current_stream()
@@ -267,15 +268,15 @@ def main():
         per_rank = {"region_ms": [round(float(x[0]), 3) for x in allr],
                     "scan_kernel_ms": [round(float(x[1]), 4) for x in allr]}
         ms = float(t.item())
-    check_l = outs[(warm + steps - 1) % 2][1].cpu().numpy()  # the last timed batch
-    check_d = outs[(warm + steps - 1) % 2][0].cpu().numpy()
+    check_l = outs[(warm + steps - 1) % n_streams][1].cpu().numpy()  # the last timed batch
+    check_d = outs[(warm + steps - 1) % n_streams][0].cpu().numpy()
     if ms < 600.0:
         # timed region too short for the 10 ms NVML sampler: keep the same load running for ~1 s more.  The number
         # of extra batches is derived from the all-reduced time, so every rank issues the same exchanges.
         extra = int(min(20000, max(4, 1000.0 / max(ms / steps, 1e-3))))
-        extra += extra % 2
-        for _ in range(extra // 2):
-            run_steps(warm + steps, 2)
+        extra += (-extra) % n_streams
+        for _ in range(extra // n_streams):
+            run_steps(warm + steps, n_streams)
         join_streams()
         torch.cuda.synchronize()
     main_clocks = sampler.summary()

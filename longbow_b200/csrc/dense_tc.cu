@@ -24,6 +24,7 @@
 namespace lb {
 
 bool g_tc_pair = true;  // lb_set_option("tc_pair"): CTA-pair (cta_group::2) scan on / off
+int g_tc_reserve_sms = 0;
 
 enum { KIND_F16 = 0, KIND_I8 = 1, KIND_TF32 = 2 };
 static_assert(LB_NEDGE == 16, "the epilogue unpacks four uint4 of ladder counters");
@@ -1059,7 +1060,12 @@ void dense_scan_tc_plan(int nq, int n_row_tiles, int sm_count, int kc, int* grou
     int cap = next_pow2(kc + TC_N);
     if (cap < 512) cap = 512;
     const int nqb = (nq + TC_M - 1) / TC_M;
-    int groups = sm_count / nqb;
+    // lb_set_option("tc_reserve_sms"): SMs the persistent scan leaves free.  One scan CTA takes an SM's whole register
+    // file, so kernels of OTHER streams (the tail of the previous batch: selection, merge, re-score, exchange) can
+    // only run on SMs the scan does not occupy.
+    int usable = sm_count - g_tc_reserve_sms;
+    if (usable < nqb) usable = nqb;
+    int groups = usable / nqb;
     if (groups < 1) groups = 1;
     if (groups > n_row_tiles) groups = n_row_tiles;
     *groups_out = groups;

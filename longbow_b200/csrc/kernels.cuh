@@ -39,6 +39,7 @@ extern int g_pq_ahead;
 extern bool g_pq_ring;
 extern bool g_hnsw_coop;
 extern bool g_tc_pair;
+extern int g_tc_reserve_sms;
 void count_launch();  // api.cu: process-wide launch counter (bench evidence)
 
 constexpr int LB_NEDGE = 16;  // rungs of the shared threshold ladder (dense_tc.cu)
