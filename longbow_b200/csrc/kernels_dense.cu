@@ -352,9 +352,13 @@ merge_partials_kernel(const uint64_t* __restrict__ partial, int parts, int nq, i
 // Output is sorted ascending.
 // ---------------------------------------------------------------------------------------------
 constexpr int MSEL_T = 256;
-constexpr int MSEL_CAP = 4096;
+constexpr int MSEL_BATCH = 4;
+// 16 KiB of keys and <= 32 registers: 8 CTAs per SM = 1184 resident, so a 1024-query batch is ONE wave (with a 32 KiB
+// buffer and 38 registers it was 888 resident = 1.15 waves, i.e. the time of two).  The final threshold of the scan
+// usually leaves a few hundred entries per query, far below the capacity.
+constexpr int MSEL_CAP = 2048;
 
-__global__ void __launch_bounds__(MSEL_T)
+__global__ void __launch_bounds__(MSEL_T, 8)
 merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int kc, uint64_t* __restrict__ merged,
                     uint64_t* __restrict__ kth, const float* __restrict__ edges, const uint32_t* __restrict__ edge_cnt,
                     const uint64_t* __restrict__ compact, const uint32_t* __restrict__ counts, size_t stride) {
@@ -396,9 +400,9 @@ merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int
         else x = (i < head) ? partial[(size_t)q * kc + i] : compact[(size_t)q * stride + (i - head)];
         return ((x != kInvalid) && ((uint32_t)(x >> 32) < thr)) ? x : kInvalid;
     };
-    // Slots are fetched 8 per thread with all loads in flight (one memory round trip per 2048 slots, not
+    // Slots are fetched MSEL_BATCH per thread with all loads in flight (one memory round trip per 1024 slots, not
     // per 256); the buffer is flushed (sorted, best kc kept) before a batch that could overflow it.
-    constexpr int BATCH = 8;
+    constexpr int BATCH = MSEL_BATCH;
     for (int base = 0; base < total; base += MSEL_T * BATCH) {
         uint64_t x[BATCH];
 #pragma unroll
@@ -439,7 +443,7 @@ merge_select_kernel(const uint64_t* __restrict__ partial, int parts, int nq, int
 cudaError_t launch_merge_select(const uint64_t* partial, int parts, int nq, int kc, uint64_t* merged, uint64_t* kth,
                                 const float* edges, const uint32_t* edge_cnt, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    if (kc > MSEL_CAP - 8 * MSEL_T) return cudaErrorInvalidValue;
+    if (kc > MSEL_CAP - MSEL_BATCH * MSEL_T) return cudaErrorInvalidValue;
     merge_select_kernel<<<nq, MSEL_T, 0, st>>>(partial, parts, nq, kc, merged, kth, edges, edge_cnt, nullptr, nullptr, 0);
     count_launch();
     return cudaGetLastError();
@@ -449,7 +453,7 @@ cudaError_t launch_merge_select_compact(const uint64_t* head, const uint64_t* co
                                         size_t stride, int nq, int kc, uint64_t* merged, const float* edges,
                                         const uint32_t* edge_cnt, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    if (kc > MSEL_CAP - 8 * MSEL_T) return cudaErrorInvalidValue;
+    if (kc > MSEL_CAP - MSEL_BATCH * MSEL_T) return cudaErrorInvalidValue;
     merge_select_kernel<<<nq, MSEL_T, 0, st>>>(head, head ? 1 : 0, nq, kc, merged, nullptr, edges, edge_cnt, compact,
                                                counts, stride);
     count_launch();
