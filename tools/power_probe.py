@@ -36,6 +36,8 @@ for dbg in cases:
     mm = dbg == "mm"
     if dbg.startswith("boot"):      # "boot8": tc_boot_tiles = 8 (0 = automatic)
         _lib.set_option("tc_debug", 0); _lib.set_option("tc_boot_tiles", int(dbg[4:]))
+    elif dbg.startswith("rsb"):     # "rsb1": rescore_block = 1 (block-per-query exact stage), "rsb0": warp-per-query
+        _lib.set_option("tc_debug", 0); _lib.set_option("rescore_block", int(dbg[3:]))
     elif not mm:
         _lib.set_option("tc_debug", int(dbg))
     run = (lambda: torch.matmul(a, b)) if mm else (lambda: idx.search_device(qs, K, od, ol))
@@ -57,4 +59,4 @@ for dbg in cases:
     extra = f"TF/s {2 * 8192**3 / per / 1e9:.0f}" if mm else f"scan_ms {ms / max(cnt, 1):.4f}"
     print(f"case {dbg} ms/iter {per:.4f} {extra} sm_mhz {statistics.median(s.mhz[half:])} "
           f"power_w {statistics.median(s.w[half:]):.0f} max_w {max(s.w):.0f}", flush=True)
-_lib.set_option("tc_debug", 0); _lib.set_option("tc_boot_tiles", 0)
+_lib.set_option("tc_debug", 0); _lib.set_option("tc_boot_tiles", 0); _lib.set_option("rescore_block", 0)
