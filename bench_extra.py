@@ -120,8 +120,13 @@ def config_c1(ctx):
                    "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 12},
            "roofline": _roof_tensor(2.0 * Q * N * D, t["kernel_ms"], ctx["peaks"], "dense_scan_tc<tf32 x3> (3xTF32 split: "
                                     "three MMAs per k-step; flops counted once)",
-                                    "51 MB database is L2-resident: launch/latency-bound, 5 kernels per search"),
+                                    "51 MB database is L2-resident.  fp32 rows cost three kind::tf32 MMAs per k-step and "
+                                    "tf32 runs at half the bf16 rate, so this method's ceiling is peak / 6 "
+                                    "(method_ceiling_tflops); the search is 5 kernels of 20-130 us each"),
            "gpu_launches": t["launches"], "clocks": t["clocks"], "checks": {}}
+    if out["roofline"]["achieved"]:
+        out["roofline"]["method_ceiling_tflops"] = out["roofline"]["peak"] / 6.0
+        out["roofline"]["frac_of_method_ceiling"] = out["roofline"]["achieved"] / (out["roofline"]["peak"] / 6.0)
     if ctx["cpu"]:
         from oracle import oracle
         cores = oracle.fast_use_all_cores()
