@@ -393,6 +393,10 @@ int lb_set_option(const char* name, int value) {
         g_opt_f32_tc.store(value ? 1 : 0);
         return LB_OK;
     }
+    if (strcmp(name, "ssel_warp") == 0) {
+        g_ssel_warp = value != 0;
+        return LB_OK;
+    }
     if (strcmp(name, "tc_reserve_sms") == 0) {
         if (value < 0 || value > 64) return fail(LB_ERR_INVALID, "tc_reserve_sms: 0..64");
         g_tc_reserve_sms = value;

@@ -25,6 +25,7 @@ namespace lb {
 
 bool g_tc_pair = true;  // lb_set_option("tc_pair"): CTA-pair (cta_group::2) scan on / off
 int g_tc_reserve_sms = 0;
+bool g_ssel_warp = true;   // lb_set_option("ssel_warp"): warp-per-query sample selection for small samples
 
 enum { KIND_F16 = 0, KIND_I8 = 1, KIND_TF32 = 2 };
 static_assert(LB_NEDGE == 16, "the epilogue unpacks four uint4 of ladder counters");
@@ -820,6 +821,71 @@ __device__ __forceinline__ uint32_t sample_key(const float* __restrict__ keys, i
     return (k < INFINITY) ? float_to_ordered(k) : 0xffffffffu;  // NaN / +inf never selected
 }
 
+// The same for E rows per thread (rows e * nt + tid), for the warp-per-query kernel: ALL loads are issued first -- predicated, nothing depends on a
+// loaded value yet, so they cost one memory round trip instead of E (sample_key() per row serialises: each row's
+// validity branch waits for its own load) -- then the validity rules are applied.
+template <int E>
+__device__ __forceinline__ void sample_keys(const float* __restrict__ keys, int ld, int S, uint32_t n_rows,
+                                            const uint32_t* __restrict__ tomb, uint32_t tomb_bits,
+                                            const uint32_t* __restrict__ allow, int q, int tid, int nt, uint32_t (&v)[E]) {
+    const float* krow = keys + (size_t)q * ld;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const uint32_t row = (uint32_t)(e * nt + tid);
+        float kf = INFINITY;
+        if ((int)row < S && row < n_rows) kf = __ldg(krow + row);
+        v[e] = __float_as_uint(kf);
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const float kf = __uint_as_float(v[e]);
+        v[e] = (kf < INFINITY) ? float_to_ordered(kf) : 0xffffffffu;
+    }
+    if (tomb != nullptr || allow != nullptr) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const uint32_t row = (uint32_t)(e * nt + tid);
+            if (v[e] != 0xffffffffu) {
+                if (tomb != nullptr && row < tomb_bits && bit_set(tomb, row)) v[e] = 0xffffffffu;
+                else if (allow != nullptr && !bit_set(allow, row)) v[e] = 0xffffffffu;
+            }
+        }
+    }
+}
+
+// The ladder of one query from its sorted sample candidates (lanes 0..15 of one warp; see the comment in
+// sample_select_kernel).  sorted[0, c): ascending packed (key, row), c >= kc.
+__device__ __forceinline__ void emit_ladder(const uint64_t* sorted, int c, int kc, const EdgeRanks& ranks, int q,
+                                            float* __restrict__ edges, uint32_t* __restrict__ edge_cnt, float* s_edge,
+                                            int* s_below, int tid) {
+    const float ktop = key_of(sorted[kc - 1]);
+    float e;
+    if (tid >= ranks.n_spare) {
+        e = nextafterf(key_of(sorted[ranks.r[tid] - 1]), INFINITY);
+    } else {
+        const int rl = ranks.r[ranks.n_spare];
+        int rm = kc / 4;
+        if (rm <= rl) rm = rl + 1;
+        const float kpd = (rm < kc) ? (ktop - key_of(sorted[rm - 1])) / log2f((float)kc / (float)rm) : 0.f;
+        const float below = (float)(ranks.n_spare - tid) * ranks.doublings / (float)ranks.n_spare;
+        e = ktop - kpd * (log2f((float)kc / (float)rl) + below);
+        if (!(e == e)) e = ktop;  // inf - inf
+    }
+    s_edge[tid] = e;
+    __syncwarp(0xffffu);
+    int pos = 0;
+    for (int u = 0; u < LB_NEDGE; u++) pos += (s_edge[u] < e || (s_edge[u] == e && u < tid)) ? 1 : 0;
+    int lo = 0, hi = c;  // sample rows with key < e: all of them are among the c sorted ones (e <= the kc-th key, bumped)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (key_of(sorted[mid]) < e) lo = mid + 1; else hi = mid;
+    }
+    s_below[pos] = lo;
+    edges[(size_t)q * LB_NEDGE + pos] = e;
+    __syncwarp(0xffffu);
+    edge_cnt[(size_t)q * LB_NEDGE + tid] = (uint32_t)(s_below[tid] - (tid ? s_below[tid - 1] : 0));
+}
+
 // Fast path.  Thread t holds the ordered keys of rows t, t+nt, t+2nt ... (row ids are implicit, so 32
 // registers hold 32 entries).  Pivot = the r-th smallest of a sub-sample (the threads' first entries),
 // r chosen so that about 4*kc of the S keys fall at or below it; everything <= pivot is collected into
@@ -874,35 +940,87 @@ sample_select_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_r
     // bucket is seeded with the sample rows that actually fall into it, so any mix of values is a valid ladder.
     __shared__ float s_edge[LB_NEDGE];
     __shared__ int s_below[LB_NEDGE];
-    if (tid < LB_NEDGE) {   // one warp
-        const float ktop = key_of(s_coll[kc - 1]);
-        float e;
-        if (tid >= ranks.n_spare) {
-            e = nextafterf(key_of(s_coll[ranks.r[tid] - 1]), INFINITY);
-        } else {
-            const int rl = ranks.r[ranks.n_spare];
-            int rm = kc / 4;
-            if (rm <= rl) rm = rl + 1;
-            const float kpd = (rm < kc) ? (ktop - key_of(s_coll[rm - 1])) / log2f((float)kc / (float)rm) : 0.f;
-            const float below = (float)(ranks.n_spare - tid) * ranks.doublings / (float)ranks.n_spare;
-            e = ktop - kpd * (log2f((float)kc / (float)rl) + below);
-            if (!(e == e)) e = ktop;  // inf - inf
-        }
-        s_edge[tid] = e;
-        __syncwarp(0xffffu);
-        int pos = 0;
-        for (int u = 0; u < LB_NEDGE; u++) pos += (s_edge[u] < e || (s_edge[u] == e && u < tid)) ? 1 : 0;
-        int lo = 0, hi = c;  // sample rows with key < e: all of them are among the c collected (e <= the kc-th key, bumped)
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (key_of(s_coll[mid]) < e) lo = mid + 1; else hi = mid;
-        }
-        s_below[pos] = lo;
-        edges[(size_t)q * LB_NEDGE + pos] = e;
-        __syncwarp(0xffffu);
-        edge_cnt[(size_t)q * LB_NEDGE + tid] = (uint32_t)(s_below[tid] - (tid ? s_below[tid - 1] : 0));
-    }
+    if (tid < LB_NEDGE) emit_ladder(s_coll, c, kc, ranks, q, edges, edge_cnt, s_edge, s_below, tid);   // one warp
     if (tid == 0) { tau[q] = nextafterf(key_of(s_coll[kc - 1]), INFINITY); done[q] = 1; }
+}
+
+// Small samples (S <= 2048, kc <= 128): ONE WARP per query.  Lane l holds the ordered keys of rows 32 e + l in 64
+// registers; the kc-th smallest key is found by an MSB-first radix search with warp votes (no sorting network, no
+// block barrier), the kc smallest (key, row) are compacted in row order -- ties at the kc-th key broken by row --
+// sorted (128 entries) and the ladder is read off them.  ~6 k warp instructions per query against ~54 k for the block
+// kernel above: on a 125 k-row shard (8 GPUs) or C1 the sample selection was a quarter of the per-batch tail.
+// Queries with fewer than kc live sample rows are left to the exact kernel (done[q] = 0).
+constexpr int SSW_E = 64;
+__global__ void __launch_bounds__(128)
+sample_select_warp_kernel(const float* __restrict__ keys, int ld, int S, uint32_t n_rows, const uint32_t* __restrict__ tomb,
+                          uint32_t tomb_bits, const uint32_t* __restrict__ allow, int nq, int kc,
+                          uint64_t* __restrict__ out, float* __restrict__ tau, float* __restrict__ edges,
+                          uint32_t* __restrict__ edge_cnt, const EdgeRanks ranks, int* __restrict__ done) {
+    __shared__ uint64_t s_top[4][128];
+    __shared__ float s_edge[4][LB_NEDGE];
+    __shared__ int s_below[4][LB_NEDGE];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 4 + w;
+    if (q >= nq) return;
+    uint32_t v[SSW_E];
+    int live = 0;
+    uint32_t a_and = 0xffffffffu, a_or = 0;
+    sample_keys<SSW_E>(keys, ld, S, n_rows, tomb, tomb_bits, allow, q, lane, 32, v);
+#pragma unroll
+    for (int e = 0; e < SSW_E; e++) {
+        if (v[e] != 0xffffffffu) { live++; a_and &= v[e]; a_or |= v[e]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        live += __shfl_xor_sync(0xffffffffu, live, o);
+        a_and &= __shfl_xor_sync(0xffffffffu, a_and, o);
+        a_or |= __shfl_xor_sync(0xffffffffu, a_or, o);
+    }
+    if (live < kc) {
+        if (lane == 0) done[q] = 0;
+        return;
+    }
+    // kc-th smallest key: the largest T with fewer than kc keys below it; bits above the highest differing bit are shared
+    const uint32_t diff = a_and ^ a_or;
+    const int top = diff ? (31 - __clz(diff)) : -1;
+    uint32_t T = (top >= 31) ? 0u : (a_and & ~((2u << top) - 1u));
+    if (top < 0) T = a_and;
+#pragma unroll 1
+    for (int bit = top; bit >= 0; bit--) {
+        const uint32_t test = T | (1u << bit);
+        int l0 = 0, l1 = 0, l2 = 0, l3 = 0;   // four chains: the per-bit step is a latency chain, not a throughput one
+#pragma unroll
+        for (int e = 0; e < SSW_E; e += 4) {
+            l0 += (v[e] < test); l1 += (v[e + 1] < test); l2 += (v[e + 2] < test); l3 += (v[e + 3] < test);
+        }
+        const int less = (int)__reduce_add_sync(0xffffffffu, (unsigned)((l0 + l1) + (l2 + l3)));
+        if (less < kc) T = test;
+    }
+    int n_less = 0;
+#pragma unroll
+    for (int e = 0; e < SSW_E; e++) n_less += (v[e] < T);
+    n_less = (int)__reduce_add_sync(0xffffffffu, (unsigned)n_less);
+    const int tie_keep = kc - n_less;   // >= 1
+    // compaction in row order (e ascending, then lane): rows below T, plus the first tie_keep rows at T
+    uint64_t* topl = s_top[w];
+    int base = 0, ties = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int e = 0; e < SSW_E; e++) {   // (fully unrolled: v[] must stay in registers)
+        const bool is_tie = v[e] == T;
+        const unsigned tb = __ballot_sync(0xffffffffu, is_tie);
+        const bool keep = (v[e] < T) || (is_tie && ties + __popc(tb & lt) < tie_keep);
+        const unsigned kb = __ballot_sync(0xffffffffu, keep);
+        if (keep) topl[base + __popc(kb & lt)] = ((uint64_t)v[e] << 32) | (uint32_t)(e * 32 + lane);
+        base += __popc(kb);
+        ties += __popc(tb);
+    }
+    for (int t = kc + lane; t < 128; t += 32) topl[t] = kInvalid;   // base == kc
+    __syncwarp();
+    warp_bitonic_sort(topl, 128, lane);
+    for (int t = lane; t < kc; t += 32) out[(size_t)q * kc + t] = topl[t];
+    if (lane < LB_NEDGE) emit_ladder(topl, kc, kc, ranks, q, edges, edge_cnt, s_edge[w], s_below[w], lane);
+    if (lane == 0) { tau[q] = nextafterf(key_of(topl[kc - 1]), INFINITY); done[q] = 1; }
 }
 
 // Exact path for the queries the fast path left (fewer than kc sample rows at or below the pivot, too
@@ -986,7 +1104,14 @@ cudaError_t launch_sample_select(const float* keys, int ld, int S, uint32_t n_ro
                                                           tau, edges, edge_cnt, done);                          \
         count_launch();                                                                                         \
     }
-    if (E == 8) LB_SSEL(8) else if (E == 16) LB_SSEL(16) else LB_SSEL(32)
+    if (S <= SSW_E * 32 && kc <= 128 && g_ssel_warp) {
+        sample_select_warp_kernel<<<(nq + 3) / 4, 128, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, tau,
+                                                                 edges, edge_cnt, er, done);
+        count_launch();
+        sample_select_exact_kernel<8><<<nq, nt, 0, st>>>(keys, ld, S, n_rows, tomb, tomb_bits, allow, nq, kc, out, tau, edges,
+                                                         edge_cnt, done);
+        count_launch();
+    } else if (E == 8) LB_SSEL(8) else if (E == 16) LB_SSEL(16) else LB_SSEL(32)
 #undef LB_SSEL
     return cudaGetLastError();
 }

@@ -40,6 +40,7 @@ extern bool g_pq_ring;
 extern bool g_hnsw_coop;
 extern bool g_tc_pair;
 extern int g_tc_reserve_sms;
+extern bool g_ssel_warp;
 void count_launch();  // api.cu: process-wide launch counter (bench evidence)
 
 constexpr int LB_NEDGE = 16;  // rungs of the shared threshold ladder (dense_tc.cu)
