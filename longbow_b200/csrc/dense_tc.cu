@@ -6,11 +6,13 @@
 //   warp 0      TMA producer   : cp.async.bulk.tensor tiles of Q and X into a 4-stage smem ring
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma (M=128, N=256), accumulators in TMEM
 //   warp 2      TMEM allocator : 512 columns = 2 accumulator stages of 256 fp32/s32 columns
-//   warps 4..11 epilogue       : two groups of 4 warps alternate tiles; tcgen05.ld a TMEM lane
-//                                (= one query) per thread, turn dot products
-//                                into ranking keys, threshold-filter them against the query's
-//                                running k-th best, append survivors to the query's candidate
-//                                list; warp-cooperative radix-select compaction when a list fills.
+//   warps 4..11 epilogue       : two groups of 4 warps drain every tile together (half the columns each);
+//                                tcgen05.ld a TMEM lane (= one query) per thread, fold the negated ranking
+//                                keys of 32 columns into four 8-column maxima, test those against the
+//                                query's running k-th best; only flagged column groups are looked at key by
+//                                key, every lane appends its own survivors (key picked out of its registers
+//                                by a select tree) to the query's candidate list; warp-cooperative
+//                                radix-select compaction when a list fills.
 // The 128 x 256 distance tile never leaves the SM: HBM only sees the database once per batch.
 //
 // Work split: query block b (128 queries) x group g; CTA (b, g) streams row tiles g, g+G, g+2G ...
