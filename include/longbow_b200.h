@@ -370,7 +370,9 @@ int64_t lb_kernel_launch_count(void);
  * "pq_scan": 0 = auto (look-up passes below 64 queries per call, decode + tensor-core coarse stage from 64 up),
  *            1 = exhaustive fp32 ADC kernel, 2 = coarse look-up scan one query per pass, 3 = four per pass,
  *            4 = decode the codes to fp16 slabs and run the dense tensor-core scan (csrc/pq_gemm.cu).
- * Every mode returns the same (id, distance) pairs: the coarse stages only pick candidates for the exact stage. */
+ * Every mode returns the same (id, distance) pairs: the coarse stages only pick candidates for the exact stage.
+ * "pq_gemm": 1 (default) lets the automatic policy take path 4 for batches; 0 keeps batches on the look-up passes
+ *            (path 4 borrows up to 4 Mi x dims x 2 bytes of scratch per concurrent search). */
 int lb_set_option(const char *name, int value);
 /* Profiling hook for bench.py's roofline: when enabled, every search brackets its dominant
  * kernel (the coarse distance scan: dense or ADC) with CUDA events on the launching stream.

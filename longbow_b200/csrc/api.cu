@@ -102,6 +102,7 @@ static std::atomic<int> g_opt_tc_debug{0};
 static std::atomic<int> g_opt_tc_boot_tiles{0};  // 0 = auto
 static std::atomic<int> g_opt_f32_tc{1};         // fp32 indexes: 3xTF32 tensor-core scan (0: SIMT scan)
 static std::atomic<int> g_opt_pq_scan{0};  // 0 auto, 1 exhaustive fp32 kernel, 2 coarse (1 query / pass), 3 coarse (4 / pass), 4 decode + tensor-core scan
+static std::atomic<int> g_opt_pq_gemm{1};   // auto policy may use the decode + tensor-core path for batches (0: never)
 static std::atomic<int> g_opt_certify{1};        // host searches: certify the coarse stage, redo flagged queries exactly
 static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off (A/B timing)    // timing probes of the tensor-core scan (results invalid when != 0)  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
 
@@ -428,6 +429,10 @@ int lb_set_option(const char* name, int value) {
     }
     if (strcmp(name, "tc_debug") == 0) {
         g_opt_tc_debug.store(value);
+        return LB_OK;
+    }
+    if (strcmp(name, "pq_gemm") == 0) {
+        g_opt_pq_gemm.store(value ? 1 : 0);
         return LB_OK;
     }
     if (strcmp(name, "pq_scan") == 0) {
@@ -1727,7 +1732,7 @@ static int pq_search_core(lb_pq* pq, const float* d_q, int64_t nq, int k, int kp
                              dense_tc_eligible(DT_F16, pq->dims, pq->codebook16, pq->codebook16, 2 * kout + 64);
         if (mode == 4 && (!gemm_ok || kout > 704))
             return fail(LB_ERR_UNSUPPORTED, "decode + tensor-core PQ scan not eligible");
-        if (mode == 4 || (mode == 0 && gemm_ok && cq >= 64 && kout <= 352)) {  // auto: only with the full 2 k' margin
+        if (mode == 4 || (mode == 0 && gemm_ok && cq >= 64 && kout <= 352 && g_opt_pq_gemm.load(std::memory_order_relaxed))) {  // auto: only with the full 2 k' margin
             int kg = 2 * kout;  // wider candidate margin than the look-up path: the fp16 rounding bound is looser
             if (kg < kc) kg = kc;
             if (kg > 704) kg = 704;

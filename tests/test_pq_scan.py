@@ -226,3 +226,29 @@ def test_gemm_path_declines_out_of_range_codebooks(oracle, pq_mode):
     with pytest.raises(_lib.LongbowError):
         enc.search(q, 10)
     enc.close()
+
+
+def test_gemm_path_can_be_switched_off(oracle):
+    """lb_set_option("pq_gemm", 0): batches stay on the look-up passes (no decode scratch); same answers."""
+    from longbow_b200 import _lib, pq
+    rng = np.random.default_rng(12)
+    M, sub, n = 16, 4, 20000
+    cb, codes = _setup(rng, n, M, sub)
+    q = rng.standard_normal((70, M * sub)).astype(np.float32)
+    enc = pq.PQEncoder(M * sub, M, 256, cb)
+    enc.add_codes(codes)
+    wd, wl = oracle.pq_search(cb, codes, None, q, 10, 0)
+    _lib.set_option("pq_gemm", 0)
+    try:
+        l0 = _lib.launch_count()
+        gd, gl = enc.search(q, 10)
+        n_off = _lib.launch_count() - l0
+    finally:
+        _lib.set_option("pq_gemm", 1)
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "pq_gemm off")
+    l0 = _lib.launch_count()
+    gd, gl = enc.search(q, 10)
+    n_on = _lib.launch_count() - l0
+    assert_topk_equal(gd, gl, wd, wl, 0.0, "pq_gemm on")
+    assert n_on != n_off   # different kernel chains actually ran
+    enc.close()
