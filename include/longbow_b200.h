@@ -239,6 +239,8 @@ int lb_exchange_error(lb_exchange *ex);
  *     ordinary search chain and its re-score kernel stores the shard's record directly into the root GPU's
  *     gather buffer over NVLink peer memory; the root merges by (distance, label).  Same certification
  *     contract as lb_index_search (uncertified queries are re-done exhaustively on every shard).
+ *     Thread safety: calls on one handle are serialised inside the library (a search occupies every GPU of the
+ *     set and owns the root's gather buffer), so callers may hold only a read lock as faiss_gpu.go:108 does.
  * ---------------------------------------------------------------------------------------- */
 typedef struct lb_shard lb_shard;
 int lb_shard_create(const int *devices, int n_devices, int dim, int dtype, int metric, int64_t total_rows,

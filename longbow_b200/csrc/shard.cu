@@ -10,6 +10,7 @@
 // (Ranks in SEPARATE processes use csrc/exchange.cu, which needs flags instead of events.)
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -40,6 +41,9 @@ struct lb_shard {
     size_t slot_bytes = 0;
     std::vector<std::vector<uint64_t>> tomb;  // host copies are not kept; per-shard device bitmaps live in the lb_index
     int64_t last_uncertified = 0;
+    // one search owns the per-device streams and the root's gather buffer: calls on one handle are serialised here
+    // (a search already occupies every GPU of the set; the Go side may hold only a read lock, faiss_gpu.go:108)
+    std::mutex mu;
 };
 
 #define SCK(call)                                                  \
@@ -121,6 +125,7 @@ int lb_shard_add(lb_shard* s, const void* rows, int64_t n) {
     if (!s || n < 0) return api_fail(LB_ERR_INVALID, "bad argument");
     if (n == 0) return LB_OK;
     if (!rows) return api_fail(LB_ERR_INVALID, "rows is NULL");
+    std::lock_guard<std::mutex> lock(s->mu);
     if (s->added + n > s->total_rows) return api_fail(LB_ERR_INVALID, "more rows than the shard set was created for");
     const size_t rb = (size_t)s->dim * elem_bytes(s->dtype);
     int64_t done = 0;
@@ -140,6 +145,7 @@ int lb_shard_add(lb_shard* s, const void* rows, int64_t n) {
 // global tombstone bitmap (bit i <-> global row i), sliced by whole words per shard
 int lb_shard_set_tombstones(lb_shard* s, const uint64_t* bitmap, int64_t nbits) {
     if (!s) return api_fail(LB_ERR_INVALID, "shard set is NULL");
+    std::lock_guard<std::mutex> lock(s->mu);
     for (int g = 0; g < s->n; g++) {
         const int64_t lo = (int64_t)g * s->rows_per_shard;
         int rc;
@@ -157,6 +163,7 @@ int lb_shard_search(lb_shard* s, const void* queries, int64_t nq, int k, const u
     if (nq == 0) return LB_OK;
     if (!queries || !distances || !labels) return api_fail(LB_ERR_INVALID, "NULL buffer");
     if ((int64_t)s->n * k > 16384) return api_fail(LB_ERR_UNSUPPORTED, "shards * k > 16384");
+    std::lock_guard<std::mutex> lock(s->mu);
     const size_t qb = (size_t)nq * s->dim * elem_bytes(s->dtype);
     const size_t loff = loff_of(nq, k);
     const size_t rec = (loff + (size_t)nq * k * 8 + 255) & ~(size_t)255;

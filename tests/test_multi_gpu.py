@@ -336,3 +336,36 @@ def test_shard_handle_near_ties_are_repaired(oracle):
     assert_topk_equal(gd, gl, wd, wl, 0.0, "sharded near ties")
     assert sh.last_uncertified() >= 1
     sh.close()
+
+
+def test_shard_handle_concurrent_searches(oracle):
+    """Four threads search ONE lb_shard handle at once, as goroutines holding the Go shim's read lock would
+    (go/longbow_b200.go SearchBatch): the handle serialises them on its own mutex (its streams and the root's gather
+    buffer belong to one search at a time), every caller gets its own exact answer."""
+    import threading
+    from longbow_b200 import gpu
+    rng = np.random.default_rng(21)
+    n, dim, k = 40003, 128, 10
+    db = make_db(rng, n, dim, np.float16)
+    sh = gpu.ShardedDenseIndex([0, 0], dim, np.float16, COS, n)
+    sh.add(db)
+    batches = [make_db(rng, nq, dim, np.float16) for nq in (33, 5, 64, 17)]  # different record sizes: the gather buffer regrows
+    want = [oracle.search(COS, db, q, k) for q in batches]
+    got = [None] * len(batches)
+    errs = []
+
+    def worker(i):
+        try:
+            for _ in range(6):
+                got[i] = sh.search(batches[i], k)
+                assert_topk_equal(got[i][0], got[i][1], want[i][0], want[i][1], 0.0, f"concurrent caller {i}")
+        except BaseException as e:  # noqa: BLE001 -- reported by the main thread
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(len(batches))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs[0]
+    sh.close()
