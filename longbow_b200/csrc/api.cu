@@ -103,6 +103,7 @@ static std::atomic<int> g_opt_tc_boot_tiles{0};  // 0 = auto
 static std::atomic<int> g_opt_f32_tc{1};         // fp32 indexes: 3xTF32 tensor-core scan (0: SIMT scan)
 static std::atomic<int> g_opt_pq_scan{0};  // 0 auto, 1 exhaustive fp32 kernel, 2 coarse (1 query / pass), 3 coarse (4 / pass), 4 decode + tensor-core scan
 static std::atomic<int> g_opt_pq_gemm{1};   // auto policy may use the decode + tensor-core path for batches (0: never)
+static std::atomic<int> g_opt_exhaustive_k{411};  // single-query searches with k >= this take the exhaustive exact chain (0: only beyond the fused selector)
 static std::atomic<int> g_opt_certify{1};        // host searches: certify the coarse stage, redo flagged queries exactly
 static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off (A/B timing)    // timing probes of the tensor-core scan (results invalid when != 0)  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
 
@@ -388,6 +389,10 @@ int lb_set_option(const char* name, int value) {
     }
     if (strcmp(name, "certify") == 0) {
         g_opt_certify.store(value ? 1 : 0);
+        return LB_OK;
+    }
+    if (strcmp(name, "exhaustive_k") == 0) {
+        g_opt_exhaustive_k.store(value < 0 ? 0 : value);
         return LB_OK;
     }
     if (strcmp(name, "f32_tc") == 0) {
@@ -695,6 +700,17 @@ static int coarse_k(int k) {
     return ((kc + 31) / 32) * 32;
 }
 
+// Which searches take the exhaustive exact chain (every row's exact distance, then select_k): k beyond the fused
+// selector's candidate capacity, and -- measured on the C2 database, tools/large_k_probe.py -- single-query calls
+// with k >= 411 (coarse list beyond 512 entries: the padded tensor-core block with the 1024-entry selector takes 3.3 ms
+// at k = 448 and 11.1 ms at k = 704 for one query over 1 M x 768 fp16, the exhaustive chain 1.8 and 2.7 ms; below that
+// the ordinary paths win: 0.72 against 1.5 ms at k = 352).  Both plans return the same (distance, id) lists.
+static bool exhaustive_plan(int64_t nq, int k) {
+    if (coarse_k(k) > 896) return true;
+    const int xk = g_opt_exhaustive_k.load(std::memory_order_relaxed);
+    return xk > 0 && nq == 1 && k >= xk;
+}
+
 // fp32 indexes: the low parts of the rows for the 3xTF32 tensor-core scan, built (or extended after an add) by
 // the first search that needs them.  Searches may run concurrently (read lock on the Go side), so the build is
 // serialised here; rows only ever grow, and add() needs exclusive access anyway.
@@ -721,8 +737,8 @@ static int search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const 
                        uint32_t* d_cert_count = nullptr) {
     if (nq == 0) return LB_OK;
     const int kc = coarse_k(k);
-    if (kc > 896) {
-        // k beyond the fused selector (k > 704): exhaustive exact kernel, one query at a time
+    if (exhaustive_plan(nq, k)) {
+        // k beyond the fused selector (k > 704), or one query with a large k: exhaustive exact kernel, one query at a time
         if (k > 2048) return fail(LB_ERR_UNSUPPORTED, "k > 2048");
         if (idx->size == 0) {
             Scratch scr0(st);
@@ -958,7 +974,7 @@ static int exact_search_one(lb_index* idx, const void* d_q1, int k, const uint64
 namespace lb {
 int api_search_core(lb_index* idx, const void* d_q, int64_t nq, int k, const uint64_t* d_allow, float* d_dist,
                     int64_t* d_lab, cudaStream_t st, uint32_t* d_flags, uint32_t* d_count) {
-    if (coarse_k(k) > 896 || idx->size == 0) d_flags = d_count = nullptr;  // exhaustive / empty: nothing to certify
+    if (exhaustive_plan(nq, k) || idx->size == 0) d_flags = d_count = nullptr;  // exhaustive / empty: nothing to certify
     return search_core(idx, d_q, nq, k, d_allow, d_dist, d_lab, st, d_flags, d_count);
 }
 int api_exact_search_one(lb_index* idx, const void* d_q1, int k, const uint64_t* d_allow, float* d_out_d,
@@ -990,7 +1006,7 @@ int lb_index_search_device_cert(lb_index* idx, const void* d_queries, int64_t nq
     if (nq == 0) return LB_OK;
     if (d_uncert_flags == nullptr && d_uncert_count == nullptr)
         return search_core(idx, d_queries, nq, k, d_allow, d_distances, d_labels, st);
-    if (coarse_k(k) > 896 || idx->size == 0) {  // exhaustive exact path: nothing to certify
+    if (exhaustive_plan(nq, k) || idx->size == 0) {  // exhaustive exact path: nothing to certify
         if (d_uncert_flags) CK(cudaMemsetAsync(d_uncert_flags, 0, (size_t)nq * 4, st));
         return search_core(idx, d_queries, nq, k, d_allow, d_distances, d_labels, st);
     }

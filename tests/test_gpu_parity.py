@@ -628,6 +628,33 @@ def test_large_k_exact_path(lbgpu, oracle, dtype, metric):
         g.Close()
 
 
+def test_single_query_large_k_plans_agree(lbgpu, oracle):
+    """One query with k >= 411 takes the exhaustive exact chain by default (measured cheaper than the padded
+    tensor-core block); lb_set_option("exhaustive_k", ...) moves the switch.  Both plans give the oracle's answer."""
+    from longbow_b200 import _lib
+    rng = np.random.default_rng(77)
+    n, dim, k = 30011, 128, 500
+    db, q = make_db(rng, n, dim, np.float16), make_db(rng, 2, dim, np.float16)
+    idx = lbgpu.DenseIndex(dim, np.float16, COS)
+    idx.add(db)
+    allow = random_bitmap(rng, n, 0.5)
+    wd, wl = oracle.search(COS, db, q, k, allow=lbgpu.pack_bitmap(allow))
+    counts = []
+    try:
+        for xk in (411, 100000, 1):
+            _lib.set_option("exhaustive_k", xk)
+            l0 = _lib.launch_count()
+            gd, gl = idx.search(q[:1], k, allow=allow)
+            counts.append(_lib.launch_count() - l0)
+            assert_topk_equal(gd, gl, wd[:1], wl[:1], 0.0, f"one query, exhaustive_k={xk}")
+            gd, gl = idx.search(q, k, allow=allow)      # two queries: always the ordinary plan
+            assert_topk_equal(gd, gl, wd, wl, 0.0, f"two queries, exhaustive_k={xk}")
+    finally:
+        _lib.set_option("exhaustive_k", 411)
+    assert counts[0] == counts[2], counts   # the default plan is the forced exhaustive chain's kernel sequence
+    idx.close()
+
+
 # ------------------------------------------------------------------ short rows on the tensor-core path
 @pytest.mark.parametrize("dtype,dims", [(np.float32, (4, 8, 12, 16, 24)), (np.float16, (8, 16, 24, 40)), (np.int8, (16, 32, 48))])
 def test_tensor_core_short_rows(lbgpu, oracle, scan_mode, dtype, dims):
