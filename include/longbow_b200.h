@@ -373,7 +373,7 @@ int64_t lb_kernel_launch_count(void);
  *            1 = exhaustive fp32 ADC kernel, 2 = coarse look-up scan one query per pass, 3 = four per pass,
  *            4 = decode the codes to fp16 slabs and run the dense tensor-core scan (csrc/pq_gemm.cu).
  * Every mode returns the same (id, distance) pairs: the coarse stages only pick candidates for the exact stage.
- * "exhaustive_k": single-query searches with k >= this value (default 411) take the exhaustive exact chain instead of
+ * "exhaustive_k": single-query searches with k >= this value (default 256) take the exhaustive exact chain instead of
  *            the coarse scan (cheaper there, tools/large_k_probe.py); 0 = only k beyond the fused selector (k > 704).
  * "pq_gemm": 1 (default) lets the automatic policy take path 4 for batches; 0 keeps batches on the look-up passes
  *            (path 4 borrows up to 4 Mi x dims x 2 bytes of scratch per concurrent search). */

@@ -103,7 +103,7 @@ static std::atomic<int> g_opt_tc_boot_tiles{0};  // 0 = auto
 static std::atomic<int> g_opt_f32_tc{1};         // fp32 indexes: 3xTF32 tensor-core scan (0: SIMT scan)
 static std::atomic<int> g_opt_pq_scan{0};  // 0 auto, 1 exhaustive fp32 kernel, 2 coarse (1 query / pass), 3 coarse (4 / pass), 4 decode + tensor-core scan
 static std::atomic<int> g_opt_pq_gemm{1};   // auto policy may use the decode + tensor-core path for batches (0: never)
-static std::atomic<int> g_opt_exhaustive_k{411};  // single-query searches with k >= this take the exhaustive exact chain (0: only beyond the fused selector)
+static std::atomic<int> g_opt_exhaustive_k{256};  // single-query searches with k >= this take the exhaustive exact chain (0: only beyond the fused selector)
 static std::atomic<int> g_opt_certify{1};        // host searches: certify the coarse stage, redo flagged queries exactly
 static std::atomic<int> g_opt_tc_boot{1};     // bootstrap threshold scan on/off (A/B timing)    // timing probes of the tensor-core scan (results invalid when != 0)  // 0 auto, 1 force SIMT, 2 force tensor-core (error if ineligible)
 
@@ -700,11 +700,12 @@ static int coarse_k(int k) {
     return ((kc + 31) / 32) * 32;
 }
 
-// Which searches take the exhaustive exact chain (every row's exact distance, then select_k): k beyond the fused
-// selector's candidate capacity, and -- measured on the C2 database, tools/large_k_probe.py -- single-query calls
-// with k >= 411 (coarse list beyond 512 entries: the padded tensor-core block with the 1024-entry selector takes 3.3 ms
-// at k = 448 and 11.1 ms at k = 704 for one query over 1 M x 768 fp16, the exhaustive chain 1.8 and 2.7 ms; below that
-// the ordinary paths win: 0.72 against 1.5 ms at k = 352).  Both plans return the same (distance, id) lists.
+// Which searches take the exhaustive exact chain (every row's exact distance, then the two-level select_k): k beyond
+// the fused selector's candidate capacity, and single-query calls with k >= 256.  Measured on the C2 database
+// (1 M x 768 fp16, tools/large_k_probe.py, profiles/r2_large_k_probe.txt): one query through the padded tensor-core
+// block costs 0.65 / 0.69 / 3.3 / 11.1 ms at k = 288 / 352 / 448 / 704 (the 1024-entry selector from a 512-entry coarse
+// list up), the exhaustive chain 0.59 / 0.62 / 0.66 / 0.79 ms; below k = 224 the streaming scan wins (0.34 against
+// 0.57 ms at k = 160).  Both plans return the same (distance, id) lists.
 static bool exhaustive_plan(int64_t nq, int k) {
     if (coarse_k(k) > 896) return true;
     const int xk = g_opt_exhaustive_k.load(std::memory_order_relaxed);
@@ -956,12 +957,10 @@ static int exact_search_one(lb_index* idx, const void* d_q1, int k, const uint64
     Scratch scr(st);
     const int64_t n = idx->size;
     if (k > 2048) return fail(LB_ERR_UNSUPPORTED, "k > 2048");
-    int chunks = (int)((n + 4095) / 4096);
-    if (chunks < 1) chunks = 1;
     float* d_o;
     uint64_t *p, *m;
     CK(scr.get((void**)&d_o, (size_t)n * 4));
-    CK(scr.get((void**)&p, (size_t)chunks * k * 8));
+    CK(scr.get((void**)&p, select_k_scratch_entries(n, k) * 8));
     CK(scr.get((void**)&m, (size_t)k * 8));
     CK(launch_batch_flat(idx->metric, idx->dtype, idx->rows, n, idx->dim, d_q1, d_o, 1, st));
     CK(launch_mask_rows(d_o, n, idx->tomb, (uint32_t)(idx->tomb_bits > 0xffffffffll ? 0xffffffffll : idx->tomb_bits),
@@ -1310,13 +1309,11 @@ int lb_select_k(int device, const float* distances, int64_t n, int k, int64_t* o
     if (rc) return rc;
     cudaStream_t st = cudaStreamPerThread;
     Scratch scr(st);
-    int chunks = (int)((n + 4095) / 4096);
-    if (chunks < 1) chunks = 1;
     float *d_d, *d_od; int64_t* d_oi; uint64_t *p, *m;
     CK(scr.get((void**)&d_d, (size_t)n * 4));
     CK(scr.get((void**)&d_od, (size_t)k * 4));
     CK(scr.get((void**)&d_oi, (size_t)k * 8));
-    CK(scr.get((void**)&p, (size_t)chunks * k * 8));
+    CK(scr.get((void**)&p, select_k_scratch_entries(n, k) * 8));
     CK(scr.get((void**)&m, (size_t)k * 8));
     if (n > 0) CK(cudaMemcpyAsync(d_d, distances, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CK(launch_select_k(d_d, n, k, p, m, d_oi, d_od, 0, st));

@@ -141,6 +141,7 @@ cudaError_t launch_row_norm_exact(int dtype, const void* db, int64_t n, int dim,
 cudaError_t launch_rescore(const RescoreArgs& a, cudaStream_t st);
 cudaError_t launch_batch_flat(int metric, int dtype, const void* db, int64_t n, int dim, const void* query,
                               float* out, int negate_dot, cudaStream_t st);
+size_t select_k_scratch_entries(int64_t n, int k);  // 8-byte entries launch_select_k needs in scratch_partial
 cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_partial, uint64_t* scratch_merged,
                             int64_t* out_idx, float* out_d, int64_t id_base, cudaStream_t st);
 cudaError_t launch_merge_topk_strided(const void* in_d_base, size_t stride_d, const void* in_l_base, size_t stride_l,

@@ -1079,15 +1079,43 @@ __global__ void unpack_topk_kernel(const uint64_t* __restrict__ merged, int nq, 
     out_l[i] = valid ? (int64_t)id_of(p) + id_base : -1;
 }
 
+// Chunks of 4096 distances are sorted by one block each (the k best kept), then merged in two levels: `groups` blocks
+// merge `per` chunk lists each, one block merges the group lists.  (One block streaming every chunk list through its
+// buffer took chunks * k / (4096 - k) sorts in sequence -- 245 x 2048 entries, 10.9 ms, for k = 2048 over 1 M rows.)
+static void select_k_plan(int64_t n, int* groups, int* per) {
+    int chunks = (int)((n + MERGE_BUF - 1) / MERGE_BUF);
+    if (chunks < 1) chunks = 1;
+    if (chunks <= 8) { *groups = 1; *per = chunks; return; }
+    int g = 1;
+    while (g * g < chunks) g++;
+    *groups = g;
+    *per = (chunks + g - 1) / g;
+}
+
+size_t select_k_scratch_entries(int64_t n, int k) {
+    int groups, per;
+    select_k_plan(n, &groups, &per);
+    return ((size_t)groups * per + (groups > 1 ? groups : 0)) * (size_t)k;
+}
+
 cudaError_t launch_select_k(const float* d, int64_t n, int k, uint64_t* scratch_partial, uint64_t* scratch_merged,
                             int64_t* out_idx, float* out_d, int64_t id_base, cudaStream_t st) {
     if (k > MERGE_BUF / 2) return cudaErrorInvalidValue;  // the streaming merge keeps k entries and needs room to refill
     int kc = k;
-    int chunks = (int)((n + MERGE_BUF - 1) / MERGE_BUF);
-    if (chunks == 0) chunks = 1;
-    select_k_chunks_kernel<<<chunks, 256, 0, st>>>(d, n, kc, scratch_partial);
+    int groups, per;
+    select_k_plan(n, &groups, &per);
+    // groups * per >= chunks: the blocks past the data emit empty (all-invalid) lists, so every group has `per` lists
+    select_k_chunks_kernel<<<groups * per, 256, 0, st>>>(d, n, kc, scratch_partial);
     count_launch();
-    merge_partials_kernel<<<1, 256, 0, st>>>(scratch_partial, chunks, 1, kc, scratch_merged);
+    if (groups > 1) {
+        uint64_t* level1 = scratch_partial + (size_t)groups * per * kc;
+        // group q merges chunk lists q, q + groups, q + 2 groups, ... (the [part][query][kc] layout of the kernel)
+        merge_partials_kernel<<<groups, 256, 0, st>>>(scratch_partial, per, groups, kc, level1);
+        count_launch();
+        merge_partials_kernel<<<1, 256, 0, st>>>(level1, groups, 1, kc, scratch_merged);
+    } else {
+        merge_partials_kernel<<<1, 256, 0, st>>>(scratch_partial, per, 1, kc, scratch_merged);
+    }
     count_launch();
     unpack_topk_kernel<<<(k + 127) / 128, 128, 0, st>>>(scratch_merged, 1, kc, k, id_base, out_d, out_idx);
     count_launch();

@@ -629,11 +629,11 @@ def test_large_k_exact_path(lbgpu, oracle, dtype, metric):
 
 
 def test_single_query_large_k_plans_agree(lbgpu, oracle):
-    """One query with k >= 411 takes the exhaustive exact chain by default (measured cheaper than the padded
+    """One query with k >= 256 takes the exhaustive exact chain by default (measured cheaper than the padded
     tensor-core block); lb_set_option("exhaustive_k", ...) moves the switch.  Both plans give the oracle's answer."""
     from longbow_b200 import _lib
     rng = np.random.default_rng(77)
-    n, dim, k = 30011, 128, 500
+    n, dim, k = 60013, 128, 500   # 15 chunks of 4096 rows: the two-level select with one empty chunk list
     db, q = make_db(rng, n, dim, np.float16), make_db(rng, 2, dim, np.float16)
     idx = lbgpu.DenseIndex(dim, np.float16, COS)
     idx.add(db)
@@ -641,7 +641,7 @@ def test_single_query_large_k_plans_agree(lbgpu, oracle):
     wd, wl = oracle.search(COS, db, q, k, allow=lbgpu.pack_bitmap(allow))
     counts = []
     try:
-        for xk in (411, 100000, 1):
+        for xk in (256, 100000, 1):
             _lib.set_option("exhaustive_k", xk)
             l0 = _lib.launch_count()
             gd, gl = idx.search(q[:1], k, allow=allow)
@@ -650,7 +650,7 @@ def test_single_query_large_k_plans_agree(lbgpu, oracle):
             gd, gl = idx.search(q, k, allow=allow)      # two queries: always the ordinary plan
             assert_topk_equal(gd, gl, wd, wl, 0.0, f"two queries, exhaustive_k={xk}")
     finally:
-        _lib.set_option("exhaustive_k", 411)
+        _lib.set_option("exhaustive_k", 256)
     assert counts[0] == counts[2], counts   # the default plan is the forced exhaustive chain's kernel sequence
     idx.close()
 
