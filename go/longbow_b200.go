@@ -303,9 +303,10 @@ func DenseWords(ids []uint32, nbits int64) []uint64 {
 // ShardedB200Index: rows split over several GPUs of this process (lb_shard_*), the drop-in for ShardedHNSW's
 // fan-out + merge (internal/store/sharded_hnsw.go:378-503).  Labels are global row positions.
 type ShardedB200Index struct {
-	h   *C.lb_shard
-	dim int
-	mu  sync.RWMutex
+	h     *C.lb_shard
+	dim   int
+	dtype DType
+	mu    sync.RWMutex
 }
 
 func NewShardedB200Index(devices []int, dim int, dt DType, m Metric, totalRows int64) (*ShardedB200Index, error) {
@@ -322,12 +323,18 @@ func NewShardedB200Index(devices []int, dim int, dt DType, m Metric, totalRows i
 	}); err != nil {
 		return nil, err
 	}
-	return &ShardedB200Index{h: h, dim: dim}, nil
+	return &ShardedB200Index{h: h, dim: dim, dtype: dt}, nil
 }
 
 func (s *ShardedB200Index) Add(vectors []float32) error {
 	s.mu.Lock()
 	defer s.mu.Unlock()
+	if s.h == nil {
+		return fmt.Errorf("index is closed")
+	}
+	if s.dtype != Float32 {
+		return fmt.Errorf("Add([]float32) on a non-fp32 shard set; use AddRaw")
+	}
 	if len(vectors) == 0 {
 		return nil
 	}
@@ -339,11 +346,58 @@ func (s *ShardedB200Index) Add(vectors []float32) error {
 	})
 }
 
+// AddRaw appends rows of the set's own element type (fp16 / int8 / fp32) from their little-endian bytes, e.g. the
+// values buffer of an Arrow FixedSizeList column.
+func (s *ShardedB200Index) AddRaw(rows []byte) error {
+	s.mu.Lock()
+	defer s.mu.Unlock()
+	if s.h == nil {
+		return fmt.Errorf("index is closed")
+	}
+	rb := s.dim * s.dtype.size()
+	if len(rows) == 0 {
+		return nil
+	}
+	if len(rows)%rb != 0 {
+		return fmt.Errorf("row data length %d not divisible by the row size %d", len(rows), rb)
+	}
+	return call("GPU shard add", func() C.int {
+		return C.lb_shard_add(s.h, unsafe.Pointer(&rows[0]), C.int64_t(len(rows)/rb))
+	})
+}
+
 func (s *ShardedB200Index) SearchBatch(queries []float32, nq, k int) ([]int64, []float32, error) {
 	s.mu.RLock()
 	defer s.mu.RUnlock()
+	if s.h == nil {
+		return nil, nil, fmt.Errorf("index is closed")
+	}
+	if s.dtype != Float32 {
+		return nil, nil, fmt.Errorf("SearchBatch([]float32) on a non-fp32 shard set; use SearchBatchRaw")
+	}
 	if nq <= 0 || k <= 0 || len(queries) != nq*s.dim {
 		return nil, nil, fmt.Errorf("bad query batch: %d values for %d queries of dimension %d, k=%d", len(queries), nq, s.dim, k)
+	}
+	distances := make([]float32, nq*k)
+	labels := make([]int64, nq*k)
+	if err := call("GPU shard search", func() C.int {
+		return C.lb_shard_search(s.h, unsafe.Pointer(&queries[0]), C.int64_t(nq), C.int(k), nil,
+			(*C.float)(unsafe.Pointer(&distances[0])), (*C.int64_t)(unsafe.Pointer(&labels[0])))
+	}); err != nil {
+		return nil, nil, err
+	}
+	return labels, distances, nil
+}
+
+// SearchBatchRaw: nq queries of the set's own element type as bytes (fp16 / int8 sets).
+func (s *ShardedB200Index) SearchBatchRaw(queries []byte, nq, k int) ([]int64, []float32, error) {
+	s.mu.RLock()
+	defer s.mu.RUnlock()
+	if s.h == nil {
+		return nil, nil, fmt.Errorf("index is closed")
+	}
+	if nq <= 0 || k <= 0 || len(queries) != nq*s.dim*s.dtype.size() {
+		return nil, nil, fmt.Errorf("bad query batch: %d bytes for %d queries of dimension %d, k=%d", len(queries), nq, s.dim, k)
 	}
 	distances := make([]float32, nq*k)
 	labels := make([]int64, nq*k)
