@@ -12,6 +12,10 @@ ABI mirrors) must pass it as well.  They widen the oracle's pin beyond tests/gol
 * internal/simd/simd_compare_test.go:7-72, branchless_test.go:55-82        MatchInt64 / MatchFloat32 truth tables
 * internal/simd/sq8_extra_test.go:9-46             QuantizeSQ8 {0,127,255,0,255}, ComputeBounds table
 
+* internal/store/result_merger_test.go:10-119      MergeSortedStreams: three streams, empty channel, limit k, interleaved
+* internal/store/adaptive_index_test.go:105-165,280-306   BruteForceIndex on createTestDatasetWithVectors: k = 10 of 100
+                                                   ascending (closed-form answer), k > size, empty index
+
 The scalar loops restated here (seq_*) are the reference's generic functions (internal/simd/simd.go:131-163) in
 float32 arithmetic, the yardstick its tests use.
 """
@@ -286,3 +290,80 @@ def test_gpu_sq8_reference_kats():
     assert dst.tolist() == want
     for vec, mn, mx in BOUNDS:
         assert simd.ComputeBounds(np.array(vec, f32)) == (mn, mx)
+
+
+# ------------------------------------------------------------------ shard merge + brute-force index reference cases
+# internal/store/result_merger_test.go:10-119: sorted per-stream results merged by score.  Streams as padded
+# [parts, 1, k_in] lists with label -1 / MaxFloat32 padding, the layout of the per-shard top lists.
+MAXF = float(np.finfo(np.float32).max)
+MERGE_CASES = [
+    # (name, streams [(id, score), ...], k, expected ids)
+    ("three_streams", [[(1, 0.1), (2, 0.4), (3, 0.7)], [(4, 0.2), (5, 0.5)], [(6, 0.3), (7, 0.6), (8, 0.9)]], 10,
+     [1, 4, 6, 2, 5, 7, 3, 8]),
+    ("empty_channel", [[], [(1, 0.5)]], 5, [1]),
+    ("limit_k", [[(1, 0.1), (2, 0.2), (3, 0.3)]], 2, [1, 2]),
+    ("interleaved", [[(1, 0.1), (2, 0.9)], [(3, 0.2), (4, 0.5)]], 10, [1, 3, 4, 2]),
+]
+
+
+def _merge_inputs(streams):
+    k_in = max(1, max(len(s) for s in streams))
+    d = np.full((len(streams), 1, k_in), MAXF, f32)
+    l = np.full((len(streams), 1, k_in), -1, np.int64)
+    for p, s in enumerate(streams):
+        for j, (i, sc) in enumerate(s):
+            d[p, 0, j], l[p, 0, j] = f32(sc), i
+    return d, l
+
+
+def _check_merge(od, ol, streams, k, want_ids):
+    score = {i: f32(sc) for s in streams for i, sc in s}
+    got = [int(x) for x in ol[0] if x >= 0]
+    assert got == want_ids[:k]
+    assert [f32(x) for x in od[0][:len(got)]] == [score[i] for i in got]      # scores travel unchanged
+    assert all(int(x) == -1 for x in ol[0][len(got):])
+
+
+@pytest.mark.parametrize("case", MERGE_CASES, ids=[c[0] for c in MERGE_CASES])
+def test_oracle_merge_sorted_streams(oracle, case):
+    _name, streams, k, want = case
+    d, l = _merge_inputs(streams)
+    od, ol = oracle.merge(d, l, k)
+    _check_merge(od, ol, streams, k, want)
+
+
+def bf_dataset(n):   # createTestDatasetWithVectors, internal/store/adaptive_index_test.go:280-306: float32(i*4+d) * 0.01
+    return np.array([[f32(f32(i * 4 + d) * f32(0.01)) for d in range(4)] for i in range(n)], f32).reshape(n, 4)
+
+
+# the distance to query (0.1, 0.2, 0.3, 0.4) is a parabola in the row number with its vertex at 5.875: no ties
+BF_WANT = [6, 5, 7, 4, 8, 3, 9, 2, 10, 1]
+
+
+def test_oracle_brute_force_reference_cases(oracle):
+    """adaptive_index_test.go:105-152: k = 10 over 100 rows comes back ascending; k = 100 over 5 rows gives 5 results."""
+    q = np.array([[0.1, 0.2, 0.3, 0.4]], f32)
+    d, l = oracle.search(L2, bf_dataset(100), q, 10)
+    assert l[0].tolist() == BF_WANT and np.all(np.diff(d[0]) >= 0)
+    d, l = oracle.search(L2, bf_dataset(5), np.array([[1.0, 0.0, 0.0, 0.0]], f32), 100)
+    assert sorted(int(x) for x in l[0] if x >= 0) == [0, 1, 2, 3, 4] and int((l[0] >= 0).sum()) == 5
+
+
+@pytest.mark.gpu
+def test_gpu_merge_and_brute_force_reference_cases():
+    from longbow_b200 import store
+    for _name, streams, k, want in MERGE_CASES:
+        d, l = _merge_inputs(streams)
+        od, ol = store.MergeShardResults(d, l, k)
+        _check_merge(od, ol, streams, k, want)
+    bf = store.BruteForceIndex(4)
+    assert bf.Len() == 0 and not bf.SearchVectors(np.array([1.0, 2.0, 3.0, 4.0], f32), 10)   # :154-165 empty index
+    bf.AddBatch(bf_dataset(100))
+    res = bf.SearchVectors(np.array([0.1, 0.2, 0.3, 0.4], f32), 10)
+    assert [r.ID for r in res] == BF_WANT and all(a.Score <= b.Score for a, b in zip(res, res[1:]))
+    bf.Close()
+    bf = store.BruteForceIndex(4)
+    bf.AddBatch(bf_dataset(5))
+    res = bf.SearchVectors(np.array([1.0, 0.0, 0.0, 0.0], f32), 100)                        # :133-152 k > index size
+    assert len(res) == 5 and sorted(r.ID for r in res) == [0, 1, 2, 3, 4]
+    bf.Close()
