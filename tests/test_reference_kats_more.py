@@ -264,8 +264,8 @@ def test_gpu_batch_cases():
         fn[metric](q, rows, res)
         for i, v in enumerate(rows):
             assert abs(float(res[i]) - float(SEQ[metric](q, v))) <= tol, (metric, i, res[i])
-    # coverage_increase_test.go:154-176: a results slot beyond len(vectors) is not touched (the non-strict F16 batch
-    # form; the fp32 batch forms require equal lengths, batch_operations.go:30-32)
+    # coverage_increase_test.go:154-176: a results slot beyond len(vectors) is not touched (shown on a non-strict
+    # batch form; EuclideanDistanceBatch itself requires equal lengths, batch_operations.go:30-32)
     res = np.array([999.0, 888.0], f32)
     simd.DotProductF16Batch(np.array([1, 2, 3], np.float16), [np.array([1, 2, 3], np.float16)], res)
     assert res[0] == 14.0 and res[1] == 888.0
@@ -367,3 +367,54 @@ def test_gpu_merge_and_brute_force_reference_cases():
     res = bf.SearchVectors(np.array([1.0, 0.0, 0.0, 0.0], f32), 100)                        # :133-152 k > index size
     assert len(res) == 5 and sorted(r.ID for r in res) == [0, 1, 2, 3, 4]
     bf.Close()
+
+
+# ------------------------------------------------------------------ a few more literals + the mirrors' error behaviour
+MORE_LITERALS = [
+    # internal/simd/jit_test.go:26-43: q = {1,1,1} against three rows: 0, 1.73205, 13 (+- 1e-4)
+    ("jit_batch_0", L2, [1, 1, 1], [1, 1, 1], 0.0, 1e-4), ("jit_batch_sqrt3", L2, [1, 1, 1], [2, 2, 2], 1.73205, 1e-4),
+    ("jit_batch_13", L2, [1, 1, 1], [4, 5, 13], 13.0, 1e-4),
+    # internal/simd/jit_test.go:10-24 / docs: sqrt(27)
+    ("jit_sqrt27", L2, [1, 2, 3], [4, 5, 6], float(f32(math.sqrt(27))), 1e-4),
+    # internal/simd/simd_fma_portable_test.go:57-70,166-179: dot 70, orthogonal cosine 1.0 (+- 1e-5)
+    ("fma_dot_70", DOT, [1, 2, 3, 4], [5, 6, 7, 8], 70.0, 1e-5), ("fma_cos_orthogonal", COS, [1, 0, 0], [0, 1, 0], 1.0, 1e-5),
+]
+
+
+@pytest.mark.parametrize("case", MORE_LITERALS, ids=[c[0] for c in MORE_LITERALS])
+def test_oracle_more_literals(oracle, case):
+    _name, metric, a, b, expected, tol = case
+    assert abs(float(oracle.raw(RAW[metric], np.array(a, f32), np.array(b, f32))) - expected) <= tol
+
+
+def test_mirror_argument_errors_need_no_gpu():
+    """The argument checks of the simd mirrors are host logic and match the reference's error behaviour: a length
+    mismatch is an error (simd_test.go:124-129,215-220; distance_functions.go:18-20), results / vectors mismatch is
+    an error for the Euclidean batch forms (batch_operations.go:18-20,30-32,92-94), a too small results slice for the
+    cosine / dot forms (:131-157), empty inputs return 0 / 1 / 0 without a kernel (distance_functions.go:21-23,51-53,63-65)."""
+    from longbow_b200 import simd
+    a, b = np.array([1, 2, 3], f32), np.array([1, 2], f32)
+    for fn in (simd.EuclideanDistance, simd.CosineDistance, simd.DotProduct, simd.EuclideanDistanceF16,
+               simd.CosineDistanceF16, simd.DotProductF16):
+        with pytest.raises(simd.SimdError, match="length mismatch"):
+            fn(a, b)
+    e = np.zeros(0, f32)
+    assert simd.EuclideanDistance(e, e) == 0.0 and simd.CosineDistance(e, e) == 1.0 and simd.DotProduct(e, e) == 0.0
+    rows = [np.array([1, 2, 3], f32)] * 2
+    for fn in (simd.EuclideanDistanceBatch, simd.EuclideanDistanceVerticalBatch):
+        with pytest.raises(simd.SimdError, match="vectors and results length mismatch"):
+            fn(a, rows, np.zeros(3, f32))
+        fn(a, [], np.zeros(0, f32))                      # nothing to do, no kernel
+    for fn in (simd.CosineDistanceBatch, simd.DotProductBatch):   # these two only need room (:131-157)
+        with pytest.raises(simd.SimdError, match="results slice too small"):
+            fn(a, rows, np.zeros(1, f32))
+        fn(a, [], np.zeros(0, f32))
+    with pytest.raises(simd.SimdError, match="results slice too small"):
+        simd.DotProductF16Batch(np.array([1, 2, 3], np.float16), [np.array([1, 2, 3], np.float16)] * 2, np.zeros(1, f32))
+    with pytest.raises(simd.SimdError, match="results length mismatch"):
+        simd.EuclideanDistanceBatchFlat(a, np.zeros(6, f32), 2, 3, np.zeros(3, f32))
+    with pytest.raises(simd.SimdError, match="flatVectors too small"):
+        simd.EuclideanDistanceBatchFlat(a, np.zeros(5, f32), 2, 3, np.zeros(2, f32))
+    with pytest.raises(simd.SimdError, match="query dimension mismatch"):
+        simd.EuclideanDistanceBatchFlat(b, np.zeros(6, f32), 2, 3, np.zeros(2, f32))
+    simd.EuclideanDistanceBatchFlat(a, np.zeros(0, f32), 0, 3, np.zeros(0, f32))   # numVectors == 0: no-op
