@@ -150,8 +150,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "C2: brute-force cosine k=100, 1M x 768 fp16, query batch 1024",
-                   "note": "CPU restatement of the reference's SIMD path (Go toolchain absent); each step is a bounded sample"},
+        # the same workload (and workload string) as the GPU arm; what differs is stated in `note` / `sample`
+        "config": {"workload": "C2: brute-force cosine k=100, 1M x 768 fp16 unit-norm embeddings, query batch 1024",
+                   "rows": N_ROWS, "dim": DIM, "queries_per_step": NQ, "k": K,
+                   "note": "CPU restatement of the reference's SIMD path (Go toolchain absent); each step is a bounded "
+                           f"sample of the batch ({nq} of its {NQ} queries against the full database)"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
