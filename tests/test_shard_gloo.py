@@ -73,3 +73,56 @@ def test_shard_range_partition():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _packed_worker(rank, world, port, ret):
+    """The exchange as ShardedIndex(exchange="nccl") really does it: ONE all-gather of the packed record
+    [nq*k f32 | pad to 16 | nq*k i64] per rank (shard.record_layout), parsed back with the record / label strides the
+    merge kernel is given (lb_merge_topk_packed_device)."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from longbow_b200.shard import record_layout, shard_range
+    from oracle import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        n, dim, nq, k = 4099, 32, 7, 9          # nq*k*4 = 252: the label block needs the 16-byte pad
+        db = rng.integers(-128, 128, (n, dim), dtype=np.int8)
+        db[5] = db[4000]                          # exact tie across shards
+        q = rng.integers(-128, 128, (nq, dim), dtype=np.int8)
+        lo, hi = shard_range(n, rank, world)
+        d, l = oracle.search(oracle.DOT, db[lo:hi], q, k, id_base=lo)
+        loff, rec = record_layout(nq, k)
+        assert loff % 16 == 0 and loff >= nq * k * 4 and rec == loff + nq * k * 8
+        local = torch.zeros(rec, dtype=torch.uint8)
+        local[:nq * k * 4] = torch.from_numpy(d.reshape(-1).view(np.uint8))
+        local[loff:] = torch.from_numpy(l.reshape(-1).view(np.uint8))
+        gathered = torch.empty(world * rec, dtype=torch.uint8)
+        dist.all_gather_into_tensor(gathered, local)
+        g = gathered.numpy()
+        gd = np.stack([g[p * rec:p * rec + nq * k * 4].view(np.float32).reshape(nq, k) for p in range(world)])
+        gl = np.stack([g[p * rec + loff:p * rec + loff + nq * k * 8].view(np.int64).reshape(nq, k) for p in range(world)])
+        md, ml = oracle.merge(gd, gl, k)
+        wd, wl = oracle.search(oracle.DOT, db, q, k)
+        ret[rank] = bool(np.array_equal(ml, wl) and np.array_equal(md, wd))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_packed_record_exchange(world):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    ret = mgr.dict()
+    procs = [ctx.Process(target=_packed_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world))
