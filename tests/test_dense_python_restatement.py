@@ -100,3 +100,63 @@ def test_oracle_search_k_larger_than_live_rows(oracle):
     gd, gl = oracle.search(L2, db, q, 10)
     assert np.array_equal(gl, wl) and np.array_equal(gd[gl >= 0], wd[wl >= 0])
     assert (gl[:, 6:] == -1).all()
+
+
+# ------------------------------------------------------------------ re-rank, shard merge, select_k, SQ8
+def rerank_py(metric, db, q, cand, k, dead=None, allow=None):
+    """internal/store/hnsw_batch.go:206-245: candidates that resolve to a stored vector (here: in range, not
+    tombstoned, allowed) keep their exact distance; ascending by (distance, id); at most k."""
+    d_all = distances_py(metric, q, db)
+    keep = [int(c) for c in cand if 0 <= c < db.shape[0] and (dead is None or not dead[c]) and (allow is None or allow[c])]
+    keep.sort(key=lambda c: (d_all[c], c))
+    return [(c, d_all[c]) for c in keep[:k]]
+
+
+def test_oracle_rerank_merge_select_match_python_restatement(oracle):
+    from longbow_b200.gpu import pack_bitmap
+    rng = np.random.default_rng(9)
+    n, dim, nq, c, k = 500, 24, 6, 40, 10
+    db, q = _data(rng, n, dim, np.float32), _data(rng, nq, dim, np.float32)
+    db[3] = db[400]
+    cand = np.stack([rng.permutation(n + 30)[:c] for _ in range(nq)]).astype(np.int64)   # some ids past the index
+    cand[0, :2] = (3, 400)
+    dead, allow = rng.random(n) < 0.1, rng.random(n) < 0.8
+    for metric in (L2, COS, DOT):
+        gd, gl = oracle.rerank(metric, db, q, cand, k, tomb=pack_bitmap(dead), allow=pack_bitmap(allow))
+        for qi in range(nq):
+            want = rerank_py(metric, db, q[qi], cand[qi], k, dead, allow)
+            assert [int(x) for x in gl[qi][:len(want)]] == [w[0] for w in want], (metric, qi)
+            assert [f32(x) for x in gd[qi][:len(want)]] == [w[1] for w in want]
+            assert (gl[qi][len(want):] == -1).all()
+    # shard merge (internal/store/sharded_hnsw.go:494-503): the k smallest of the concatenation by (distance, label)
+    parts, k_in = 5, 8
+    d = np.sort(rng.random((parts, nq, k_in)).astype(f32), axis=2)
+    d[rng.random(d.shape) < 0.3] = f32(0.25)
+    d = np.sort(d, axis=2)
+    l = rng.permutation(parts * nq * k_in).reshape(parts, nq, k_in).astype(np.int64)
+    l[2, :, 5:] = -1
+    md, ml = oracle.merge(d, l, k)
+    for qi in range(nq):
+        pairs = sorted((float(d[p, qi, j]), int(l[p, qi, j])) for p in range(parts) for j in range(k_in) if l[p, qi, j] >= 0)
+        assert [(float(a), int(b)) for a, b in zip(md[qi], ml[qi])] == pairs[:k]
+    # select_k (internal/store/arrow_kernels.go:230-345): indices of the k smallest values, (value, index) order
+    x = rng.random(5000).astype(f32)
+    x[77] = x[4000]
+    sd, si = oracle.select_k(x, 25)
+    order = np.lexsort((np.arange(x.size), x))[:25]
+    assert np.array_equal(si, order) and np.array_equal(sd, x[order])
+
+
+def test_oracle_sq8_distance_matches_python_restatement(oracle):
+    """EuclideanSQ8Generic (internal/simd/sq8.go:45-66): exact int32 sum of squared byte differences; the batch form
+    reports float32(d) (simd.go:170-182)."""
+    rng = np.random.default_rng(10)
+    for dim in (0, 1, 7, 8, 9, 33, 127, 1024):
+        a = rng.integers(0, 256, dim, dtype=np.uint8)
+        rows = rng.integers(0, 256, (5, dim), dtype=np.uint8)
+        want = ((rows.astype(np.int64) - a.astype(np.int64)) ** 2).sum(axis=1)
+        assert want.max(initial=0) < 2 ** 31
+        if dim == 0:
+            continue
+        got = oracle.batch_flat(L2, a, rows)
+        assert np.array_equal(got, want.astype(np.int32).astype(f32)), dim
