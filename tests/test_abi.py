@@ -118,3 +118,57 @@ def test_header_is_plain_c():
         pytest.skip("gcc not available")
     hdr = os.path.join(ROOT, "include", "longbow_b200.h")
     subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+
+
+def _split_top(args: str):
+    out, depth, cur = [], 0, ""
+    for ch in args:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur)
+    return out
+
+
+def _call_args(src: str, start: int):
+    """Text between the parenthesis at src[start] and its match."""
+    depth = 0
+    for i in range(start, len(src)):
+        if src[i] == "(":
+            depth += 1
+        elif src[i] == ")":
+            depth -= 1
+            if depth == 0:
+                return src[start + 1:i]
+    raise AssertionError("unbalanced call")
+
+
+def test_go_shim_calls_match_the_header():
+    """The Go toolchain is absent here, so the cgo shim (go/*.go) cannot be compiled; this keeps it from drifting:
+    every C.<symbol>(...) call names a function the header declares and passes as many arguments as it takes."""
+    hdr = open(os.path.join(ROOT, "include", "longbow_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    nparams = {}
+    for m in re.finditer(r"\b((?:lb|faiss_gpu)_[a-z0-9_]+)\s*\(", hdr):
+        args = _call_args(hdr, m.end() - 1).strip()
+        nparams[m.group(1)] = 0 if args in ("", "void") else len(_split_top(args))
+    calls = 0
+    for fn in sorted(os.listdir(os.path.join(ROOT, "go"))):
+        if not fn.endswith(".go"):
+            continue
+        src = open(os.path.join(ROOT, "go", fn)).read()
+        src = re.sub(r"//[^\n]*", "", src)
+        for m in re.finditer(r"\bC\.((?:lb|faiss_gpu)_[a-z0-9_]+)\s*\(", src):
+            name = m.group(1)
+            assert name in nparams, f"{fn}: C.{name} is not declared in include/longbow_b200.h"
+            got = len(_split_top(_call_args(src, m.end() - 1)))
+            assert got == nparams[name], f"{fn}: C.{name} called with {got} arguments, the header takes {nparams[name]}"
+            calls += 1
+    assert calls >= 15
