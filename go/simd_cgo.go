@@ -23,12 +23,10 @@ func EuclideanDistanceBatchFlat(device int, query, flat []float32, n, dims int, 
 	if len(flat) < n*dims || len(results) < n || len(query) != dims {
 		return errors.New("simd: size mismatch")
 	}
-	rc := C.lb_simd_distance_batch_flat(C.int(device), C.int(MetricEuclidean), C.int(Float32),
-		unsafe.Pointer(&query[0]), unsafe.Pointer(&flat[0]), C.int64_t(n), C.int(dims), (*C.float)(unsafe.Pointer(&results[0])))
-	if rc != 0 {
-		return lastErr(rc)
-	}
-	return nil
+	return call("simd: batch distance", func() C.int {
+		return C.lb_simd_distance_batch_flat(C.int(device), C.int(MetricEuclidean), C.int(Float32),
+			unsafe.Pointer(&query[0]), unsafe.Pointer(&flat[0]), C.int64_t(n), C.int(dims), (*C.float)(unsafe.Pointer(&results[0])))
+	})
 }
 
 // ADCDistanceBatch mirrors simd.ADCDistanceBatch (internal/simd/batch_operations.go:119-127).
@@ -39,23 +37,28 @@ func ADCDistanceBatch(device int, table []float32, flatCodes []byte, m int, resu
 	if m <= 0 {
 		return errors.New("simd: invalid m parameter")
 	}
-	rc := C.lb_simd_adc_distance_batch(C.int(device), (*C.float)(unsafe.Pointer(&table[0])),
-		(*C.uint8_t)(unsafe.Pointer(&flatCodes[0])), C.int(m), C.int64_t(len(results)), (*C.float)(unsafe.Pointer(&results[0])))
-	if rc != 0 {
-		return lastErr(rc)
+	if len(results) == 0 || len(flatCodes) < len(results)*m {
+		return errors.New("simd: results / codes size mismatch")
 	}
-	return nil
+	return call("simd: ADC batch distance", func() C.int {
+		return C.lb_simd_adc_distance_batch(C.int(device), (*C.float)(unsafe.Pointer(&table[0])),
+			(*C.uint8_t)(unsafe.Pointer(&flatCodes[0])), C.int(m), C.int64_t(len(results)), (*C.float)(unsafe.Pointer(&results[0])))
+	})
 }
 
 // MergeTopK mirrors the tail of ShardedHNSW.SearchVectors (internal/store/sharded_hnsw.go:432-503):
 // [parts][nq][kIn] per-shard lists with global ids -> [nq][k] by (distance, id).
 func MergeTopK(device int, distances []float32, labels []int64, parts, nq, kIn, k int) ([]float32, []int64, error) {
+	if parts <= 0 || nq <= 0 || kIn <= 0 || k <= 0 || len(distances) != parts*nq*kIn || len(labels) != len(distances) {
+		return nil, nil, errors.New("merge: parts x nq x kIn does not match the list lengths")
+	}
 	od := make([]float32, nq*k)
 	ol := make([]int64, nq*k)
-	rc := C.lb_merge_topk(C.int(device), (*C.float)(unsafe.Pointer(&distances[0])), (*C.int64_t)(unsafe.Pointer(&labels[0])),
-		C.int(parts), C.int64_t(nq), C.int(kIn), C.int(k), (*C.float)(unsafe.Pointer(&od[0])), (*C.int64_t)(unsafe.Pointer(&ol[0])))
-	if rc != 0 {
-		return nil, nil, lastErr(rc)
+	if err := call("GPU merge", func() C.int {
+		return C.lb_merge_topk(C.int(device), (*C.float)(unsafe.Pointer(&distances[0])), (*C.int64_t)(unsafe.Pointer(&labels[0])),
+			C.int(parts), C.int64_t(nq), C.int(kIn), C.int(k), (*C.float)(unsafe.Pointer(&od[0])), (*C.int64_t)(unsafe.Pointer(&ol[0])))
+	}); err != nil {
+		return nil, nil, err
 	}
 	return od, ol, nil
 }

@@ -172,3 +172,31 @@ def test_go_shim_calls_match_the_header():
             assert got == nparams[name], f"{fn}: C.{name} called with {got} arguments, the header takes {nparams[name]}"
             calls += 1
     assert calls >= 15
+
+
+def test_go_shim_calls_only_defined_functions():
+    """A crude stand-in for `go vet`: every bare function call in go/*.go is a Go builtin / conversion or a function
+    defined somewhere in the package (catches helpers that were renamed away, e.g. lastErr)."""
+    builtins = {"len", "cap", "make", "append", "copy", "new", "panic", "delete", "min", "max", "func", "if", "for", "switch",
+                "return", "import", "var", "const", "type", "defer", "go", "range", "select", "case", "else", "int", "int32", "int64", "uint32", "uint64", "float32", "float64", "byte", "string", "bool"}
+    srcs = {}
+    for fn in sorted(os.listdir(os.path.join(ROOT, "go"))):
+        if fn.endswith(".go"):
+            src = open(os.path.join(ROOT, "go", fn)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)       # the cgo preamble
+            src = re.sub(r"//[^\n]*", "", src)
+            srcs[fn] = re.sub(r'"(?:[^"\\\n]|\\.)*"', '""', src)   # string literals
+    defined = set()
+    for src in srcs.values():
+        defined |= set(re.findall(r"\bfunc\s+(?:\([^)]*\)\s*)?([A-Za-z_][A-Za-z0-9_]*)\s*\(", src))
+        defined |= set(re.findall(r"\btype\s+([A-Za-z_][A-Za-z0-9_]*)\b", src))
+        defined |= set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s+func\(", src))         # function-typed parameters
+        defined |= set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*:=\s*func\(", src))    # local closures
+    defined |= {"GPUConfig", "Index"}   # declared by the package this file joins (internal/gpu/interface.go:10-19,21-30)
+    for fn, src in srcs.items():
+        for m in re.finditer(r"(?<![.\w])([A-Za-z_][A-Za-z0-9_]*)\s*\(", src):
+            name = m.group(1)
+            if name in builtins or name in defined:
+                continue
+            line = src[:m.start()].count("\n") + 1
+            raise AssertionError(f"go/{fn}:{line}: call of undefined function {name}()")
