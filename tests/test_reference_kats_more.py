@@ -418,3 +418,48 @@ def test_mirror_argument_errors_need_no_gpu():
     with pytest.raises(simd.SimdError, match="query dimension mismatch"):
         simd.EuclideanDistanceBatchFlat(b, np.zeros(6, f32), 2, 3, np.zeros(2, f32))
     simd.EuclideanDistanceBatchFlat(a, np.zeros(0, f32), 0, 3, np.zeros(0, f32))   # numVectors == 0: no-op
+
+
+# ------------------------------------------------------------------ conjunctions of predicates (FilterEvaluator)
+# internal/query/filter_evaluator_test.go:70-193: record batches of int64 / float32 columns, filters AND-combined,
+# expected row indices as literals.  Operators as the parser maps them onto simd.CompareOp.
+FE_OPS = {"=": EQ, "!=": NEQ, ">": GT, ">=": GE, "<": LT, "<=": LE}
+FE_BATCH8 = {"id": np.arange(1, 9, dtype=np.int64), "category": np.array([1, 1, 2, 2, 1, 1, 2, 2], np.int64)}
+FE_BATCH10 = {"id": np.arange(1, 11, dtype=np.int64), "category": np.array([1, 1, 2, 2, 1, 1, 2, 2, 1, 1], np.int64),
+              "value": np.arange(1, 11).astype(f32)}
+FE_CASES = [
+    (FE_BATCH8, [("id", ">=", 3), ("category", "=", 1)], [4, 5]),                                  # :70-106
+    (FE_BATCH10, [("id", ">=", 5)], [4, 5, 6, 7, 8, 9]),                                           # :124-134
+    (FE_BATCH10, [("id", ">=", 3), ("category", "=", 1)], [4, 5, 8, 9]),                           # :136-147
+    (FE_BATCH10, [("id", ">=", 3), ("category", "=", 1), ("value", "<=", 6.0)], [4, 5]),           # :149-161
+    (FE_BATCH10, [], list(range(10))),                                                             # :174-181 no filters
+    (FE_BATCH10, [("id", ">", 100)], []),                                                          # :183-192
+]
+
+
+def _numpy_filter(column, op, value, bitmap=None):
+    """Same contract as longbow_b200.store.GenerateFilterBitset, on the CPU (validates the test body without a GPU)."""
+    col = np.asarray(column)
+    hit = {EQ: col == value, NEQ: col != value, GT: col > value, GE: col >= value, LT: col < value, LE: col <= value}[op]
+    words = np.packbits(np.pad(hit, (0, (-col.size) % 64)), bitorder="little").view(np.uint64).copy()
+    return words if bitmap is None else (words & np.asarray(bitmap, np.uint64))
+
+
+def _run_filter_cases(filter_fn):
+    for batch, filters, want in FE_CASES:
+        n = len(next(iter(batch.values())))
+        bm = None
+        for field, op, value in filters:
+            bm = filter_fn(batch[field], FE_OPS[op], value, bm)
+        rows = list(range(n)) if bm is None else [i for i in range(n) if (int(bm[i // 64]) >> (i % 64)) & 1]
+        assert rows == want, (filters, rows)
+
+
+def test_filter_evaluator_cases_restated():
+    _run_filter_cases(_numpy_filter)
+
+
+@pytest.mark.gpu
+def test_gpu_filter_evaluator_cases():
+    from longbow_b200 import store
+    _run_filter_cases(lambda col, op, value, bm: store.GenerateFilterBitset(col, op, value, bitmap=bm))
