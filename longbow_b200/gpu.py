@@ -147,6 +147,17 @@ def pack_bitmap(mask: np.ndarray, n: int | None = None) -> np.ndarray:
     return np.packbits(padded, bitorder="little").view(np.uint64).copy()
 
 
+def dense_words(ids, nbits: int) -> np.ndarray:
+    """A predicate set given as VectorIDs -- what the reference's roaring Bitset hands out through ToUint32Array
+    (internal/query/bitmap.go:95-100) -- as the dense little-endian words the C ABI consumes; ids >= nbits are
+    dropped.  Same contract as gpu.DenseWords in go/longbow_b200.go."""
+    ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+    ids = ids[(ids >= 0) & (ids < nbits)]
+    mask = np.zeros(int(nbits), dtype=bool)
+    mask[ids] = True
+    return pack_bitmap(mask, int(nbits))
+
+
 class DenseIndex:
     """Extended dense handle: one Arrow FixedSizeList<T, dim> column mirrored in HBM."""
 

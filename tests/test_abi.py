@@ -83,6 +83,17 @@ def test_pack_bitmap_layout():
     assert w[0] == (1 | (1 << 63)) and w[1] == 1 and w[2] == 2
 
 
+def test_dense_words_from_id_sets():
+    """The roaring -> dense conversion (internal/query/bitmap.go:95-100 feeding the allow / tombstone bitmaps)."""
+    from longbow_b200.gpu import dense_words, pack_bitmap
+    w = dense_words([0, 63, 64, 129, 129, 500], 130)          # a duplicate and an id past the index
+    assert w.dtype == np.uint64 and w.tolist() == [1 | (1 << 63), 1, 2]
+    assert dense_words([], 65).tolist() == [0, 0]
+    rng = np.random.default_rng(0)
+    mask = rng.random(1000) < 0.3
+    assert np.array_equal(dense_words(np.flatnonzero(mask).astype(np.uint32), 1000), pack_bitmap(mask))
+
+
 def test_pq_blob_roundtrip_host():
     # internal/pq/persistence.go:15-80 format; parsing errors surface before any device work
     import struct
